@@ -1,0 +1,17 @@
+"""solid_dsp_b200 -- B200 (sm_100a) implementation of juliantos/solid-dsp's filtering hot path.
+
+Layout mirrors the reference crate's modules for that path only:
+    solid_dsp_b200.filter.fir   FIRFilter, DecimatingFIRFilter, InterpolatingFIRFilter, PolyPhaseFilterBank
+    solid_dsp_b200.filter.iir   IIRFilter, SecondOrderFilter, DecimatingIIRFilter, InterpolatingIIRFilter
+    solid_dsp_b200.dot_product  DotProduct, Direction
+    solid_dsp_b200.window       Window           (host-side history type, window/mod.rs)
+    solid_dsp_b200.circular_buffer CircularBuffer (host-side ring FIFO, circular_buffer/mod.rs)
+    solid_dsp_b200.filter.firdes / iirdes  host f64 design helpers that feed the filters their taps
+
+All execute paths call the CUDA library through the C ABI in include/solid_gpu.h; importing this
+package fails loudly when libsolid_gpu.so is absent (no CPU fallback).
+"""
+from . import _ffi  # noqa: F401  (loads libsolid_gpu.so or raises)
+from ._ffi import SolidGpuError, device_info, launch_count  # noqa: F401
+
+__all__ = ["SolidGpuError", "device_info", "launch_count"]

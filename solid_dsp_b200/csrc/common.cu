@@ -1,0 +1,143 @@
+// Library-level entry points: errors, device probe, launch counter, sharding arithmetic.
+#include "sgpu_common.cuh"
+
+namespace sgpu {
+
+std::atomic<uint64_t> g_launches{0};
+
+char *err_buf() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+int fail(int status, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int require_device(int *device_out, int *sm_count_out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SGPU_ERR_NO_DEVICE, "no CUDA device (%s); libsolid_gpu has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = 0;
+    SGPU_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    SGPU_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major < 10)
+        return fail(SGPU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    dev, p.major, p.minor);
+    if (device_out) *device_out = dev;
+    if (sm_count_out) *sm_count_out = p.multiProcessorCount;
+    return SGPU_OK;
+}
+
+int Staging::ensure(size_t need_in, size_t need_out) {
+    if (need_in > in_bytes) {
+        if (in) cudaFree(in);
+        in = nullptr;
+        in_bytes = 0;
+        SGPU_CUDA(cudaMalloc(&in, need_in));
+        in_bytes = need_in;
+    }
+    if (need_out > out_bytes) {
+        if (out) cudaFree(out);
+        out = nullptr;
+        out_bytes = 0;
+        SGPU_CUDA(cudaMalloc(&out, need_out));
+        out_bytes = need_out;
+    }
+    return SGPU_OK;
+}
+
+void Staging::release() {
+    if (in) cudaFree(in);
+    if (out) cudaFree(out);
+    in = out = nullptr;
+    in_bytes = out_bytes = 0;
+}
+
+}  // namespace sgpu
+
+SGPU_EXPORT int sgpu_abi_version(void) { return SGPU_ABI_VERSION; }
+
+SGPU_EXPORT const char *sgpu_last_error(void) { return sgpu::err_buf(); }
+
+SGPU_EXPORT const char *sgpu_status_name(int s) {
+    switch (s) {
+        case SGPU_OK: return "SGPU_OK";
+        case SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO: return "FIRErrorCode::CoefficientsLengthZero";
+        case SGPU_ERR_FIR_DECIMATION_LESS_THAN_ONE: return "FIRErrorCode::DecimationLessThanOne";
+        case SGPU_ERR_FIR_INTERPOLATION_LESS_THAN_ONE: return "FIRErrorCode::InterpolationLessThanOne";
+        case SGPU_ERR_FIR_NOT_ENOUGH_FILTERS: return "FIRErrorCode::NotEnoughFilters";
+        case SGPU_ERR_IIR_NUMERATOR_LENGTH_ZERO: return "IIRErrorCode::NumeratorLengthZero";
+        case SGPU_ERR_IIR_DENOMINATOR_LENGTH_ZERO: return "IIRErrorCode::DenominatorLengthZero";
+        case SGPU_ERR_IIR_SOS_SIZE_ZERO: return "IIRErrorCode::SecondOrderSectionSizeZero";
+        case SGPU_ERR_IIR_SOS_SIZE_MISMATCH: return "IIRErrorCode::SecondOrderSectionSizeMismatch";
+        case SGPU_ERR_IIR_SOS_SIZE_NOT_MULTIPLE_OF_3: return "IIRErrorCode::SecondOrderSectionSizeNotMultpleOf3";
+        case SGPU_ERR_IIR_DECIMATION_LESS_THAN_ONE: return "IIRErrorCode::DecimationLessThanOne";
+        case SGPU_ERR_IIR_INTERPOLATION_LESS_THAN_ONE: return "IIRErrorCode::InterpolationLessThanOne";
+        case SGPU_ERR_SOS_COEFFICIENTS_NOT_IN_RANGE: return "SecondOrderErrorCode::CoefficientsNotInRange";
+        case SGPU_ERR_INVALID_ARGUMENT: return "SGPU_ERR_INVALID_ARGUMENT";
+        case SGPU_ERR_CAPACITY: return "SGPU_ERR_CAPACITY";
+        case SGPU_ERR_CUDA: return "SGPU_ERR_CUDA";
+        case SGPU_ERR_UNSUPPORTED: return "SGPU_ERR_UNSUPPORTED";
+        case SGPU_ERR_NO_DEVICE: return "SGPU_ERR_NO_DEVICE";
+        case SGPU_ERR_ALLOC: return "SGPU_ERR_ALLOC";
+        default: return "SGPU_ERR_UNKNOWN";
+    }
+}
+
+SGPU_EXPORT int sgpu_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor,
+                                 size_t *total_mem) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return sgpu::fail(SGPU_ERR_NO_DEVICE, "no CUDA device (%s)",
+                          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = 0;
+    SGPU_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    SGPU_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (device) *device = dev;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT uint64_t sgpu_launch_count(void) {
+    return sgpu::g_launches.load(std::memory_order_relaxed);
+}
+
+SGPU_EXPORT int sgpu_shard_channels(size_t n_channels, int world, int rank, size_t *first,
+                                    size_t *count) {
+    if (world < 1 || rank < 0 || rank >= world || !first || !count)
+        return sgpu::fail(SGPU_ERR_INVALID_ARGUMENT, "shard_channels: bad world/rank");
+    size_t base = n_channels / (size_t)world, rem = n_channels % (size_t)world;
+    size_t r = (size_t)rank;
+    *count = base + (r < rem ? 1 : 0);
+    *first = r * base + (r < rem ? r : rem);
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_shard_stream(size_t n_samples, size_t align, int world, int rank,
+                                  size_t *first, size_t *count) {
+    if (world < 1 || rank < 0 || rank >= world || !first || !count || align < 1)
+        return sgpu::fail(SGPU_ERR_INVALID_ARGUMENT, "shard_stream: bad world/rank/align");
+    // segment boundaries at multiples of `align`; the last rank takes the ragged tail
+    size_t units = n_samples / align;
+    size_t base = units / (size_t)world, rem = units % (size_t)world;
+    size_t r = (size_t)rank;
+    size_t u0 = r * base + (r < rem ? r : rem);
+    size_t u1 = u0 + base + (r < rem ? 1 : 0);
+    *first = u0 * align;
+    size_t end = (rank == world - 1) ? n_samples : u1 * align;
+    *count = end - *first;
+    return SGPU_OK;
+}

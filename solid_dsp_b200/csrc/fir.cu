@@ -1,0 +1,903 @@
+// FIRFilter / DecimatingFIRFilter / InterpolatingFIRFilter (PolyPhaseFilterBank) on sm_100a.
+//
+// Reference loops replaced (relative to the reference's src/):
+//   FIRFilter::execute_block            filter/fir/mod.rs:235-241  -> :209-212
+//   DecimatingFIRFilter::execute_block  filter/fir/decim.rs:250-256 -> :221-228
+//   InterpolatingFIRFilter::execute_block filter/fir/interp.rs:102-111 -> pfb.rs:85-90
+//   Window::push / to_vec               window/mod.rs:63-71,44-51  (history: hist_update_kernel)
+//   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
+#include "fir_core.cuh"
+#include "sgpu_common.cuh"
+
+namespace sgpu {
+namespace {
+
+constexpr int kMaxSmem = 227 * 1024;
+
+struct FirArgs {
+    const float2 *in;
+    float2 *out;
+    const float2 *hist;  // [C][T-1], oldest first (state entering this call)
+    const float *taps;   // [nsets][Qpad] taps (x2 floats when PACKED), device
+    long long in_stride, out_stride;
+    long long n_in, n_out;  // per channel
+    int T;                  // taps of the full filter
+    int M;                  // decimation (decim kernel) or interpolation L (interp kernel)
+    int c0;                 // decimator phase counter on entry (current_item)
+    int Qpad;               // taps per phase, padded to a multiple of 2R
+    int RS;                 // row stride of a plane in float4, odd
+    int vec_in, vec_out;    // 16-byte vector access allowed
+    float scale_re, scale_im;
+};
+
+// sample `i` of this call's logical input: i < 0 reads the history, beyond either end is 0
+__device__ __forceinline__ float2 fetch_sample(const float2 *__restrict__ x,
+                                               const float2 *__restrict__ hist, const long long i,
+                                               const long long n_in, const int T) {
+    if (i >= 0) return i < n_in ? x[i] : make_float2(0.f, 0.f);
+    const long long h = (long long)(T - 1) + i;
+    return h >= 0 ? hist[h] : make_float2(0.f, 0.f);
+}
+
+// --------------------------------------------------------------------------------------------
+// FIR (M1 = true) and decimating FIR.  Block = NT threads, tile = NT*R outputs of one channel.
+// Output m of this call is produced by input n_m = m*M + (M-1-c0); with k = q*M + p,
+//   y[m] = scale * sum_p sum_q g[q*M+p] * x[(m-q)*M + (M-1-c0) - p]
+// i.e. M short FIRs (taps g_p[q]) over the phase sequences x_p[m'] = x[m'*M + (M-1-c0) - p],
+// which the loader de-interleaves into M shared-memory planes.
+template <int R, bool PACKED, bool M1, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
+    extern __shared__ float4 smem[];
+    const int tid = threadIdx.x;
+    const int M = M1 ? 1 : a.M;
+    const int Qpad = a.Qpad;
+    const int HR = Qpad / R;
+    const int rows = HR + NT;
+    const int RS = a.RS;
+    const int plane_f4 = (R / 2) * RS + 1;  // +1: consecutive planes are skewed by 16 bytes
+    constexpr int TW = PACKED ? 2 : 1;
+    float *taps_s = reinterpret_cast<float *>(smem + (size_t)M * plane_f4);
+
+    const int ch = blockIdx.y;
+    const long long m_base = (long long)blockIdx.x * (NT * R);
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
+
+    {  // taps image -> shared memory
+        const int n4 = M * Qpad * TW / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        float4 *dst = reinterpret_cast<float4 *>(taps_s);
+        for (int i = tid; i < n4; i += NT) dst[i] = src[i];
+    }
+
+    // ---- tile load: rows*R*M consecutive input samples starting at i_lo, two per thread-step
+    const long long i_lo = (m_base - Qpad) * M - a.c0;
+    const int total_pairs = rows * R * M / 2;
+    if constexpr (M1) {
+        for (int pe = tid; pe < total_pairs; pe += NT) {
+            const long long i = i_lo + 2 * pe;
+            float4 v;
+            if (a.vec_in && i >= 0 && i + 1 < a.n_in) {
+                v = *reinterpret_cast<const float4 *>(x + i);
+            } else {
+                const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
+                const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
+                v = make_float4(s0.x, s0.y, s1.x, s1.y);
+            }
+            const int rho = pe / (R / 2), jj = pe % (R / 2);
+            smem[jj * RS + rho] = v;
+        }
+    } else {
+        int e = 2 * tid;
+        int q = e / M, rem = e - q * M;
+        const int qs = (2 * NT) / M, rs = (2 * NT) - qs * M;
+        const bool lo_even = (i_lo & 1) == 0;
+        for (int pe = tid; pe < total_pairs; pe += NT) {
+            const long long i = i_lo + 2 * pe;
+            float2 s0, s1;
+            if (a.vec_in && lo_even && i >= 0 && i + 1 < a.n_in) {
+                const float4 v = *reinterpret_cast<const float4 *>(x + i);
+                s0 = make_float2(v.x, v.y);
+                s1 = make_float2(v.z, v.w);
+            } else {
+                s0 = fetch_sample(x, hist, i, a.n_in, a.T);
+                s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
+            }
+            {
+                const int p = M - 1 - rem, rho = q / R, j = q % R;
+                reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho)[j & 1] = s0;
+            }
+            {
+                int q1 = q, rem1 = rem + 1;
+                if (rem1 == M) { rem1 = 0; q1++; }
+                const int p = M - 1 - rem1, rho = q1 / R, j = q1 % R;
+                reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho)[j & 1] = s1;
+            }
+            q += qs;
+            rem += rs;
+            if (rem >= M) { rem -= M; q++; }
+        }
+    }
+    __syncthreads();
+
+    // ---- compute
+    float2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+    const int row0 = HR + tid;
+    const int npairs = Qpad / (2 * R);
+    for (int p = 0; p < M; ++p)
+        fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * Qpad * TW,
+                            npairs);
+
+    // ---- epilogue: scale (fir/mod.rs:211), stage through plane 0, coalesced store
+    __syncthreads();
+    const float s = a.scale_re;
+#pragma unroll
+    for (int jj = 0; jj < R / 2; ++jj)
+        smem[jj * RS + tid] = make_float4(acc[2 * jj].x * s, acc[2 * jj].y * s, acc[2 * jj + 1].x * s,
+                                          acc[2 * jj + 1].y * s);
+    __syncthreads();
+    float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
+    for (int idx = tid; idx < NT * R / 2; idx += NT) {
+        const int rho = idx / (R / 2), jj = idx % (R / 2);
+        const long long o = m_base + (long long)rho * R + 2 * jj;
+        if (o >= a.n_out) continue;
+        const float4 v = smem[jj * RS + rho];
+        if (a.vec_out && o + 1 < a.n_out) {
+            *reinterpret_cast<float4 *>(y + o) = v;
+        } else {
+            y[o] = make_float2(v.x, v.y);
+            if (o + 1 < a.n_out) y[o + 1] = make_float2(v.z, v.w);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Interpolator: y[n*L + p] = sum_{j<S} hp[p][j] * x[n-j], hp[p][j] = hpad[p + (S-1-j)*L].
+// One input plane, L tap sets; a thread runs the L phases one after the other over the same
+// R input positions and stages the interleaved outputs in shared memory.  a.M carries L.
+template <int R, bool PACKED, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
+    extern __shared__ float4 smem[];
+    const int tid = threadIdx.x;
+    const int L = a.M;
+    const int Qpad = a.Qpad;
+    const int HR = Qpad / R;
+    const int rows = HR + NT;
+    const int RS = a.RS;
+    const int plane_f4 = (R / 2) * RS + 1;
+    constexpr int TW = PACKED ? 2 : 1;
+    float *taps_s = reinterpret_cast<float *>(smem + plane_f4);
+    // staging: NT*R*L outputs, thread t's run skewed by t float2 (bank spread)
+    float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * Qpad * TW);
+
+    const int ch = blockIdx.y;
+    const long long n_base = (long long)blockIdx.x * (NT * R);
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T = S here
+
+    {
+        const int n4 = L * Qpad * TW / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        float4 *dst = reinterpret_cast<float4 *>(taps_s);
+        for (int i = tid; i < n4; i += NT) dst[i] = src[i];
+    }
+    const long long i_lo = n_base - Qpad;
+    const int total_pairs = rows * R / 2;
+    for (int pe = tid; pe < total_pairs; pe += NT) {
+        const long long i = i_lo + 2 * pe;
+        float4 v;
+        if (a.vec_in && i >= 0 && i + 1 < a.n_in) {
+            v = *reinterpret_cast<const float4 *>(x + i);
+        } else {
+            const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
+            const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
+            v = make_float4(s0.x, s0.y, s1.x, s1.y);
+        }
+        const int rho = pe / (R / 2), jj = pe % (R / 2);
+        smem[jj * RS + rho] = v;
+    }
+    __syncthreads();
+
+    const int row0 = HR + tid;
+    const int npairs = Qpad / (2 * R);
+    float2 *my = stage + (size_t)tid * (R * L + 1);
+    for (int p = 0; p < L; ++p) {
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+        fir_core<R, PACKED>(acc, smem, RS, row0, taps_s + (size_t)p * Qpad * TW, npairs);
+#pragma unroll
+        for (int r = 0; r < R; ++r) my[r * L + p] = acc[r];  // no scale: pfb.rs:85-90
+    }
+    __syncthreads();
+    float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
+    const int per_thread = R * L;
+    const long long o_base = n_base * L;
+    for (int idx = tid; idx < NT * per_thread; idx += NT) {
+        const long long o = o_base + idx;
+        if (o >= a.n_out) break;
+        const int t = idx / per_thread;
+        y[o] = stage[idx + t];
+    }
+}
+
+// new history = last T-1 samples of (old history ++ x[0..n_in))   (Window::push, window/mod.rs:63-71)
+__global__ void hist_update_kernel(const float2 *__restrict__ in, long long in_stride, long long n_in,
+                                   const float2 *__restrict__ hist_old, float2 *__restrict__ hist_new,
+                                   int H /* = T-1 */) {
+    const int ch = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H) return;
+    const long long s = n_in - H + i;
+    float2 v;
+    if (s >= 0) v = in[(long long)ch * in_stride + s];
+    else {
+        const long long h = (long long)H + s;  // index into old history
+        v = h >= 0 ? hist_old[(long long)ch * H + h] : make_float2(0.f, 0.f);
+    }
+    hist_new[(long long)ch * H + i] = v;
+}
+
+// PolyPhaseFilterBank::execute(index): one dot product per channel over the history ++ nothing.
+// hist holds the last S-1 samples; the window's newest element is hist[S-2] ... the PFB window
+// has capacity S, so the bank keeps S samples: we store S-1 "history" plus the newest in `last`.
+__global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const float *__restrict__ taps,
+                                 int Qpad, int tw, int phase, float2 *__restrict__ out, int C) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= C) return;
+    // window (newest first) = hist[S-1], hist[S-2], ..., hist[0]  with hist of S samples
+    const float2 *h = hist + (long long)ch * S;
+    const float *g = taps + (size_t)phase * Qpad * tw;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = 0; j < S; ++j) {
+        const float gj = g[j * tw];
+        const float2 w = h[S - 1 - j];
+        acc.x = fmaf(gj, w.x, acc.x);
+        acc.y = fmaf(gj, w.y, acc.y);
+    }
+    out[ch] = acc;
+}
+
+}  // namespace
+}  // namespace sgpu
+
+// =============================================================================================
+// Handles
+// =============================================================================================
+using namespace sgpu;
+
+namespace {
+
+constexpr int kR = 16;
+constexpr int kNT_FIR = 128;
+constexpr int kNT_DEC = 64;
+constexpr int kNT_INT = 64;
+
+bool packed_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SGPU_FIR_SCALAR_FMA");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// Host-side image of the taps as the kernels consume them: nsets phase filters of Qpad taps.
+void build_tap_image(const std::vector<float> &phase_taps /*[nsets][Q]*/, int nsets, int Q, int Qpad,
+                     bool packed, std::vector<float> &img) {
+    const int tw = packed ? 2 : 1;
+    img.assign((size_t)nsets * Qpad * tw, 0.f);
+    for (int p = 0; p < nsets; ++p)
+        for (int q = 0; q < Q; ++q) {
+            const float g = phase_taps[(size_t)p * Q + q];
+            if (packed) {
+                img[((size_t)p * Qpad + q) * 2] = g;
+                img[((size_t)p * Qpad + q) * 2 + 1] = g;
+            } else {
+                img[(size_t)p * Qpad + q] = g;
+            }
+        }
+}
+
+}  // namespace
+
+struct sgpu_fir {
+    int device = 0, sm_count = 0;
+    size_t T = 0, C = 0, M = 1;
+    bool is_decim = false, complex_taps = false, packed = true;
+    double scale_re = 1.0, scale_im = 0.0;
+    std::vector<float> taps_f32;  // caller order h[0..T), rounded to f32 (x2 when complex)
+    uint64_t current_item = 0;    // fir/decim.rs:8
+    int Q = 0, Qpad = 0;          // taps per phase
+    float *d_taps = nullptr;      // tap image
+    float2 *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    Staging stage;
+};
+
+static int fir_upload_taps(sgpu_fir *f) {
+    const int T = (int)f->T, M = (int)f->M;
+    f->Q = (T + M - 1) / M;
+    f->Qpad = (int)round_up((size_t)f->Q, 2 * kR);
+    // g[k] = h[T-1-k] (REVERSE, fir/mod.rs:86); phase p filter: g_p[q] = g[q*M + p]
+    std::vector<float> ph((size_t)M * f->Q, 0.f);
+    for (int k = 0; k < T; ++k) ph[(size_t)(k % M) * f->Q + k / M] = f->taps_f32[T - 1 - k];
+    std::vector<float> img;
+    build_tap_image(ph, M, f->Q, f->Qpad, f->packed, img);
+    if (f->d_taps) cudaFree(f->d_taps);
+    f->d_taps = nullptr;
+    SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
+    SGPU_CUDA(cudaMemcpy(f->d_taps, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                double scale_re, double scale_im, int is_decimator, size_t decimation,
+                                sgpu_fir **out) {
+    if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "fir_create: out is NULL");
+    *out = nullptr;
+    if (n_taps == 0 || !taps)  // fir/mod.rs:80-82, decim.rs:28-29
+        return fail(SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO, "FIR Filter Error CoefficientsLengthZero");
+    if (is_decimator && decimation < 1)  // decim.rs:30-31
+        return fail(SGPU_ERR_FIR_DECIMATION_LESS_THAN_ONE, "FIR Filter Error DecimationLessThanOne");
+    if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "fir_create: n_channels == 0");
+    if (kind == SGPU_TAPS_COMPLEX)
+        return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet (real taps only)");
+    if (n_taps > (1u << 20) || (is_decimator && decimation > 4096))
+        return fail(SGPU_ERR_UNSUPPORTED, "fir_create: n_taps/decimation beyond supported range");
+    int dev = 0, sms = 0;
+    int st = require_device(&dev, &sms);
+    if (st) return st;
+    sgpu_fir *f = new (std::nothrow) sgpu_fir();
+    if (!f) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    f->device = dev;
+    f->sm_count = sms;
+    f->T = n_taps;
+    f->C = n_channels;
+    f->is_decim = is_decimator != 0;
+    f->M = f->is_decim ? decimation : 1;
+    f->scale_re = scale_re;
+    f->scale_im = scale_im;
+    f->packed = packed_default();
+    f->taps_f32.resize(n_taps);
+    for (size_t i = 0; i < n_taps; ++i) f->taps_f32[i] = (float)taps[i];
+    st = fir_upload_taps(f);
+    if (st) { sgpu_fir_destroy(f); return st; }
+    const size_t hbytes = n_channels * (n_taps > 1 ? n_taps - 1 : 1) * sizeof(float2);
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc(&f->d_hist[i], hbytes) != cudaSuccess) {
+            sgpu_fir_destroy(f);
+            return fail(SGPU_ERR_CUDA, "cudaMalloc(history %zu bytes) failed", hbytes);
+        }
+        cudaMemset(f->d_hist[i], 0, hbytes);
+    }
+    *out = f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_destroy(sgpu_fir *f) {
+    if (!f) return SGPU_OK;
+    DeviceGuard g(f->device);
+    if (f->d_taps) cudaFree(f->d_taps);
+    for (int i = 0; i < 2; ++i)
+        if (f->d_hist[i]) cudaFree(f->d_hist[i]);
+    f->stage.release();
+    delete f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT size_t sgpu_fir_out_len(const sgpu_fir *f, size_t n_in) {
+    if (!f) return 0;
+    return f->is_decim ? (size_t)((f->current_item + n_in) / f->M) : n_in;
+}
+SGPU_EXPORT size_t sgpu_fir_len(const sgpu_fir *f) { return f ? f->T : 0; }
+SGPU_EXPORT size_t sgpu_fir_decimation(const sgpu_fir *f) { return f ? f->M : 0; }
+SGPU_EXPORT size_t sgpu_fir_channels(const sgpu_fir *f) { return f ? f->C : 0; }
+
+SGPU_EXPORT int sgpu_fir_set_scale(sgpu_fir *f, double re, double im) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    f->scale_re = re;
+    f->scale_im = im;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_fir_get_scale(const sgpu_fir *f, double *re, double *im) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (re) *re = f->scale_re;
+    if (im) *im = f->scale_im;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_fir_coefficients(const sgpu_fir *f, double *out) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    for (size_t i = 0; i < f->T; ++i) out[i] = (double)f->taps_f32[f->T - 1 - i];  // stored order
+    return SGPU_OK;
+}
+
+namespace {
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    SGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SGPU_OK;
+}
+
+// Enqueue the history update for a handle (ping-pong) on `s`.
+int enqueue_hist_update(const float2 *d_in, long long in_stride, long long n_in, float2 *hist[2], int &cur,
+                        size_t C, size_t H, cudaStream_t s) {
+    if (H == 0 || n_in == 0) return SGPU_OK;
+    dim3 grid((unsigned)ceil_div(H, 128), (unsigned)C);
+    hist_update_kernel<<<grid, 128, 0, s>>>(d_in, in_stride, n_in, hist[cur], hist[cur ^ 1], (int)H);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    cur ^= 1;
+    return SGPU_OK;
+}
+
+int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
+               long long out_stride, long long n_out, cudaStream_t s) {
+    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
+    FirArgs a{};
+    a.in = d_in;
+    a.out = d_out;
+    a.hist = f->d_hist[f->cur];
+    a.taps = f->d_taps;
+    a.in_stride = in_stride;
+    a.out_stride = out_stride;
+    a.n_in = n_in;
+    a.n_out = n_out;
+    a.T = (int)f->T;
+    a.M = (int)f->M;
+    a.c0 = (int)f->current_item;
+    a.Qpad = f->Qpad;
+    a.vec_in = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (in_stride % 2 == 0);
+    a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (out_stride % 2 == 0);
+    a.scale_re = (float)f->scale_re;
+    a.scale_im = (float)f->scale_im;
+    const int tw = f->packed ? 2 : 1;
+    if (n_out > 0) {
+        const bool m1 = f->M == 1;
+        const int NT = m1 ? kNT_FIR : kNT_DEC;
+        const int rows = f->Qpad / kR + NT;
+        a.RS = rows | 1;
+        const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
+        const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * f->Qpad * tw * sizeof(float);
+        if (smem > (size_t)kMaxSmem)
+            return fail(SGPU_ERR_UNSUPPORTED, "filter too long for one shared-memory tile (%zu bytes needed)", smem);
+        const long long tiles = (n_out + (long long)NT * kR - 1) / ((long long)NT * kR);
+        dim3 grid((unsigned)tiles, (unsigned)f->C);
+        int st;
+#define LAUNCH_FIR(PK, M1, NTV, MINB)                                                       \
+    do {                                                                                    \
+        auto kern = fir_decim_kernel<kR, PK, M1, NTV, MINB>;                                \
+        st = set_smem(kern, smem);                                                          \
+        if (st) return st;                                                                  \
+        kern<<<grid, NTV, smem, s>>>(a);                                                    \
+    } while (0)
+        if (m1) {
+            if (f->packed) LAUNCH_FIR(true, true, kNT_FIR, 4);
+            else LAUNCH_FIR(false, true, kNT_FIR, 4);
+        } else {
+            if (f->packed) LAUNCH_FIR(true, false, kNT_DEC, 3);
+            else LAUNCH_FIR(false, false, kNT_DEC, 3);
+        }
+#undef LAUNCH_FIR
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+    }
+    return SGPU_OK;
+}
+
+}  // namespace
+
+SGPU_EXPORT int sgpu_fir_execute_block(sgpu_fir *f, const float *in, size_t n_in, size_t in_stride,
+                                       float *out, size_t out_stride, size_t *n_out_p, sgpu_mem mem,
+                                       void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t n_out = sgpu_fir_out_len(f, n_in);
+    if (n_out_p) *n_out_p = n_out;
+    if (n_in == 0) return SGPU_OK;
+    if (!in || (n_out && !out)) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
+    if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    float2 *d_out = reinterpret_cast<float2 *>(out);
+    long long istr = (long long)in_stride, ostr = (long long)out_stride;
+    if (mem == SGPU_HOST) {
+        const size_t in_b = f->C * n_in * sizeof(float2), out_b = f->C * (n_out ? n_out : 1) * sizeof(float2);
+        int st = f->stage.ensure(in_b, out_b);
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        d_out = (float2 *)f->stage.out;
+        istr = (long long)n_in;
+        ostr = (long long)(n_out ? n_out : 1);
+    }
+    int st = fir_launch(f, d_in, (long long)n_in, istr, d_out, ostr, (long long)n_out, s);
+    if (st) return st;
+    st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->T - 1, s);
+    if (st) return st;
+    if (f->is_decim) f->current_item = (f->current_item + n_in) % f->M;  // decim.rs:116
+    if (mem == SGPU_HOST) {
+        if (n_out)
+            SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
+                                        n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
+        SGPU_CUDA(cudaStreamSynchronize(s));
+    }
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_write(sgpu_fir *f, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem,
+                               void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_in == 0) return SGPU_OK;
+    if (!in) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    long long istr = (long long)in_stride;
+    if (mem == SGPU_HOST) {
+        int st = f->stage.ensure(f->C * n_in * sizeof(float2), 0);
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        istr = (long long)n_in;
+    }
+    int st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->T - 1, s);
+    if (st) return st;
+    if (f->is_decim) f->current_item = (f->current_item + n_in) % f->M;  // decim.rs:137
+    if (mem == SGPU_HOST) SGPU_CUDA(cudaStreamSynchronize(s));
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_get_state(sgpu_fir *f, float *history, uint64_t *current_item) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    if (history && f->T > 1) {
+        SGPU_CUDA(cudaDeviceSynchronize());
+        SGPU_CUDA(cudaMemcpy(history, f->d_hist[f->cur], f->C * (f->T - 1) * sizeof(float2),
+                             cudaMemcpyDeviceToHost));
+    }
+    if (current_item) *current_item = f->current_item;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_set_state(sgpu_fir *f, const float *history, uint64_t current_item) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    if (history && f->T > 1) {
+        SGPU_CUDA(cudaDeviceSynchronize());
+        SGPU_CUDA(cudaMemcpy(f->d_hist[f->cur], history, f->C * (f->T - 1) * sizeof(float2),
+                             cudaMemcpyHostToDevice));
+    }
+    f->current_item = f->is_decim ? current_item % f->M : 0;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_reset(sgpu_fir *f) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemset(f->d_hist[f->cur], 0, f->C * (f->T > 1 ? f->T - 1 : 1) * sizeof(float2)));
+    f->current_item = 0;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(f->device);
+    std::vector<double> taps(f->T);
+    for (size_t i = 0; i < f->T; ++i) taps[i] = (double)f->taps_f32[i];
+    sgpu_fir *c = nullptr;
+    int st = sgpu_fir_create(taps.data(), f->T, SGPU_TAPS_REAL, f->C, f->scale_re, f->scale_im, f->is_decim,
+                             f->M, &c);
+    if (st) return st;
+    if (f->T > 1) {
+        SGPU_CUDA(cudaDeviceSynchronize());
+        SGPU_CUDA(cudaMemcpy(c->d_hist[c->cur], f->d_hist[f->cur], f->C * (f->T - 1) * sizeof(float2),
+                             cudaMemcpyDeviceToDevice));
+    }
+    c->current_item = f->current_item;
+    *out = c;
+    return SGPU_OK;
+}
+
+// =============================================================================================
+// InterpolatingFIRFilter / PolyPhaseFilterBank
+// =============================================================================================
+struct sgpu_interp {
+    int device = 0, sm_count = 0;
+    size_t T = 0, C = 0, L = 1, S = 0;  // S = sub-filter length
+    bool packed = true;
+    double scale_re = 1.0, scale_im = 0.0;  // stored, never applied (pfb.rs:85-90)
+    std::vector<float> phase_taps;           // [L][S]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first)
+    int Qpad = 0;
+    float *d_taps = nullptr;
+    float2 *d_hist[2] = {nullptr, nullptr};  // S samples per channel: the PFB window (oldest first)
+    int cur = 0;
+    Staging stage;
+};
+
+static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S values */) {
+    const int L = (int)f->L, S = (int)f->S;
+    f->phase_taps.assign((size_t)L * S, 0.f);
+    for (int p = 0; p < L; ++p)
+        for (int j = 0; j < S; ++j) f->phase_taps[(size_t)p * S + j] = (float)taps_eff[p + (size_t)(S - 1 - j) * L];
+    f->Qpad = (int)round_up((size_t)S, 2 * kR);
+    std::vector<float> img;
+    build_tap_image(f->phase_taps, L, S, f->Qpad, f->packed, img);
+    SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
+    SGPU_CUDA(cudaMemcpy(f->d_taps, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // window of S samples; kernels treat the last S-1 as "history" (T-1 with T = S)
+    const size_t hbytes = f->C * (size_t)S * sizeof(float2);
+    for (int i = 0; i < 2; ++i) {
+        SGPU_CUDA(cudaMalloc(&f->d_hist[i], hbytes));
+        SGPU_CUDA(cudaMemset(f->d_hist[i], 0, hbytes));
+    }
+    return SGPU_OK;
+}
+
+static int interp_create_common(const double *taps_eff, size_t n_eff, size_t n_taps, size_t n_channels,
+                                size_t L, size_t S, double sre, double sim, sgpu_interp **out) {
+    (void)n_eff;
+    if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels == 0");
+    if (L > 4096 || S > (1u << 20)) return fail(SGPU_ERR_UNSUPPORTED, "interpolation/sub-filter too large");
+    int dev = 0, sms = 0;
+    int st = require_device(&dev, &sms);
+    if (st) return st;
+    sgpu_interp *f = new (std::nothrow) sgpu_interp();
+    if (!f) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    f->device = dev;
+    f->sm_count = sms;
+    f->T = n_taps;
+    f->C = n_channels;
+    f->L = L;
+    f->S = S;
+    f->scale_re = sre;
+    f->scale_im = sim;
+    f->packed = packed_default();
+    st = interp_build(f, taps_eff);
+    if (st) { sgpu_interp_destroy(f); return st; }
+    *out = f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                   size_t interpolation, sgpu_interp **out) {
+    if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (n_taps == 0 || !taps)  // interp.rs:28-29
+        return fail(SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO, "FIR Filter Error CoefficientsLengthZero");
+    if (interpolation < 1)  // interp.rs:30-31
+        return fail(SGPU_ERR_FIR_INTERPOLATION_LESS_THAN_ONE, "FIR Filter Error InterpolationLessThanOne");
+    if (kind == SGPU_TAPS_COMPLEX) return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet");
+    // interp.rs:35-40: sub-filter length through an f32 quotient
+    const float q = (float)n_taps / (float)interpolation;
+    const size_t S = (q == floorf(q)) ? (size_t)q : (size_t)ceilf(q);
+    const size_t eff = S * interpolation;  // interp.rs:43
+    std::vector<double> padded(eff > n_taps ? eff : n_taps, 0.0);
+    for (size_t i = 0; i < n_taps; ++i) padded[i] = taps[i];
+    return interp_create_common(padded.data(), eff, n_taps, n_channels, interpolation, S, 1.0, 0.0, out);
+}
+
+SGPU_EXPORT int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                size_t filters, double scale_re, double scale_im, sgpu_interp **out) {
+    if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (filters == 0)  // pfb.rs:25-26
+        return fail(SGPU_ERR_FIR_NOT_ENOUGH_FILTERS, "FIR Filter Error NotEnoughFilters");
+    if (n_taps == 0 || !taps)  // pfb.rs:27-28
+        return fail(SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO, "FIR Filter Error CoefficientsLengthZero");
+    if (kind == SGPU_TAPS_COMPLEX) return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet");
+    const size_t S = n_taps / filters;  // pfb.rs:32 (truncating)
+    if (S == 0)  // reference: Window::new(0) assertion panic (window/mod.rs:18)
+        return fail(SGPU_ERR_FIR_NOT_ENOUGH_FILTERS, "FIR Filter Error NotEnoughFilters (filters > taps)");
+    return interp_create_common(taps, S * filters, n_taps, n_channels, filters, S, scale_re, scale_im, out);
+}
+
+SGPU_EXPORT int sgpu_interp_destroy(sgpu_interp *f) {
+    if (!f) return SGPU_OK;
+    DeviceGuard g(f->device);
+    if (f->d_taps) cudaFree(f->d_taps);
+    for (int i = 0; i < 2; ++i)
+        if (f->d_hist[i]) cudaFree(f->d_hist[i]);
+    f->stage.release();
+    delete f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT size_t sgpu_interp_interpolation(const sgpu_interp *f) { return f ? f->L : 0; }
+SGPU_EXPORT size_t sgpu_interp_sub_len(const sgpu_interp *f) { return f ? f->S : 0; }
+SGPU_EXPORT size_t sgpu_interp_channels(const sgpu_interp *f) { return f ? f->C : 0; }
+SGPU_EXPORT int sgpu_interp_set_scale(sgpu_interp *f, double re, double im) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    f->scale_re = re;
+    f->scale_im = im;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_interp_get_scale(const sgpu_interp *f, double *re, double *im) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (re) *re = f->scale_re;
+    if (im) *im = f->scale_im;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_interp_coefficients(const sgpu_interp *f, double *out) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    // pfb.rs:71-73: each DotProduct's stored order = rev_sub_coefs; rev_sub[S-1-idx] = h[p + idx*L]
+    // so stored[i] = h[p + (S-1-i)*L] = phase_taps[p][i]
+    for (size_t i = 0; i < f->L * f->S; ++i) out[i] = (double)f->phase_taps[i];
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_t n_in, size_t in_stride,
+                                          float *out, size_t out_stride, size_t *n_out_p, sgpu_mem mem,
+                                          void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t n_out = n_in * f->L;
+    if (n_out_p) *n_out_p = n_out;
+    if (n_in == 0) return SGPU_OK;
+    if (!in || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
+    if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    float2 *d_out = reinterpret_cast<float2 *>(out);
+    long long istr = (long long)in_stride, ostr = (long long)out_stride;
+    if (mem == SGPU_HOST) {
+        int st = f->stage.ensure(f->C * n_in * sizeof(float2), f->C * n_out * sizeof(float2));
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        d_out = (float2 *)f->stage.out;
+        istr = (long long)n_in;
+        ostr = (long long)n_out;
+    }
+    FirArgs a{};
+    a.in = d_in;
+    a.out = d_out;
+    // the kernel's history convention is "T-1 samples before x[0]" with T = S+1 here: the PFB
+    // window keeps S samples, of which the interpolator only ever reads the newest S-1 as past.
+    a.hist = f->d_hist[f->cur];
+    a.taps = f->d_taps;
+    a.in_stride = istr;
+    a.out_stride = ostr;
+    a.n_in = (long long)n_in;
+    a.n_out = (long long)n_out;
+    a.T = (int)f->S + 1;
+    a.M = (int)f->L;
+    a.c0 = 0;
+    a.Qpad = f->Qpad;
+    a.vec_in = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (istr % 2 == 0);
+    a.vec_out = 0;
+    a.scale_re = 1.f;
+    const int tw = f->packed ? 2 : 1;
+    const int NT = kNT_INT;
+    const int rows = f->Qpad / kR + NT;
+    a.RS = rows | 1;
+    const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
+    const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)f->Qpad * tw * sizeof(float) +
+                        (size_t)NT * (kR * f->L + 1) * sizeof(float2);
+    if (smem > (size_t)kMaxSmem)
+        return fail(SGPU_ERR_UNSUPPORTED, "interpolator tile needs %zu bytes of shared memory", smem);
+    const long long tiles = ((long long)n_in + (long long)NT * kR - 1) / ((long long)NT * kR);
+    dim3 grid((unsigned)tiles, (unsigned)f->C);
+    int st;
+    if (f->packed) {
+        auto kern = fir_interp_kernel<kR, true, kNT_INT, 4>;
+        st = set_smem(kern, smem);
+        if (st) return st;
+        kern<<<grid, NT, smem, s>>>(a);
+    } else {
+        auto kern = fir_interp_kernel<kR, false, kNT_INT, 4>;
+        st = set_smem(kern, smem);
+        if (st) return st;
+        kern<<<grid, NT, smem, s>>>(a);
+    }
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->S, s);
+    if (st) return st;
+    if (mem == SGPU_HOST) {
+        SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
+                                    n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
+        SGPU_CUDA(cudaStreamSynchronize(s));
+    }
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_interp_push(sgpu_interp *f, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem,
+                                 void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_in == 0) return SGPU_OK;
+    if (!in) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    long long istr = (long long)in_stride;
+    if (mem == SGPU_HOST) {
+        int st = f->stage.ensure(f->C * n_in * sizeof(float2), 0);
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        istr = (long long)n_in;
+    }
+    int st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->S, s);
+    if (st) return st;
+    if (mem == SGPU_HOST) SGPU_CUDA(cudaStreamSynchronize(s));
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_interp_execute_phase(sgpu_interp *f, size_t index, float *out, sgpu_mem mem, void *stream) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    if (index >= f->L) return fail(SGPU_ERR_INVALID_ARGUMENT, "phase index %zu >= %zu filters", index, f->L);
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    float2 *d_out = reinterpret_cast<float2 *>(out);
+    if (mem == SGPU_HOST) {
+        int st = f->stage.ensure(0, f->C * sizeof(float2));
+        if (st) return st;
+        d_out = (float2 *)f->stage.out;
+    }
+    const int tw = f->packed ? 2 : 1;
+    pfb_phase_kernel<<<(unsigned)ceil_div(f->C, 128), 128, 0, s>>>(f->d_hist[f->cur], (int)f->S, f->d_taps,
+                                                                     f->Qpad, tw, (int)index, d_out, (int)f->C);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    if (mem == SGPU_HOST) {
+        SGPU_CUDA(cudaMemcpyAsync(out, d_out, f->C * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        SGPU_CUDA(cudaStreamSynchronize(s));
+    }
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_interp_get_state(sgpu_interp *f, float *history) {
+    if (!f || !history) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(f->device);
+    SGPU_CUDA(cudaDeviceSynchronize());
+    // expose the S-1 samples that influence future outputs (drop the oldest of the S kept)
+    if (f->S > 1)
+        SGPU_CUDA(cudaMemcpy2D(history, (f->S - 1) * sizeof(float2), f->d_hist[f->cur] + 1, f->S * sizeof(float2),
+                               (f->S - 1) * sizeof(float2), f->C, cudaMemcpyDeviceToHost));
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_interp_set_state(sgpu_interp *f, const float *history) {
+    if (!f || !history) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(f->device);
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemset(f->d_hist[f->cur], 0, f->C * f->S * sizeof(float2)));
+    if (f->S > 1)
+        SGPU_CUDA(cudaMemcpy2D(f->d_hist[f->cur] + 1, f->S * sizeof(float2), history, (f->S - 1) * sizeof(float2),
+                               (f->S - 1) * sizeof(float2), f->C, cudaMemcpyHostToDevice));
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_interp_reset(sgpu_interp *f) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemset(f->d_hist[f->cur], 0, f->C * f->S * sizeof(float2)));
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_interp_clone(const sgpu_interp *f, sgpu_interp **out) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(f->device);
+    // rebuild the effective tap vector hpad[p + (S-1-j)*L] = phase_taps[p][j]
+    std::vector<double> eff(f->L * f->S);
+    for (size_t p = 0; p < f->L; ++p)
+        for (size_t j = 0; j < f->S; ++j) eff[p + (f->S - 1 - j) * f->L] = (double)f->phase_taps[p * f->S + j];
+    sgpu_interp *c = nullptr;
+    int st = interp_create_common(eff.data(), eff.size(), f->T, f->C, f->L, f->S, f->scale_re, f->scale_im, &c);
+    if (st) return st;
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemcpy(c->d_hist[c->cur], f->d_hist[f->cur], f->C * f->S * sizeof(float2),
+                         cudaMemcpyDeviceToDevice));
+    *out = c;
+    return SGPU_OK;
+}

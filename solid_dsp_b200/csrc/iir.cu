@@ -1,0 +1,876 @@
+// IIRFilter (SecondOrder cascade + Normal), DecimatingIIRFilter, InterpolatingIIRFilter on sm_100a.
+//
+// Reference loops replaced (relative to the reference's src/):
+//   IIRFilter::execute_block            filter/iir/mod.rs:310-316 -> :270-289
+//   SecondOrderFilter::execute          filter/iir/sos.rs:92-114
+//   DecimatingIIRFilter::execute_block  filter/iir/decim.rs:222-233
+//   InterpolatingIIRFilter::execute_block filter/iir/interp.rs:215-221 -> :184-190
+//
+// Two strategies for the SOS cascade:
+//   batch : one (virtual) channel per thread.  A warp owns 32 channels and streams them in tiles
+//           of 16 samples: cp.async (LDGSTS) global -> shared, double buffered, 128-byte coalesced
+//           per channel; lanes then walk their own row from registers/shared and write the
+//           outputs in place; the tile goes back to global coalesced.
+//   scan  : one long stream is cut into P chunks that become "virtual channels" of the batch
+//           kernel.  Pass A runs every chunk from zero state and keeps only the end state z_p;
+//           the carry kernel solves s_{p+1} = A^Lc s_p + z_p (A^Lc built on the host in f64,
+//           recurrence evaluated in f64 on the device, hierarchically); pass C re-runs every
+//           chunk from its true start state and writes the outputs.
+#include "sgpu_common.cuh"
+
+using namespace sgpu;
+
+namespace {
+
+constexpr int kMaxSec = 16;
+constexpr int kTile = 16;  // samples per channel per tile (128 bytes)
+
+struct SosCoefs {  // normalised by a0 (sos.rs:62-68); na* are the negated feedback taps
+    float b0[kMaxSec], b1[kMaxSec], b2[kMaxSec], na1[kMaxSec], na2[kMaxSec];
+};
+
+struct IirArgs {
+    const float2 *in;
+    float2 *out;
+    const float2 *state_in;  // [VC][NSEC][2] (v1, v2) start states, nullptr = zero
+    float2 *state_out;       // [VC][NSEC][2] end states, nullptr = discard
+    long long in_stride, out_stride;
+    long long n_in;   // samples per real channel (WRAP 2: outputs per channel = n_in * factor)
+    long long Lc;     // chunk length; P == 1 -> whole stream
+    int C, P;         // real channels, chunks per channel (multiple of 32 when > 1)
+    int write_out;
+    int factor, idx0;  // decimation / interpolation factor, decimator counter on entry
+    int vec;           // 16-byte aligned pointers and even strides -> cp.async path
+    SosCoefs k;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// one biquad on one complex sample, direct form II, real coefficients
+template <bool PACKED>
+__device__ __forceinline__ float2 biquad(float2 x, float2 &v1, float2 &v2, const float b0, const float b1,
+                                         const float b2, const float na1, const float na2) {
+    float2 v0, y;
+    if constexpr (PACKED) {
+        v0 = __ffma2_rn(v1, make_float2(na1, na1), x);
+        v0 = __ffma2_rn(v2, make_float2(na2, na2), v0);
+        y = __fmul2_rn(v2, make_float2(b2, b2));
+        y = __ffma2_rn(v1, make_float2(b1, b1), y);
+        y = __ffma2_rn(v0, make_float2(b0, b0), y);
+    } else {
+        v0.x = fmaf(na2, v2.x, fmaf(na1, v1.x, x.x));
+        v0.y = fmaf(na2, v2.y, fmaf(na1, v1.y, x.y));
+        y.x = fmaf(b0, v0.x, fmaf(b1, v1.x, b2 * v2.x));
+        y.y = fmaf(b0, v0.y, fmaf(b1, v1.y, b2 * v2.y));
+    }
+    v2 = v1;
+    v1 = v0;
+    return y;
+}
+
+// WRAP: 0 plain, 1 decimating (keep every M-th output), 2 interpolating (L-1 zeros after each input)
+//
+// Full tiles (every row of the warp has 16 more samples) take the fast path: cp.async prefetch of
+// the next tile, unpredicated fully unrolled cascade, 16-byte coalesced stores.  The ragged tail
+// (and every tile of the interpolating wrapper) takes the guarded path.
+template <int NSEC, bool PACKED, int WRAP>
+__global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const IirArgs a) {
+    extern __shared__ float4 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long VC = (long long)a.C * a.P;
+    const long long vc0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (vc0 >= VC) return;
+    float4 *buf = smem + warp * (2 * 32 * 8);
+
+    // affine row addressing for this warp (rows = 32 consecutive virtual channels)
+    long long in_base, out_base, rstr_in, rstr_out, p0 = 0;
+    if (a.P == 1) {
+        in_base = vc0 * a.in_stride;
+        out_base = vc0 * a.out_stride;
+        rstr_in = a.in_stride;
+        rstr_out = a.out_stride;
+    } else {
+        const long long c = vc0 / a.P;
+        p0 = vc0 - c * a.P;
+        in_base = c * a.in_stride + p0 * a.Lc;
+        out_base = c * a.out_stride + p0 * a.Lc;
+        rstr_in = a.Lc;
+        rstr_out = a.Lc;
+    }
+    // per-row length in "loop samples" (inputs for WRAP 0/1, outputs for WRAP 2)
+    const long long n_loop = WRAP == 2 ? a.n_in * a.factor : a.n_in;
+    auto row_len = [&](int r) -> long long {
+        if (vc0 + r >= VC) return 0;
+        if (a.P == 1) return n_loop;
+        long long l = n_loop - (p0 + r) * a.Lc;
+        return l < 0 ? 0 : (l > a.Lc ? a.Lc : l);
+    };
+    const long long my_len = row_len(lane);
+    long long max_len = my_len, min_len = my_len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long u = __shfl_xor_sync(0xffffffffu, max_len, o);
+        const long long v = __shfl_xor_sync(0xffffffffu, min_len, o);
+        max_len = u > max_len ? u : max_len;
+        min_len = v < min_len ? v : min_len;
+    }
+    const long long ntiles = (max_len + kTile - 1) / kTile;
+    const long long full_tiles = WRAP == 2 ? 0 : min_len / kTile;
+
+    // state
+    float2 v1[NSEC], v2[NSEC];
+    const long long my_vc = vc0 + lane;
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        v1[s] = make_float2(0.f, 0.f);
+        v2[s] = make_float2(0.f, 0.f);
+    }
+    if (a.state_in && my_vc < VC) {
+        const float4 *sp = reinterpret_cast<const float4 *>(a.state_in + my_vc * (2 * NSEC));
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            const float4 t = sp[s];
+            v1[s] = make_float2(t.x, t.y);
+            v2[s] = make_float2(t.z, t.w);
+        }
+    }
+
+    const int lrow = lane >> 3, lj = lane & 7;  // loader role: rows lrow + 4*i, chunk lj
+    const int swz = lane & 7;
+    int dec_cnt = a.idx0;                          // decimator phase (WRAP 1)
+    float2 *dec_ptr = a.out + out_base + (long long)lane * rstr_out;  // next decimated output (WRAP 1)
+
+    // ------------------------------------------------------------------ fast path: full tiles
+    if (full_tiles > 0) {
+        const float2 *ld_ptr = a.in + in_base + (long long)lrow * rstr_in + 2 * lj;
+        float2 *st_ptr = a.out + out_base + (long long)lrow * rstr_out + 2 * lj;
+        const long long ld_step = 4 * rstr_in, st_step = 4 * rstr_out;
+        auto prefetch = [&](float4 *dst) {
+            const float2 *src = ld_ptr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = lrow + 4 * i;
+                float4 *d = dst + r * 8 + (lj ^ (r & 7));
+                if (a.vec) {
+                    cp_async16(d, src);
+                } else {
+                    cp_async8(d, src);
+                    cp_async8(reinterpret_cast<float2 *>(d) + 1, src + 1);
+                }
+                src += ld_step;
+            }
+            cp_async_commit();
+            ld_ptr += kTile;
+        };
+        prefetch(buf);
+        for (long long t = 0; t < full_tiles; ++t) {
+            float4 *cur = buf + (t & 1) * (32 * 8);
+            if (t + 1 < full_tiles) {
+                prefetch(buf + ((t + 1) & 1) * (32 * 8));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            float4 *myrow = cur + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 *cell = myrow + (j ^ swz);
+                const float4 xin = *cell;
+                float2 y0 = make_float2(xin.x, xin.y), y1 = make_float2(xin.z, xin.w);
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s)
+                    y0 = biquad<PACKED>(y0, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                if constexpr (WRAP == 1) {
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y0; ++dec_ptr; }
+                }
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s)
+                    y1 = biquad<PACKED>(y1, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                if constexpr (WRAP == 1) {
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y1; ++dec_ptr; }
+                }
+                if constexpr (WRAP == 0) *cell = make_float4(y0.x, y0.y, y1.x, y1.y);
+            }
+            if constexpr (WRAP == 0) {
+                __syncwarp();
+                if (a.write_out) {
+                    float2 *dst = st_ptr;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = lrow + 4 * i;
+                        const float4 v = cur[r * 8 + (lj ^ (r & 7))];
+                        if (a.vec) {
+                            *reinterpret_cast<float4 *>(dst) = v;
+                        } else {
+                            dst[0] = make_float2(v.x, v.y);
+                            dst[1] = make_float2(v.z, v.w);
+                        }
+                        dst += st_step;
+                    }
+                }
+                st_ptr += kTile;
+            }
+            __syncwarp();
+        }
+    }
+
+    // ------------------------------------------------------------------ guarded path: ragged tail
+    if (full_tiles < ntiles) {
+        float4 *cur = buf;
+        const float2 *my_in = a.in + in_base + (long long)lane * rstr_in;
+        int ip_cnt = 0;       // interpolator phase (WRAP 2)
+        long long ip_in = 0;  // next input index (WRAP 2)
+        for (long long t = full_tiles; t < ntiles; ++t) {
+            const long long s0 = t * kTile;
+            if constexpr (WRAP != 2) {
+                for (int i = 0; i < 8; ++i) {
+                    const int r = lrow + 4 * i;
+                    const long long rl = row_len(r);
+                    const long long sidx = s0 + 2 * lj;
+                    const float2 *src = a.in + in_base + (long long)r * rstr_in + sidx;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sidx < rl) { const float2 q = src[0]; v.x = q.x; v.y = q.y; }
+                    if (sidx + 1 < rl) { const float2 q = src[1]; v.z = q.x; v.w = q.y; }
+                    cur[r * 8 + (lj ^ (r & 7))] = v;
+                }
+                __syncwarp();
+            }
+            float2 *myrow2 = reinterpret_cast<float2 *>(cur + lane * 8);
+            for (int n = 0; n < kTile; ++n) {
+                if (s0 + n >= my_len) break;
+                float2 *cell = myrow2 + (((n >> 1) ^ swz) << 1) + (n & 1);
+                float2 y;
+                if constexpr (WRAP == 2) {
+                    y = make_float2(0.f, 0.f);
+                    if (ip_cnt == 0) y = my_in[ip_in++];
+                    if (++ip_cnt == a.factor) ip_cnt = 0;
+                } else {
+                    y = *cell;
+                }
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s)
+                    y = biquad<PACKED>(y, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                if constexpr (WRAP == 1) {
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y; ++dec_ptr; }
+                } else {
+                    *cell = y;
+                }
+            }
+            if constexpr (WRAP != 1) {
+                __syncwarp();
+                if (a.write_out) {
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = lrow + 4 * i;
+                        const long long rl = row_len(r);
+                        const long long sidx = s0 + 2 * lj;
+                        const float4 v = cur[r * 8 + (lj ^ (r & 7))];
+                        float2 *dst = a.out + out_base + (long long)r * rstr_out + sidx;
+                        if (sidx < rl) dst[0] = make_float2(v.x, v.y);
+                        if (sidx + 1 < rl) dst[1] = make_float2(v.z, v.w);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    if (a.state_out && my_vc < VC) {
+        float4 *sp = reinterpret_cast<float4 *>(a.state_out + my_vc * (2 * NSEC));
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) sp[s] = make_float4(v1[s].x, v1[s].y, v2[s].x, v2[s].y);
+    }
+}
+
+// ---- carry recurrence s_{p+1} = Mat * s_p + z_p in f64, one warp per (channel, group) -------
+// mode 0: zero start over the group's chunks           -> gagg[c*G+g]
+// mode 1: one warp per channel over groups (Mat = A^(Lc*CH)): Sg[c*G+g] = start state of group g
+// mode 2: from Sg[c*G+g] (or state0[c] when Sg == nullptr): sbuf[c*P+p] = start state of chunk p
+__global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__restrict__ Mat, int D,
+                                                    const float2 *__restrict__ z, double2 *gagg, double2 *Sg,
+                                                    float2 *__restrict__ sbuf, const float2 *__restrict__ state0,
+                                                    int P, int CH, int G, int n_units) {
+    __shared__ double2 sh[4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int unit = blockIdx.x * 4 + w;
+    if (unit >= n_units) return;
+    double m[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m[j] = (lane < D && j < D) ? Mat[lane * D + j] : 0.0;
+    double2 *s = sh[w];
+    auto step = [&](double2 add) {
+        double2 acc = add;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < D) {
+                const double2 sj = s[j];
+                acc.x = fma(m[j], sj.x, acc.x);
+                acc.y = fma(m[j], sj.y, acc.y);
+            }
+        }
+        __syncwarp();
+        s[lane] = acc;
+        __syncwarp();
+    };
+    if (mode == 1) {
+        const int c = unit;
+        const float2 i0 = lane < D ? state0[(long long)c * D + lane] : make_float2(0.f, 0.f);
+        s[lane] = make_double2(i0.x, i0.y);
+        __syncwarp();
+        for (int g = 0; g < G; ++g) {
+            if (lane < D) Sg[((long long)c * G + g) * D + lane] = s[lane];
+            const double2 add = lane < D ? gagg[((long long)c * G + g) * D + lane] : make_double2(0., 0.);
+            step(add);
+        }
+        return;
+    }
+    const int c = unit / G, g = unit - c * G;
+    const int p_lo = g * CH, p_hi = min(P, p_lo + CH);
+    if (mode == 0) {
+        s[lane] = make_double2(0., 0.);
+    } else {
+        double2 st = make_double2(0., 0.);
+        if (lane < D) {
+            if (Sg) st = Sg[((long long)c * G + g) * D + lane];
+            else {
+                const float2 i0 = state0[(long long)c * D + lane];
+                st = make_double2(i0.x, i0.y);
+            }
+        }
+        s[lane] = st;
+    }
+    __syncwarp();
+    for (int p = p_lo; p < p_hi; ++p) {
+        const long long vc = (long long)c * P + p;
+        if (mode == 2 && lane < D) sbuf[vc * D + lane] = make_float2((float)s[lane].x, (float)s[lane].y);
+        float2 zz = make_float2(0.f, 0.f);
+        if (lane < D) zz = z[vc * D + lane];
+        step(make_double2(zz.x, zz.y));
+    }
+    if (mode == 0 && lane < D) gagg[((long long)c * G + g) * D + lane] = s[lane];
+}
+
+// ---- Normal mode: one direct-form II of arbitrary order (iir/mod.rs:98-130,272-280) ---------
+constexpr int kMaxOrder = 64;
+struct NormalArgs {
+    const float2 *in;
+    float2 *out;
+    float2 *state;  // [C][W] newest first
+    long long in_stride, out_stride, n_in;
+    int C, W, nb, na1;  // na1 = len(a) - 1 feedback taps
+    int wrap, factor, idx0;
+    float b[kMaxOrder], a[kMaxOrder];  // b[0..nb), a[i] = fb[i+1]/a0
+};
+
+__global__ void __launch_bounds__(128) iir_normal_kernel(const NormalArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    float2 w[kMaxOrder];
+    const int W = a.W;
+    for (int i = 0; i < W; ++i) w[i] = a.state[(long long)c * W + i];
+    int head = 0;  // w[(head + i) % W] = i-th newest
+    const float2 *x = a.in + (long long)c * a.in_stride;
+    float2 *y = a.out + (long long)c * a.out_stride;
+    const int nden = min(W - 1, a.na1);  // iir/mod.rs:274 + dot_product/mod.rs:160
+    const int nnum = min(W, a.nb);
+    long long cnt = a.idx0, o = 0;
+    const long long n_loop = a.wrap == 2 ? a.n_in * a.factor : a.n_in;
+    int ip = 0;
+    long long in_i = 0;
+    for (long long n = 0; n < n_loop; ++n) {
+        float2 xin;
+        if (a.wrap == 2) {
+            xin = ip == 0 ? x[in_i++] : make_float2(0.f, 0.f);
+            if (++ip == a.factor) ip = 0;
+        } else {
+            xin = x[n];
+        }
+        float2 den = make_float2(0.f, 0.f);
+        for (int i = 0; i < nden; ++i) {
+            const float2 v = w[(head + i) % W];
+            den.x = fmaf(a.a[i], v.x, den.x);
+            den.y = fmaf(a.a[i], v.y, den.y);
+        }
+        const float2 v0 = make_float2(xin.x - den.x, xin.y - den.y);
+        head = (head + W - 1) % W;
+        w[head] = v0;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int i = 0; i < nnum; ++i) {
+            const float2 v = w[(head + i) % W];
+            acc.x = fmaf(a.b[i], v.x, acc.x);
+            acc.y = fmaf(a.b[i], v.y, acc.y);
+        }
+        if (a.wrap == 1) {
+            if (++cnt == a.factor) {
+                cnt = 0;
+                y[o++] = acc;
+            }
+        } else {
+            y[n] = acc;
+        }
+    }
+    for (int i = 0; i < W; ++i) a.state[(long long)c * W + i] = w[(head + i) % W];
+}
+
+bool iir_packed_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SGPU_IIR_PACKED");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+int pad_sections(int nsec) {
+    const int opts[] = {1, 2, 4, 8, 16};
+    for (int o : opts)
+        if (nsec <= o) return o;
+    return -1;
+}
+
+}  // namespace
+
+struct sgpu_iir {
+    int device = 0, sm_count = 0;
+    int type = SGPU_IIR_SECOND_ORDER;
+    int wrap = SGPU_IIR_PLAIN;
+    size_t factor = 1, C = 0;
+    int nsec = 0, nsec_pad = 0;       // SOS
+    int W = 0, nb = 0, na = 0;        // Normal
+    uint64_t index = 0;               // decimator counter (iir/decim.rs:9)
+    int mode = -1;
+    bool packed = false;
+    std::vector<double> ff_raw, fb_raw;  // as given (numerator_coefs()/denominator_coefs() in SOS mode)
+    std::vector<double> num_norm, den_norm;  // Normal mode: ff/a0, fb[1..]/a0
+    SosCoefs k{};
+    std::vector<double> kd;  // f32-rounded normalised coefs as doubles [nsec][5] = b0,b1,b2,a1,a2
+    float2 *d_state = nullptr;  // SOS: [C][nsec_pad][2]; Normal: [C][W]
+    // scan scratch
+    float2 *d_z = nullptr, *d_s = nullptr;
+    double2 *d_gagg = nullptr, *d_Sg = nullptr;
+    double *d_mat = nullptr;  // [2][D*D]: A^Lc, A^(Lc*CH)
+    size_t scratch_vc = 0, scratch_units = 0;
+    long long mat_Lc = -1, mat_CH = -1;
+    Staging stage;
+};
+
+namespace {
+
+size_t state_len_dev(const sgpu_iir *f) {
+    return f->type == SGPU_IIR_SECOND_ORDER ? (size_t)f->nsec_pad * 2 : (size_t)f->W;
+}
+
+// one-sample zero-input transition matrix of the cascade, state order [s][v1,v2], in f64
+void build_transition(const sgpu_iir *f, std::vector<double> &A) {
+    const int D = 2 * f->nsec_pad;
+    A.assign((size_t)D * D, 0.0);
+    for (int col = 0; col < D; ++col) {
+        std::vector<double> st(D, 0.0);
+        st[col] = 1.0;
+        double y = 0.0;  // zero input
+        for (int s = 0; s < f->nsec_pad; ++s) {
+            double b0 = 1, b1 = 0, b2 = 0, a1 = 0, a2 = 0;
+            if (s < f->nsec) {
+                b0 = f->kd[s * 5 + 0]; b1 = f->kd[s * 5 + 1]; b2 = f->kd[s * 5 + 2];
+                a1 = f->kd[s * 5 + 3]; a2 = f->kd[s * 5 + 4];
+            }
+            const double v1 = st[2 * s], v2 = st[2 * s + 1];
+            const double v0 = y - (a1 * v1 + a2 * v2);
+            y = b0 * v0 + b1 * v1 + b2 * v2;
+            st[2 * s + 1] = v1;
+            st[2 * s] = v0;
+        }
+        for (int r = 0; r < D; ++r) A[(size_t)r * D + col] = st[r];
+    }
+}
+
+void mat_mul(const std::vector<double> &X, const std::vector<double> &Y, std::vector<double> &Z, int D) {
+    std::vector<double> T((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) {
+            const double x = X[(size_t)i * D + k];
+            if (x == 0.0) continue;
+            for (int j = 0; j < D; ++j) T[(size_t)i * D + j] += x * Y[(size_t)k * D + j];
+        }
+    Z.swap(T);
+}
+
+void mat_pow(std::vector<double> A, long long e, std::vector<double> &R, int D) {
+    R.assign((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i) R[(size_t)i * D + i] = 1.0;
+    while (e > 0) {
+        if (e & 1) mat_mul(R, A, R, D);
+        e >>= 1;
+        if (e) mat_mul(A, A, A, D);
+    }
+}
+
+template <int NSEC, bool PACKED, int WRAP>
+int launch_sos_t(const IirArgs &a, cudaStream_t s) {
+    const long long VC = (long long)a.C * a.P;
+    const int warps_per_block = 8;
+    const long long warps = (VC + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + warps_per_block - 1) / warps_per_block);
+    const size_t smem = (size_t)warps_per_block * 2 * 32 * 8 * sizeof(float4);
+    auto kern = iir_sos_kernel<NSEC, PACKED, WRAP>;
+    SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, warps_per_block * 32, smem, s>>>(a);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    return SGPU_OK;
+}
+
+template <int NSEC>
+int launch_sos_n(const IirArgs &a, bool packed, int wrap, cudaStream_t s) {
+    if (wrap == 1) return launch_sos_t<NSEC, false, 1>(a, s);
+    if (wrap == 2) return launch_sos_t<NSEC, false, 2>(a, s);
+    return packed ? launch_sos_t<NSEC, true, 0>(a, s) : launch_sos_t<NSEC, false, 0>(a, s);
+}
+
+int launch_sos(const sgpu_iir *f, const IirArgs &a, int wrap, cudaStream_t s) {
+    switch (f->nsec_pad) {
+        case 1: return launch_sos_n<1>(a, f->packed, wrap, s);
+        case 2: return launch_sos_n<2>(a, f->packed, wrap, s);
+        case 4: return launch_sos_n<4>(a, f->packed, wrap, s);
+        case 8: return launch_sos_n<8>(a, f->packed, wrap, s);
+        case 16: return launch_sos_n<16>(a, f->packed, wrap, s);
+    }
+    return fail(SGPU_ERR_UNSUPPORTED, "unsupported section count");
+}
+
+int ensure_scan_scratch(sgpu_iir *f, size_t vc, size_t units, long long Lc, long long CH) {
+    const int D = 2 * f->nsec_pad;
+    if (vc > f->scratch_vc) {
+        if (f->d_z) cudaFree(f->d_z);
+        if (f->d_s) cudaFree(f->d_s);
+        f->d_z = f->d_s = nullptr;
+        f->scratch_vc = 0;
+        SGPU_CUDA(cudaMalloc(&f->d_z, vc * D * sizeof(float2)));
+        SGPU_CUDA(cudaMalloc(&f->d_s, vc * D * sizeof(float2)));
+        f->scratch_vc = vc;
+    }
+    if (units > f->scratch_units) {
+        if (f->d_gagg) cudaFree(f->d_gagg);
+        if (f->d_Sg) cudaFree(f->d_Sg);
+        f->d_gagg = f->d_Sg = nullptr;
+        f->scratch_units = 0;
+        SGPU_CUDA(cudaMalloc(&f->d_gagg, units * D * sizeof(double2)));
+        SGPU_CUDA(cudaMalloc(&f->d_Sg, units * D * sizeof(double2)));
+        f->scratch_units = units;
+    }
+    if (!f->d_mat) SGPU_CUDA(cudaMalloc(&f->d_mat, 2 * (size_t)D * D * sizeof(double)));
+    if (f->mat_Lc != Lc || f->mat_CH != CH) {
+        std::vector<double> A, ALc, AG;
+        build_transition(f, A);
+        mat_pow(A, Lc, ALc, D);
+        mat_pow(ALc, CH, AG, D);
+        SGPU_CUDA(cudaMemcpy(f->d_mat, ALc.data(), (size_t)D * D * sizeof(double), cudaMemcpyHostToDevice));
+        SGPU_CUDA(cudaMemcpy(f->d_mat + (size_t)D * D, AG.data(), (size_t)D * D * sizeof(double),
+                             cudaMemcpyHostToDevice));
+        f->mat_Lc = Lc;
+        f->mat_CH = CH;
+    }
+    return SGPU_OK;
+}
+
+int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, float2 *d_out, long long ostr,
+            cudaStream_t s) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (istr % 2 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (ostr % 2 == 0);
+    if (f->type == SGPU_IIR_NORMAL) {
+        NormalArgs a{};
+        a.in = d_in; a.out = d_out; a.state = f->d_state;
+        a.in_stride = istr; a.out_stride = ostr; a.n_in = n_in;
+        a.C = (int)f->C; a.W = f->W; a.nb = f->nb; a.na1 = f->na - 1;
+        a.wrap = f->wrap; a.factor = (int)f->factor; a.idx0 = (int)f->index;
+        for (int i = 0; i < f->nb; ++i) a.b[i] = (float)f->num_norm[i];
+        for (int i = 0; i < f->na - 1; ++i) a.a[i] = (float)f->den_norm[i];
+        iir_normal_kernel<<<(unsigned)ceil_div(f->C, 128), 128, 0, s>>>(a);
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+        return SGPU_OK;
+    }
+    IirArgs a{};
+    a.in = d_in; a.out = d_out;
+    a.in_stride = istr; a.out_stride = ostr; a.n_in = n_in;
+    a.C = (int)f->C; a.factor = (int)f->factor; a.idx0 = (int)f->index;
+    a.vec = vec ? 1 : 0;
+    a.k = f->k;
+    // strategy: scan when there are too few channels to fill the chip and the stream is long
+    const long long target_threads = (long long)f->sm_count * 1024;
+    bool scan = f->wrap == SGPU_IIR_PLAIN &&
+                (f->mode == 1 || (f->mode == -1 && (long long)f->C * 8 <= target_threads && n_in >= 16384));
+    if (!scan) {
+        a.P = 1; a.Lc = n_in;
+        a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
+        return launch_sos(f, a, f->wrap, s);
+    }
+    // ---- chunked scan
+    long long P = ceil_div((size_t)target_threads, f->C);
+    long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)P), kTile);
+    if (Lc < 256) Lc = 256;
+    const long long P_real = (n_in + Lc - 1) / Lc;
+    P = (long long)round_up((size_t)P_real, 32);
+    const long long CH = 256;
+    const long long G = (P + CH - 1) / CH;
+    const int D = 2 * f->nsec_pad;
+    int st = ensure_scan_scratch(f, (size_t)f->C * P, (size_t)f->C * G, Lc, CH);
+    if (st) return st;
+    a.P = (int)P; a.Lc = Lc;
+    // pass A: zero-state end states
+    a.state_in = nullptr; a.state_out = f->d_z; a.write_out = 0;
+    st = launch_sos(f, a, 0, s);
+    if (st) return st;
+    // carries
+    if (G > 1) {
+        const int units = (int)(f->C * G);
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(0, f->d_mat, D, f->d_z, f->d_gagg, nullptr,
+                                                                         nullptr, nullptr, (int)P, (int)CH, (int)G, units);
+        SGPU_LAUNCH_CHECK();
+        carry_kernel<<<(unsigned)ceil_div(f->C, 4), 128, 0, s>>>(1, f->d_mat + (size_t)D * D, D, nullptr, f->d_gagg,
+                                                                 f->d_Sg, nullptr, f->d_state, (int)P, (int)CH, (int)G,
+                                                                 (int)f->C);
+        SGPU_LAUNCH_CHECK();
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, f->d_Sg,
+                                                                         f->d_s, f->d_state, (int)P, (int)CH, (int)G, units);
+        SGPU_LAUNCH_CHECK();
+        count_launch(3);
+    } else {
+        const int units = (int)f->C;
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, nullptr,
+                                                                         f->d_s, f->d_state, (int)P, (int)CH, 1, units);
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+    }
+    // pass C: true start states, outputs, end states
+    a.state_in = f->d_s; a.state_out = f->d_z; a.write_out = 1;
+    st = launch_sos(f, a, 0, s);
+    if (st) return st;
+    // the handle's new state = end state of the last non-empty chunk of every channel
+    SGPU_CUDA(cudaMemcpy2DAsync(f->d_state, (size_t)D * sizeof(float2), f->d_z + (size_t)(P_real - 1) * D,
+                                (size_t)P * D * sizeof(float2), (size_t)D * sizeof(float2), f->C,
+                                cudaMemcpyDeviceToDevice, s));
+    return SGPU_OK;
+}
+
+}  // namespace
+
+SGPU_EXPORT int sgpu_iir_create(sgpu_iirtype type, const double *ff, size_t n_ff, const double *fb, size_t n_fb,
+                                size_t n_channels, sgpu_iirwrap wrap, size_t factor, sgpu_iir **out) {
+    if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (wrap != SGPU_IIR_PLAIN) {  // iir/decim.rs:31-41, iir/interp.rs:30-40
+        if (n_ff == 0) return fail(SGPU_ERR_IIR_NUMERATOR_LENGTH_ZERO, "IIR Filter Error NumeratorLengthZero");
+        if (n_fb == 0) return fail(SGPU_ERR_IIR_DENOMINATOR_LENGTH_ZERO, "IIR Filter Error DenominatorLengthZero");
+        if (factor < 1)
+            return wrap == SGPU_IIR_DECIMATING
+                       ? fail(SGPU_ERR_IIR_DECIMATION_LESS_THAN_ONE, "IIR Filter Error DecimationLessThanOne")
+                       : fail(SGPU_ERR_IIR_INTERPOLATION_LESS_THAN_ONE, "IIR Filter Error InterpolationLessThanOne");
+    }
+    if (type == SGPU_IIR_NORMAL) {  // iir/mod.rs:99-103
+        if (n_ff == 0) return fail(SGPU_ERR_IIR_NUMERATOR_LENGTH_ZERO, "IIR Filter Error NumeratorLengthZero");
+        if (n_fb == 0) return fail(SGPU_ERR_IIR_DENOMINATOR_LENGTH_ZERO, "IIR Filter Error DenominatorLengthZero");
+    } else {  // iir/mod.rs:132-142
+        if (n_ff != n_fb) return fail(SGPU_ERR_IIR_SOS_SIZE_MISMATCH, "IIR Filter Error SecondOrderSectionSizeMismatch");
+        if (n_ff == 0) return fail(SGPU_ERR_IIR_SOS_SIZE_ZERO, "IIR Filter Error SecondOrderSectionSizeZero");
+        if (n_ff % 3 != 0)
+            return fail(SGPU_ERR_IIR_SOS_SIZE_NOT_MULTIPLE_OF_3, "IIR Filter Error SecondOrderSectionSizeNotMultpleOf3");
+    }
+    if (!ff || !fb) return fail(SGPU_ERR_INVALID_ARGUMENT, "null coefficients");
+    if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels == 0");
+    if (type == SGPU_IIR_SECOND_ORDER && n_ff / 3 > (size_t)kMaxSec)
+        return fail(SGPU_ERR_UNSUPPORTED, "more than %d second-order sections", kMaxSec);
+    if (type == SGPU_IIR_NORMAL && (n_ff > (size_t)kMaxOrder || n_fb > (size_t)kMaxOrder))
+        return fail(SGPU_ERR_UNSUPPORTED, "Normal-mode order above %d", kMaxOrder);
+    int dev = 0, sms = 0;
+    int st = require_device(&dev, &sms);
+    if (st) return st;
+    sgpu_iir *f = new (std::nothrow) sgpu_iir();
+    if (!f) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    f->device = dev;
+    f->sm_count = sms;
+    f->type = type;
+    f->wrap = wrap;
+    f->factor = wrap == SGPU_IIR_PLAIN ? 1 : factor;
+    f->C = n_channels;
+    f->packed = iir_packed_default();
+    f->ff_raw.assign(ff, ff + n_ff);
+    f->fb_raw.assign(fb, fb + n_fb);
+    if (type == SGPU_IIR_SECOND_ORDER) {
+        f->nsec = (int)(n_ff / 3);
+        f->nsec_pad = pad_sections(f->nsec);
+        f->kd.assign((size_t)f->nsec * 5, 0.0);
+        for (int s = 0; s < kMaxSec; ++s) {  // identity padding: y = x
+            f->k.b0[s] = 1.f; f->k.b1[s] = 0.f; f->k.b2[s] = 0.f; f->k.na1[s] = 0.f; f->k.na2[s] = 0.f;
+        }
+        for (int s = 0; s < f->nsec; ++s) {
+            const double a0 = fb[3 * s];  // sos.rs:62-68
+            const float b0 = (float)(ff[3 * s] / a0), b1 = (float)(ff[3 * s + 1] / a0), b2 = (float)(ff[3 * s + 2] / a0);
+            const float a1 = (float)(fb[3 * s + 1] / a0), a2 = (float)(fb[3 * s + 2] / a0);
+            f->k.b0[s] = b0; f->k.b1[s] = b1; f->k.b2[s] = b2; f->k.na1[s] = -a1; f->k.na2[s] = -a2;
+            f->kd[s * 5 + 0] = b0; f->kd[s * 5 + 1] = b1; f->kd[s * 5 + 2] = b2;
+            f->kd[s * 5 + 3] = a1; f->kd[s * 5 + 4] = a2;
+        }
+    } else {
+        f->nb = (int)n_ff;
+        f->na = (int)n_fb;
+        f->W = (int)(n_fb > n_ff ? n_fb : n_ff);  // iir/mod.rs:105-109
+        const double a0 = fb[0];
+        for (size_t i = 0; i < n_ff; ++i) f->num_norm.push_back(ff[i] / a0);
+        for (size_t i = 1; i < n_fb; ++i) f->den_norm.push_back(fb[i] / a0);
+    }
+    const size_t sb = n_channels * state_len_dev(f) * sizeof(float2);
+    if (cudaMalloc(&f->d_state, sb) != cudaSuccess) {
+        sgpu_iir_destroy(f);
+        return fail(SGPU_ERR_CUDA, "cudaMalloc(iir state %zu bytes) failed", sb);
+    }
+    cudaMemset(f->d_state, 0, sb);
+    *out = f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_iir_destroy(sgpu_iir *f) {
+    if (!f) return SGPU_OK;
+    DeviceGuard g(f->device);
+    if (f->d_state) cudaFree(f->d_state);
+    if (f->d_z) cudaFree(f->d_z);
+    if (f->d_s) cudaFree(f->d_s);
+    if (f->d_gagg) cudaFree(f->d_gagg);
+    if (f->d_Sg) cudaFree(f->d_Sg);
+    if (f->d_mat) cudaFree(f->d_mat);
+    f->stage.release();
+    delete f;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT size_t sgpu_iir_out_len(const sgpu_iir *f, size_t n_in) {
+    if (!f) return 0;
+    if (f->wrap == SGPU_IIR_DECIMATING) return (size_t)((f->index + n_in) / f->factor);
+    if (f->wrap == SGPU_IIR_INTERPOLATING) return n_in * f->factor;
+    return n_in;
+}
+SGPU_EXPORT size_t sgpu_iir_sections(const sgpu_iir *f) { return f ? (size_t)f->nsec : 0; }
+SGPU_EXPORT size_t sgpu_iir_channels(const sgpu_iir *f) { return f ? f->C : 0; }
+SGPU_EXPORT int sgpu_iir_type(const sgpu_iir *f) { return f ? f->type : -1; }
+SGPU_EXPORT size_t sgpu_iir_state_len(const sgpu_iir *f) {
+    if (!f) return 0;
+    return f->type == SGPU_IIR_SECOND_ORDER ? (size_t)f->nsec * 2 : (size_t)f->W;
+}
+SGPU_EXPORT int sgpu_iir_set_mode(sgpu_iir *f, int mode) {
+    if (!f || mode < -1 || mode > 1) return fail(SGPU_ERR_INVALID_ARGUMENT, "bad mode");
+    f->mode = mode;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_iir_numerator_coefs(const sgpu_iir *f, double *out, size_t *n) {
+    if (!f || !n) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    const std::vector<double> &v = f->type == SGPU_IIR_SECOND_ORDER ? f->ff_raw : f->num_norm;
+    if (out)
+        for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    *n = v.size();
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_iir_denominator_coefs(const sgpu_iir *f, double *out, size_t *n) {
+    if (!f || !n) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    const std::vector<double> &v = f->type == SGPU_IIR_SECOND_ORDER ? f->fb_raw : f->den_norm;
+    if (out)
+        for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    *n = v.size();
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_iir_execute_block(sgpu_iir *f, const float *in, size_t n_in, size_t in_stride, float *out,
+                                       size_t out_stride, size_t *n_out_p, sgpu_mem mem, void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t n_out = sgpu_iir_out_len(f, n_in);
+    if (n_out_p) *n_out_p = n_out;
+    if (n_in == 0) return SGPU_OK;
+    if (!in || (n_out && !out)) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
+    if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    float2 *d_out = reinterpret_cast<float2 *>(out);
+    long long istr = (long long)in_stride, ostr = (long long)out_stride;
+    if (mem == SGPU_HOST) {
+        int st = f->stage.ensure(f->C * n_in * sizeof(float2), f->C * (n_out ? n_out : 1) * sizeof(float2));
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        d_out = (float2 *)f->stage.out;
+        istr = (long long)n_in;
+        ostr = (long long)(n_out ? n_out : 1);
+    }
+    int st = iir_run(f, d_in, (long long)n_in, istr, d_out, ostr, s);
+    if (st) return st;
+    if (f->wrap == SGPU_IIR_DECIMATING) f->index = (f->index + n_in) % f->factor;  // iir/decim.rs:225
+    if (mem == SGPU_HOST) {
+        if (n_out)
+            SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
+                                        n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
+        SGPU_CUDA(cudaStreamSynchronize(s));
+    }
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_iir_get_state(sgpu_iir *f, float *state, uint64_t *index) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    if (state) {
+        SGPU_CUDA(cudaDeviceSynchronize());
+        const size_t api = sgpu_iir_state_len(f), dev = state_len_dev(f);
+        SGPU_CUDA(cudaMemcpy2D(state, api * sizeof(float2), f->d_state, dev * sizeof(float2), api * sizeof(float2),
+                               f->C, cudaMemcpyDeviceToHost));
+    }
+    if (index) *index = f->index;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_iir_set_state(sgpu_iir *f, const float *state, uint64_t index) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    if (state) {
+        SGPU_CUDA(cudaDeviceSynchronize());
+        const size_t api = sgpu_iir_state_len(f), dev = state_len_dev(f);
+        SGPU_CUDA(cudaMemset(f->d_state, 0, f->C * dev * sizeof(float2)));
+        SGPU_CUDA(cudaMemcpy2D(f->d_state, dev * sizeof(float2), state, api * sizeof(float2), api * sizeof(float2),
+                               f->C, cudaMemcpyHostToDevice));
+    }
+    f->index = f->wrap == SGPU_IIR_DECIMATING ? index % f->factor : 0;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_iir_reset(sgpu_iir *f) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard g(f->device);
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemset(f->d_state, 0, f->C * state_len_dev(f) * sizeof(float2)));
+    f->index = 0;
+    return SGPU_OK;
+}
+SGPU_EXPORT int sgpu_iir_clone(const sgpu_iir *f, sgpu_iir **out) {
+    if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(f->device);
+    sgpu_iir *c = nullptr;
+    int st = sgpu_iir_create((sgpu_iirtype)f->type, f->ff_raw.data(), f->ff_raw.size(), f->fb_raw.data(),
+                             f->fb_raw.size(), f->C, (sgpu_iirwrap)f->wrap, f->factor, &c);
+    if (st) return st;
+    SGPU_CUDA(cudaDeviceSynchronize());
+    SGPU_CUDA(cudaMemcpy(c->d_state, f->d_state, f->C * state_len_dev(f) * sizeof(float2), cudaMemcpyDeviceToDevice));
+    c->index = f->index;
+    c->mode = f->mode;
+    *out = c;
+    return SGPU_OK;
+}
