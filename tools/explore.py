@@ -12,7 +12,10 @@ sys.path.insert(0, ".")
 from solid_dsp_b200 import _ffi  # noqa: E402
 
 
-def ev_time(fn, reps=5, warm=2):
+def ev_time(fn, reps=None, warm=None):
+    import os
+    reps = int(os.environ.get('EXPLORE_REPS', 5)) if reps is None else reps
+    warm = int(os.environ.get('EXPLORE_WARM', 2)) if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
