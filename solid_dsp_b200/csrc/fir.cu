@@ -39,6 +39,16 @@ __device__ __forceinline__ float2 fetch_sample(const float2 *__restrict__ x,
     return h >= 0 ? hist[h] : make_float2(0.f, 0.f);
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // --------------------------------------------------------------------------------------------
 // FIR (M1 = true) and decimating FIR.  Block = NT threads, tile = NT*R outputs of one channel.
 // Output m of this call is produced by input n_m = m*M + (M-1-c0); with k = q*M + p,
@@ -74,50 +84,56 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const long long i_lo = (m_base - Qpad) * M - a.c0;
     const int total_pairs = rows * R * M / 2;
     if constexpr (M1) {
+        // asynchronous (LDGSTS) for everything inside the input; history / edges take the guarded path
         for (int pe = tid; pe < total_pairs; pe += NT) {
             const long long i = i_lo + 2 * pe;
-            float4 v;
-            if (a.vec_in && i >= 0 && i + 1 < a.n_in) {
-                v = *reinterpret_cast<const float4 *>(x + i);
+            const int rho = pe / (R / 2), jj = pe % (R / 2);
+            float4 *dst = smem + jj * RS + rho;
+            if (i >= 0 && i + 1 < a.n_in) {
+                if (a.vec_in) {
+                    cp_async16(dst, x + i);
+                } else {
+                    cp_async8(dst, x + i);
+                    cp_async8(reinterpret_cast<float2 *>(dst) + 1, x + i + 1);
+                }
             } else {
                 const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
                 const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
-                v = make_float4(s0.x, s0.y, s1.x, s1.y);
+                *dst = make_float4(s0.x, s0.y, s1.x, s1.y);
             }
-            const int rho = pe / (R / 2), jj = pe % (R / 2);
-            smem[jj * RS + rho] = v;
         }
     } else {
         int e = 2 * tid;
         int q = e / M, rem = e - q * M;
         const int qs = (2 * NT) / M, rs = (2 * NT) - qs * M;
         const bool lo_even = (i_lo & 1) == 0;
+        (void)lo_even;
         for (int pe = tid; pe < total_pairs; pe += NT) {
             const long long i = i_lo + 2 * pe;
-            float2 s0, s1;
-            if (a.vec_in && lo_even && i >= 0 && i + 1 < a.n_in) {
-                const float4 v = *reinterpret_cast<const float4 *>(x + i);
-                s0 = make_float2(v.x, v.y);
-                s1 = make_float2(v.z, v.w);
-            } else {
-                s0 = fetch_sample(x, hist, i, a.n_in, a.T);
-                s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
-            }
+            float2 *d0, *d1;
             {
                 const int p = M - 1 - rem, rho = q / R, j = q % R;
-                reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho)[j & 1] = s0;
+                d0 = reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho) + (j & 1);
             }
             {
                 int q1 = q, rem1 = rem + 1;
                 if (rem1 == M) { rem1 = 0; q1++; }
                 const int p = M - 1 - rem1, rho = q1 / R, j = q1 % R;
-                reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho)[j & 1] = s1;
+                d1 = reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + rho) + (j & 1);
+            }
+            if (i >= 0 && i + 1 < a.n_in) {  // the de-interleave rides on 8-byte LDGSTS
+                cp_async8(d0, x + i);
+                cp_async8(d1, x + i + 1);
+            } else {
+                *d0 = fetch_sample(x, hist, i, a.n_in, a.T);
+                *d1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
             }
             q += qs;
             rem += rs;
             if (rem >= M) { rem -= M; q++; }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- compute
@@ -187,17 +203,22 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const int total_pairs = rows * R / 2;
     for (int pe = tid; pe < total_pairs; pe += NT) {
         const long long i = i_lo + 2 * pe;
-        float4 v;
-        if (a.vec_in && i >= 0 && i + 1 < a.n_in) {
-            v = *reinterpret_cast<const float4 *>(x + i);
+        const int rho = pe / (R / 2), jj = pe % (R / 2);
+        float4 *dst = smem + jj * RS + rho;
+        if (i >= 0 && i + 1 < a.n_in) {
+            if (a.vec_in) {
+                cp_async16(dst, x + i);
+            } else {
+                cp_async8(dst, x + i);
+                cp_async8(reinterpret_cast<float2 *>(dst) + 1, x + i + 1);
+            }
         } else {
             const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
             const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
-            v = make_float4(s0.x, s0.y, s1.x, s1.y);
+            *dst = make_float4(s0.x, s0.y, s1.x, s1.y);
         }
-        const int rho = pe / (R / 2), jj = pe % (R / 2);
-        smem[jj * RS + rho] = v;
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const int row0 = HR + tid;
