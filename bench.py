@@ -231,14 +231,13 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from solid_dsp_b200 import _ffi, launch_count
+    from solid_dsp_b200 import _ffi, launch_count, sharding
     from solid_dsp_b200.filter.fir import DecimatingFIRFilter, FIRFilter, InterpolatingFIRFilter
     from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
 
     name = args.workload
     W = WORKLOADS[name]
     taps = workload_taps(name)
-    first, count = _ffi.c_size(), _ffi.c_size()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
 
@@ -250,8 +249,7 @@ def run_gpu_arm(args):
     halo_prev = None
     if name == "fir":
         n_total = 1 << args.log2_samples
-        _ffi.check(_ffi.lib.sgpu_shard_stream(n_total, 1, world, rank, C.byref(first), C.byref(count)))
-        n_loc = count.value
+        _, n_loc = sharding.shard_stream(n_total, 1, world, rank)
         x = rand_c((n_loc,))
         filt = FIRFilter(taps, 1.0)
         T = len(taps)
@@ -261,14 +259,7 @@ def run_gpu_arm(args):
 
         def step():
             # halo: last T-1 samples of the previous rank's segment (rank 0: zeros = fresh filter)
-            if world > 1:
-                ops = []
-                if rank + 1 < world:
-                    ops.append(dist.P2POp(dist.isend, x[-(T - 1):], rank + 1))
-                if rank > 0:
-                    ops.append(dist.P2POp(dist.irecv, halo_prev, rank - 1))
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
+            sharding.exchange_halo(x, halo_prev, rank, world, dist)
             filt.write(halo_prev)
             return filt.execute_block(x)
     else:
@@ -280,8 +271,7 @@ def run_gpu_arm(args):
             c_loc = 1  # does not shard: replicas only
             units_total = n_per * world
         else:
-            _ffi.check(_ffi.lib.sgpu_shard_channels(chans, world, rank, C.byref(first), C.byref(count)))
-            c_loc = count.value
+            _, c_loc = sharding.shard_channels(chans, world, rank)
             units_total = chans * n_per * (4 if name == "interp" else 1)
         x = rand_c((c_loc, n_per))
         if name == "decim":

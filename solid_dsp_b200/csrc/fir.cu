@@ -55,21 +55,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   y[m] = scale * sum_p sum_q g[q*M+p] * x[(m-q)*M + (M-1-c0) - p]
 // i.e. M short FIRs (taps g_p[q]) over the phase sequences x_p[m'] = x[m'*M + (M-1-c0) - p],
 // which the loader de-interleaves into M shared-memory planes.
-template <int R, bool PACKED, bool M1, int NT, int MINB>
+//
+// PS = phase split: PS adjacent lanes share one run of R outputs and each walks M/PS of the phase
+// planes; their partial sums meet in a warp-shuffle butterfly.  This keeps R = 16 (one LDS.128 per
+// 16 complex MACs) while a tile needs only NT/PS * R * M input samples of shared memory, so 3-6
+// blocks of 4 warps stay resident per SM and tile loads overlap other blocks' arithmetic.
+template <int R, bool PACKED, bool M1, int NT, int MINB, int PS>
 __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
+    static_assert(M1 ? PS == 1 : true, "the plain FIR has a single phase");
     const int tid = threadIdx.x;
     const int M = M1 ? 1 : a.M;
     const int Qpad = a.Qpad;
     const int HR = Qpad / R;
-    const int rows = HR + NT;
+    constexpr int OT = NT / PS;  // output-owning thread groups per block
+    const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;  // +1: consecutive planes are skewed by 16 bytes
     constexpr int TW = PACKED ? 2 : 1;
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)M * plane_f4);
 
     const int ch = blockIdx.y;
-    const long long m_base = (long long)blockIdx.x * (NT * R);
+    const long long m_base = (long long)blockIdx.x * (OT * R);
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
 
@@ -102,12 +109,38 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
                 *dst = make_float4(s0.x, s0.y, s1.x, s1.y);
             }
         }
+    } else if (NT % (R * M) == 0) {
+        // Fast de-interleave: R*M consecutive input samples form one row of every phase plane and
+        // NT is a multiple of that, so a thread keeps its (phase, position-in-row) for the whole
+        // tile and only walks down the rows: one LDGSTS.64 plus two adds per sample.
+        const int rm = R * M;
+        const int e_in = tid % rm;
+        const int rem = e_in % M, j = e_in / M;
+        const int row_step = NT / rm;
+        const int p = M - 1 - rem;
+        float2 *dst = reinterpret_cast<float2 *>(smem + (size_t)p * plane_f4 + (j >> 1) * RS + tid / rm) + (j & 1);
+        const long long total = (long long)rows * rm;
+        const bool interior = i_lo >= 0 && i_lo + total <= a.n_in;
+        if (interior) {
+            const float2 *src = x + i_lo + tid;
+            for (int rho = tid / rm; rho < rows; rho += row_step) {
+                cp_async8(dst, src);
+                dst += 2 * row_step;  // next row = next float4 of the plane
+                src += NT;
+            }
+        } else {
+            long long i = i_lo + tid;
+            for (int rho = tid / rm; rho < rows; rho += row_step) {
+                if (i >= 0 && i < a.n_in) cp_async8(dst, x + i);
+                else *dst = fetch_sample(x, hist, i, a.n_in, a.T);
+                dst += 2 * row_step;
+                i += NT;
+            }
+        }
     } else {
         int e = 2 * tid;
         int q = e / M, rem = e - q * M;
         const int qs = (2 * NT) / M, rs = (2 * NT) - qs * M;
-        const bool lo_even = (i_lo & 1) == 0;
-        (void)lo_even;
         for (int pe = tid; pe < total_pairs; pe += NT) {
             const long long i = i_lo + 2 * pe;
             float2 *d0, *d1;
@@ -140,22 +173,38 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     float2 acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-    const int row0 = HR + tid;
+    const int ot = tid / PS, part = tid % PS;
+    const int row0 = HR + ot;
     const int npairs = Qpad / (2 * R);
-    for (int p = 0; p < M; ++p)
-        fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * Qpad * TW,
-                            npairs);
+    const int Mp = (M + PS - 1) / PS;  // phases per lane of a split group (contiguous block)
+    for (int sidx = 0; sidx < Mp; ++sidx) {
+        const int p = part * Mp + sidx;
+        if (p < M)
+            fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * Qpad * TW,
+                                npairs);
+    }
+    if constexpr (PS > 1) {  // butterfly over the PS lanes of a group: everyone ends with the full sums
+#pragma unroll
+        for (int o = 1; o < PS; o <<= 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
+                acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
+            }
+        }
+    }
 
     // ---- epilogue: scale (fir/mod.rs:211), stage through plane 0, coalesced store
     __syncthreads();
     const float s = a.scale_re;
 #pragma unroll
     for (int jj = 0; jj < R / 2; ++jj)
-        smem[jj * RS + tid] = make_float4(acc[2 * jj].x * s, acc[2 * jj].y * s, acc[2 * jj + 1].x * s,
-                                          acc[2 * jj + 1].y * s);
+        if (jj / (R / 2 / PS) == part)  // each lane of a group stages its share of the run
+            smem[jj * RS + ot] = make_float4(acc[2 * jj].x * s, acc[2 * jj].y * s, acc[2 * jj + 1].x * s,
+                                             acc[2 * jj + 1].y * s);
     __syncthreads();
     float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
-    for (int idx = tid; idx < NT * R / 2; idx += NT) {
+    for (int idx = tid; idx < OT * R / 2; idx += NT) {
         const int rho = idx / (R / 2), jj = idx % (R / 2);
         const long long o = m_base + (long long)rho * R + 2 * jj;
         if (o >= a.n_out) continue;
@@ -173,14 +222,16 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
 // Interpolator: y[n*L + p] = sum_{j<S} hp[p][j] * x[n-j], hp[p][j] = hpad[p + (S-1-j)*L].
 // One input plane, L tap sets; a thread runs the L phases one after the other over the same
 // R input positions and stages the interleaved outputs in shared memory.  a.M carries L.
-template <int R, bool PACKED, int NT, int MINB>
+// PS adjacent lanes share one run of R input positions and split the L output phases.
+template <int R, bool PACKED, int NT, int MINB, int PS>
 __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
     const int L = a.M;
     const int Qpad = a.Qpad;
     const int HR = Qpad / R;
-    const int rows = HR + NT;
+    constexpr int OT = NT / PS;
+    const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;
     constexpr int TW = PACKED ? 2 : 1;
@@ -189,9 +240,9 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * Qpad * TW);
 
     const int ch = blockIdx.y;
-    const long long n_base = (long long)blockIdx.x * (NT * R);
+    const long long n_base = (long long)blockIdx.x * (OT * R);
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
-    const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T = S here
+    const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T - 1 = S samples kept
 
     {
         const int n4 = L * Qpad * TW / 4;
@@ -221,10 +272,14 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     cp_async_wait_all();
     __syncthreads();
 
-    const int row0 = HR + tid;
+    const int ot = tid / PS, part = tid % PS;
+    const int row0 = HR + ot;
     const int npairs = Qpad / (2 * R);
-    float2 *my = stage + (size_t)tid * (R * L + 1);
-    for (int p = 0; p < L; ++p) {
+    float2 *my = stage + (size_t)ot * (R * L + 1);
+    const int Lp = (L + PS - 1) / PS;
+    for (int sidx = 0; sidx < Lp; ++sidx) {
+        const int p = part * Lp + sidx;
+        if (p >= L) break;
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
@@ -236,11 +291,12 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
     const int per_thread = R * L;
     const long long o_base = n_base * L;
-    for (int idx = tid; idx < NT * per_thread; idx += NT) {
-        const long long o = o_base + idx;
-        if (o >= a.n_out) break;
-        const int t = idx / per_thread;
-        y[o] = stage[idx + t];
+    // warp w drains the runs of groups w, w+NT/32, ...: 32 lanes stride over one run's R*L outputs
+    for (int g = tid >> 5; g < OT; g += NT / 32) {
+        const float2 *run = stage + (size_t)g * (per_thread + 1);
+        const long long og = o_base + (long long)g * per_thread;
+        for (int k = tid & 31; k < per_thread; k += 32)
+            if (og + k < a.n_out) y[og + k] = run[k];
     }
 }
 
@@ -292,9 +348,12 @@ using namespace sgpu;
 namespace {
 
 constexpr int kR = 16;
-constexpr int kNT_FIR = 128;
-constexpr int kNT_DEC = 64;
-constexpr int kNT_INT = 64;
+constexpr int kNT = 128;  // 4 warps per block: one per SM sub-partition
+
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 bool packed_default() {
     static int v = -1;
@@ -478,29 +537,39 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     const int tw = f->packed ? 2 : 1;
     if (n_out > 0) {
         const bool m1 = f->M == 1;
-        const int NT = m1 ? kNT_FIR : kNT_DEC;
-        const int rows = f->Qpad / kR + NT;
+        // phase split: as many lanes per output run as there are phases to share, up to 4
+        int PS = m1 ? 1 : (f->M >= 4 ? 4 : (f->M >= 2 ? 2 : 1));
+        const int want = env_int("SGPU_DEC_PS", 0);
+        if (!m1 && (want == 1 || want == 2 || want == 4) && want <= (int)f->M) PS = want;
+        const int OT = kNT / PS;
+        const int rows = f->Qpad / kR + OT;
         a.RS = rows | 1;
         const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
         const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * f->Qpad * tw * sizeof(float);
         if (smem > (size_t)kMaxSmem)
             return fail(SGPU_ERR_UNSUPPORTED, "filter too long for one shared-memory tile (%zu bytes needed)", smem);
-        const long long tiles = (n_out + (long long)NT * kR - 1) / ((long long)NT * kR);
+        const long long tiles = (n_out + (long long)OT * kR - 1) / ((long long)OT * kR);
         dim3 grid((unsigned)tiles, (unsigned)f->C);
         int st;
-#define LAUNCH_FIR(PK, M1, NTV, MINB)                                                       \
+#define LAUNCH_FIR(PK, M1, MINB, PSV)                                                       \
     do {                                                                                    \
-        auto kern = fir_decim_kernel<kR, PK, M1, NTV, MINB>;                                \
+        auto kern = fir_decim_kernel<kR, PK, M1, kNT, MINB, PSV>;                           \
         st = set_smem(kern, smem);                                                          \
         if (st) return st;                                                                  \
-        kern<<<grid, NTV, smem, s>>>(a);                                                    \
+        kern<<<grid, kNT, smem, s>>>(a);                                                    \
     } while (0)
         if (m1) {
-            if (f->packed) LAUNCH_FIR(true, true, kNT_FIR, 4);
-            else LAUNCH_FIR(false, true, kNT_FIR, 4);
+            if (f->packed) LAUNCH_FIR(true, true, 4, 1);
+            else LAUNCH_FIR(false, true, 4, 1);
+        } else if (PS == 4) {
+            if (f->packed) LAUNCH_FIR(true, false, 4, 4);
+            else LAUNCH_FIR(false, false, 4, 4);
+        } else if (PS == 2) {
+            if (f->packed) LAUNCH_FIR(true, false, 3, 2);
+            else LAUNCH_FIR(false, false, 3, 2);
         } else {
-            if (f->packed) LAUNCH_FIR(true, false, kNT_DEC, 3);
-            else LAUNCH_FIR(false, false, kNT_DEC, 3);
+            if (f->packed) LAUNCH_FIR(true, false, 1, 1);
+            else LAUNCH_FIR(false, false, 1, 1);
         }
 #undef LAUNCH_FIR
         SGPU_LAUNCH_CHECK();
@@ -799,28 +868,35 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->packed ? 2 : 1;
-    const int NT = kNT_INT;
-    const int rows = f->Qpad / kR + NT;
+    int PS = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
+    const int want = env_int("SGPU_INT_PS", 0);
+    if ((want == 1 || want == 2 || want == 4) && want <= (int)f->L) PS = want;
+    const int OT = kNT / PS;
+    const int rows = f->Qpad / kR + OT;
     a.RS = rows | 1;
     const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
     const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)f->Qpad * tw * sizeof(float) +
-                        (size_t)NT * (kR * f->L + 1) * sizeof(float2);
+                        (size_t)OT * (kR * f->L + 1) * sizeof(float2);
     if (smem > (size_t)kMaxSmem)
         return fail(SGPU_ERR_UNSUPPORTED, "interpolator tile needs %zu bytes of shared memory", smem);
-    const long long tiles = ((long long)n_in + (long long)NT * kR - 1) / ((long long)NT * kR);
+    const long long tiles = ((long long)n_in + (long long)OT * kR - 1) / ((long long)OT * kR);
     dim3 grid((unsigned)tiles, (unsigned)f->C);
     int st;
-    if (f->packed) {
-        auto kern = fir_interp_kernel<kR, true, kNT_INT, 4>;
-        st = set_smem(kern, smem);
-        if (st) return st;
-        kern<<<grid, NT, smem, s>>>(a);
+#define LAUNCH_INT(PK, PSV)                                     \
+    do {                                                        \
+        auto kern = fir_interp_kernel<kR, PK, kNT, 4, PSV>;     \
+        st = set_smem(kern, smem);                              \
+        if (st) return st;                                      \
+        kern<<<grid, kNT, smem, s>>>(a);                        \
+    } while (0)
+    if (PS == 4) {
+        if (f->packed) LAUNCH_INT(true, 4); else LAUNCH_INT(false, 4);
+    } else if (PS == 2) {
+        if (f->packed) LAUNCH_INT(true, 2); else LAUNCH_INT(false, 2);
     } else {
-        auto kern = fir_interp_kernel<kR, false, kNT_INT, 4>;
-        st = set_smem(kern, smem);
-        if (st) return st;
-        kern<<<grid, NT, smem, s>>>(a);
+        if (f->packed) LAUNCH_INT(true, 1); else LAUNCH_INT(false, 1);
     }
+#undef LAUNCH_INT
     SGPU_LAUNCH_CHECK();
     count_launch();
     st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->S, s);

@@ -1,0 +1,45 @@
+"""Multi-GPU partitioning of the filtering path.  One process per GPU.
+
+  * independent channels (decimator / interpolator / batched IIR): contiguous channel ranges, no
+    data-path collective at all;
+  * one long FIR stream: contiguous time segments; rank r > 0 needs the T-1 samples that precede
+    its segment (the "halo") -- one tiny point-to-point message per boundary per step.  For a
+    decimator the segment starts are multiples of M so every rank starts at decimator phase 0.
+
+The arithmetic lives in the C ABI (sgpu_shard_channels / sgpu_shard_stream); the exchange uses
+torch.distributed point-to-point ops so the same code runs over NCCL (GPU) and gloo (CPU tests)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _ffi
+
+
+def shard_channels(n_channels: int, world: int, rank: int):
+    first, count = _ffi.c_size(), _ffi.c_size()
+    _ffi.check(_ffi.lib.sgpu_shard_channels(n_channels, world, rank, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+def shard_stream(n_samples: int, align: int, world: int, rank: int):
+    first, count = _ffi.c_size(), _ffi.c_size()
+    _ffi.check(_ffi.lib.sgpu_shard_stream(n_samples, align, world, rank, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+def exchange_halo(x_local, halo_out, rank: int, world: int, dist):
+    """Send the last len(halo_out) samples of this rank's segment to rank+1 and receive the
+    previous rank's tail into halo_out (rank 0 keeps halo_out as is: the filter's own history).
+    x_local / halo_out are 1-D complex64 torch tensors on the communicator's device."""
+    if world == 1:
+        return halo_out
+    h = halo_out.shape[0]
+    ops = []
+    if rank + 1 < world:
+        tail = x_local[-h:].contiguous()
+        ops.append(dist.P2POp(dist.isend, tail, rank + 1))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, halo_out, rank - 1))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return halo_out
