@@ -61,6 +61,65 @@ void Staging::release() {
     in_bytes = out_bytes = 0;
 }
 
+int HostPipe::ensure(size_t need_in, size_t need_out) {
+    if (!s_in) {
+        SGPU_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        SGPU_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SGPU_CUDA(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
+            SGPU_CUDA(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
+            SGPU_CUDA(cudaEventCreateWithFlags(&e_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (need_in > in_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (d_in[i]) cudaFree(d_in[i]);
+            d_in[i] = nullptr;
+        }
+        in_bytes = 0;
+        for (int i = 0; i < 2; ++i) SGPU_CUDA(cudaMalloc(&d_in[i], need_in));
+        in_bytes = need_in;
+    }
+    if (need_out > out_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (d_out[i]) cudaFree(d_out[i]);
+            d_out[i] = nullptr;
+        }
+        out_bytes = 0;
+        for (int i = 0; i < 2; ++i) SGPU_CUDA(cudaMalloc(&d_out[i], need_out));
+        out_bytes = need_out;
+    }
+    return SGPU_OK;
+}
+
+void HostPipe::release() {
+    for (int i = 0; i < 2; ++i) {
+        if (d_in[i]) cudaFree(d_in[i]);
+        if (d_out[i]) cudaFree(d_out[i]);
+        if (e_in[i]) cudaEventDestroy(e_in[i]);
+        if (e_comp[i]) cudaEventDestroy(e_comp[i]);
+        if (e_out[i]) cudaEventDestroy(e_out[i]);
+        d_in[i] = d_out[i] = nullptr;
+        e_in[i] = e_comp[i] = e_out[i] = nullptr;
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    s_in = s_out = nullptr;
+    in_bytes = out_bytes = 0;
+}
+
+size_t host_chunk_len(size_t C, size_t n_in) {
+    // ~64 MiB of input per chunk: large enough for PCIe efficiency and full-chip kernels, small
+    // enough that the first copy-in and the last copy-out (the un-overlapped ends) stay short
+    size_t target = (size_t)64 << 20;
+    const char *e = getenv("SGPU_HOST_CHUNK_MB");
+    if (e && atoi(e) > 0) target = (size_t)atoi(e) << 20;
+    size_t chunk = target / 8 / (C ? C : 1);
+    if (chunk < 4096) chunk = 4096;
+    chunk = (chunk + 63) / 64 * 64;
+    return chunk < n_in ? chunk : (n_in ? n_in : 1);
+}
+
 }  // namespace sgpu
 
 SGPU_EXPORT int sgpu_abi_version(void) { return SGPU_ABI_VERSION; }

@@ -395,6 +395,7 @@ struct sgpu_fir {
     float2 *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     Staging stage;
+    HostPipe pipe;
 };
 
 static int fir_upload_taps(sgpu_fir *f) {
@@ -464,6 +465,7 @@ SGPU_EXPORT int sgpu_fir_destroy(sgpu_fir *f) {
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     f->stage.release();
+    f->pipe.release();
     delete f;
     return SGPU_OK;
 }
@@ -538,7 +540,7 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     if (n_out > 0) {
         const bool m1 = f->M == 1;
         // phase split: as many lanes per output run as there are phases to share, up to 4
-        int PS = m1 ? 1 : (f->M >= 4 ? 4 : (f->M >= 2 ? 2 : 1));
+        int PS = m1 ? 1 : (f->M >= 2 ? 2 : 1);  // measured: PS=2 beats 1 and 4 at M=8
         const int want = env_int("SGPU_DEC_PS", 0);
         if (!m1 && (want == 1 || want == 2 || want == 4) && want <= (int)f->M) PS = want;
         const int OT = kNT / PS;
@@ -592,32 +594,21 @@ SGPU_EXPORT int sgpu_fir_execute_block(sgpu_fir *f, const float *in, size_t n_in
     if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const float2 *d_in = reinterpret_cast<const float2 *>(in);
-    float2 *d_out = reinterpret_cast<float2 *>(out);
-    long long istr = (long long)in_stride, ostr = (long long)out_stride;
-    if (mem == SGPU_HOST) {
-        const size_t in_b = f->C * n_in * sizeof(float2), out_b = f->C * (n_out ? n_out : 1) * sizeof(float2);
-        int st = f->stage.ensure(in_b, out_b);
+    // one pass over device-resident samples: kernel + history update + phase counter
+    auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,
+                   cudaStream_t st_) -> int {
+        int st = fir_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
         if (st) return st;
-        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
-                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
-        d_in = (const float2 *)f->stage.in;
-        d_out = (float2 *)f->stage.out;
-        istr = (long long)n_in;
-        ostr = (long long)(n_out ? n_out : 1);
-    }
-    int st = fir_launch(f, d_in, (long long)n_in, istr, d_out, ostr, (long long)n_out, s);
-    if (st) return st;
-    st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->T - 1, s);
-    if (st) return st;
-    if (f->is_decim) f->current_item = (f->current_item + n_in) % f->M;  // decim.rs:116
-    if (mem == SGPU_HOST) {
-        if (n_out)
-            SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
-                                        n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
-        SGPU_CUDA(cudaStreamSynchronize(s));
-    }
-    return SGPU_OK;
+        st = enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->T - 1, st_);
+        if (st) return st;
+        if (f->is_decim) f->current_item = (f->current_item + nc) % f->M;  // decim.rs:116
+        return SGPU_OK;
+    };
+    if (mem == SGPU_DEVICE)
+        return run(reinterpret_cast<const float2 *>(in), n_in, (long long)in_stride, reinterpret_cast<float2 *>(out),
+                   (long long)out_stride, n_out, s);
+    return host_pipeline(f->pipe, f->C, in, n_in, in_stride, out, out_stride, 1,
+                         [f](size_t nc) { return sgpu_fir_out_len(f, nc); }, run, s);
 }
 
 SGPU_EXPORT int sgpu_fir_write(sgpu_fir *f, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem,
@@ -710,6 +701,7 @@ struct sgpu_interp {
     float2 *d_hist[2] = {nullptr, nullptr};  // S samples per channel: the PFB window (oldest first)
     int cur = 0;
     Staging stage;
+    HostPipe pipe;
 };
 
 static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S values */) {
@@ -796,6 +788,7 @@ SGPU_EXPORT int sgpu_interp_destroy(sgpu_interp *f) {
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     f->stage.release();
+    f->pipe.release();
     delete f;
     return SGPU_OK;
 }
@@ -823,32 +816,9 @@ SGPU_EXPORT int sgpu_interp_coefficients(const sgpu_interp *f, double *out) {
     return SGPU_OK;
 }
 
-SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_t n_in, size_t in_stride,
-                                          float *out, size_t out_stride, size_t *n_out_p, sgpu_mem mem,
-                                          void *stream) {
-    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
-    const size_t n_out = n_in * f->L;
-    if (n_out_p) *n_out_p = n_out;
-    if (n_in == 0) return SGPU_OK;
-    if (!in || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
-    if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
-    if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
-    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
-    DeviceGuard g(f->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    const float2 *d_in = reinterpret_cast<const float2 *>(in);
-    float2 *d_out = reinterpret_cast<float2 *>(out);
-    long long istr = (long long)in_stride, ostr = (long long)out_stride;
-    if (mem == SGPU_HOST) {
-        int st = f->stage.ensure(f->C * n_in * sizeof(float2), f->C * n_out * sizeof(float2));
-        if (st) return st;
-        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
-                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
-        d_in = (const float2 *)f->stage.in;
-        d_out = (float2 *)f->stage.out;
-        istr = (long long)n_in;
-        ostr = (long long)n_out;
-    }
+namespace {
+int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long istr, float2 *d_out, long long ostr,
+                  long long n_out, cudaStream_t s) {
     FirArgs a{};
     a.in = d_in;
     a.out = d_out;
@@ -858,8 +828,8 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
     a.taps = f->d_taps;
     a.in_stride = istr;
     a.out_stride = ostr;
-    a.n_in = (long long)n_in;
-    a.n_out = (long long)n_out;
+    a.n_in = n_in;
+    a.n_out = n_out;
     a.T = (int)f->S + 1;
     a.M = (int)f->L;
     a.c0 = 0;
@@ -868,7 +838,7 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->packed ? 2 : 1;
-    int PS = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
+    int PS = f->L >= 2 ? 2 : 1;
     const int want = env_int("SGPU_INT_PS", 0);
     if ((want == 1 || want == 2 || want == 4) && want <= (int)f->L) PS = want;
     const int OT = kNT / PS;
@@ -899,14 +869,35 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
 #undef LAUNCH_INT
     SGPU_LAUNCH_CHECK();
     count_launch();
-    st = enqueue_hist_update(d_in, istr, (long long)n_in, f->d_hist, f->cur, f->C, f->S, s);
-    if (st) return st;
-    if (mem == SGPU_HOST) {
-        SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
-                                    n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
-        SGPU_CUDA(cudaStreamSynchronize(s));
-    }
     return SGPU_OK;
+}
+}  // namespace
+
+SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_t n_in, size_t in_stride,
+                                          float *out, size_t out_stride, size_t *n_out_p, sgpu_mem mem,
+                                          void *stream) {
+    if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    const size_t n_out = n_in * f->L;
+    if (n_out_p) *n_out_p = n_out;
+    if (n_in == 0) return SGPU_OK;
+    if (!in || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
+    if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,
+                   cudaStream_t st_) -> int {
+        int st = interp_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
+        if (st) return st;
+        return enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->S, st_);
+    };
+    if (mem == SGPU_DEVICE)
+        return run(reinterpret_cast<const float2 *>(in), n_in, (long long)in_stride, reinterpret_cast<float2 *>(out),
+                   (long long)out_stride, n_out, s);
+    const size_t L = f->L;
+    return host_pipeline(f->pipe, f->C, in, n_in, in_stride, out, out_stride, L,
+                         [L](size_t nc) { return nc * L; }, run, s);
 }
 
 SGPU_EXPORT int sgpu_interp_push(sgpu_interp *f, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem,

@@ -464,6 +464,7 @@ struct sgpu_iir {
     size_t scratch_vc = 0, scratch_units = 0;
     long long mat_Lc = -1, mat_CH = -1;
     Staging stage;
+    HostPipe pipe;
 };
 
 namespace {
@@ -751,6 +752,7 @@ SGPU_EXPORT int sgpu_iir_destroy(sgpu_iir *f) {
     if (f->d_Sg) cudaFree(f->d_Sg);
     if (f->d_mat) cudaFree(f->d_mat);
     f->stage.release();
+    f->pipe.release();
     delete f;
     return SGPU_OK;
 }
@@ -802,29 +804,19 @@ SGPU_EXPORT int sgpu_iir_execute_block(sgpu_iir *f, const float *in, size_t n_in
     if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const float2 *d_in = reinterpret_cast<const float2 *>(in);
-    float2 *d_out = reinterpret_cast<float2 *>(out);
-    long long istr = (long long)in_stride, ostr = (long long)out_stride;
-    if (mem == SGPU_HOST) {
-        int st = f->stage.ensure(f->C * n_in * sizeof(float2), f->C * (n_out ? n_out : 1) * sizeof(float2));
+    auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t /*nout*/,
+                   cudaStream_t st_) -> int {
+        int st = iir_run(f, d_in, (long long)nc, istr, d_out, ostr, st_);
         if (st) return st;
-        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2),
-                                    n_in * sizeof(float2), f->C, cudaMemcpyHostToDevice, s));
-        d_in = (const float2 *)f->stage.in;
-        d_out = (float2 *)f->stage.out;
-        istr = (long long)n_in;
-        ostr = (long long)(n_out ? n_out : 1);
-    }
-    int st = iir_run(f, d_in, (long long)n_in, istr, d_out, ostr, s);
-    if (st) return st;
-    if (f->wrap == SGPU_IIR_DECIMATING) f->index = (f->index + n_in) % f->factor;  // iir/decim.rs:225
-    if (mem == SGPU_HOST) {
-        if (n_out)
-            SGPU_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), d_out, n_out * sizeof(float2),
-                                        n_out * sizeof(float2), f->C, cudaMemcpyDeviceToHost, s));
-        SGPU_CUDA(cudaStreamSynchronize(s));
-    }
-    return SGPU_OK;
+        if (f->wrap == SGPU_IIR_DECIMATING) f->index = (f->index + nc) % f->factor;  // iir/decim.rs:225
+        return SGPU_OK;
+    };
+    if (mem == SGPU_DEVICE)
+        return run(reinterpret_cast<const float2 *>(in), n_in, (long long)in_stride, reinterpret_cast<float2 *>(out),
+                   (long long)out_stride, n_out, s);
+    return host_pipeline(f->pipe, f->C, in, n_in, in_stride, out, out_stride,
+                         f->wrap == SGPU_IIR_INTERPOLATING ? f->factor : 1,
+                         [f](size_t nc) { return sgpu_iir_out_len(f, nc); }, run, s);
 }
 
 SGPU_EXPORT int sgpu_iir_get_state(sgpu_iir *f, float *state, uint64_t *index) {

@@ -51,6 +51,60 @@ struct Staging {
     void release();
 };
 
+// SGPU_HOST convenience path, pipelined: the call is cut into chunks along time; chunk k+1 is copied
+// host->device on one stream while chunk k runs on the caller's stream and chunk k-1 is copied
+// device->host on a third, through two staging buffers per direction owned by the handle.  The
+// per-chunk `run` is the same code the SGPU_DEVICE path executes, so streaming state (history tails,
+// decimator phase, IIR state) carries across chunks exactly as it does across calls.
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+    void *d_in[2] = {nullptr, nullptr};
+    void *d_out[2] = {nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0;
+    int ensure(size_t need_in, size_t need_out);
+    void release();
+};
+
+// chunk length (samples per channel) for a host call of n_in samples on C channels
+size_t host_chunk_len(size_t C, size_t n_in);
+
+template <class OutLen, class Run>
+int host_pipeline(HostPipe &hp, size_t C, const float *in, size_t n_in, size_t in_stride, float *out,
+                  size_t out_stride, size_t max_out_per_in, OutLen out_len, Run run, cudaStream_t s) {
+    const size_t chunk = host_chunk_len(C, n_in);
+    const size_t max_out = chunk * max_out_per_in + 1;
+    int st = hp.ensure(C * chunk * 8, C * max_out * 8);
+    if (st) return st;
+    const float *src = in;
+    size_t out_off = 0;
+    size_t k = 0;
+    for (size_t done = 0; done < n_in; done += chunk, ++k) {
+        const int b = (int)(k & 1);
+        const size_t nc = n_in - done < chunk ? n_in - done : chunk;
+        if (k >= 2) SGPU_CUDA(cudaStreamWaitEvent(hp.s_in, hp.e_comp[b], 0));
+        SGPU_CUDA(cudaMemcpy2DAsync(hp.d_in[b], nc * 8, src + 2 * done, in_stride * 8, nc * 8, C,
+                                    cudaMemcpyHostToDevice, hp.s_in));
+        SGPU_CUDA(cudaEventRecord(hp.e_in[b], hp.s_in));
+        SGPU_CUDA(cudaStreamWaitEvent(s, hp.e_in[b], 0));
+        if (k >= 2) SGPU_CUDA(cudaStreamWaitEvent(s, hp.e_out[b], 0));
+        const size_t nout = out_len(nc);
+        st = run(reinterpret_cast<const float2 *>(hp.d_in[b]), nc, (long long)nc,
+                 reinterpret_cast<float2 *>(hp.d_out[b]), (long long)(nout ? nout : 1), nout, s);
+        if (st) return st;
+        SGPU_CUDA(cudaEventRecord(hp.e_comp[b], s));
+        SGPU_CUDA(cudaStreamWaitEvent(hp.s_out, hp.e_comp[b], 0));
+        if (nout)
+            SGPU_CUDA(cudaMemcpy2DAsync(out + 2 * out_off, out_stride * 8, hp.d_out[b], (nout ? nout : 1) * 8, nout * 8,
+                                        C, cudaMemcpyDeviceToHost, hp.s_out));
+        SGPU_CUDA(cudaEventRecord(hp.e_out[b], hp.s_out));
+        out_off += nout;
+    }
+    SGPU_CUDA(cudaStreamSynchronize(hp.s_out));
+    SGPU_CUDA(cudaStreamSynchronize(s));
+    return SGPU_OK;
+}
+
 // RAII guard: make the handle's device current for the duration of a call.
 struct DeviceGuard {
     int prev = -1;
