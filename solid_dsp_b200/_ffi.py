@@ -174,6 +174,8 @@ def peak_lib():
         P = C.CDLL(str(PEAK_LIB_PATH))
         P.sgpu_peak_fma.restype = C.c_int
         P.sgpu_peak_fma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
+        P.sgpu_peak_fma_ex.restype = C.c_int
+        P.sgpu_peak_fma_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
         P.sgpu_peak_copy.restype = C.c_int
         P.sgpu_peak_copy.argtypes = [c_size, C.c_int, c_dp, c_dp]
         _peak = P

@@ -7,6 +7,7 @@
 //   Window::push / to_vec               window/mod.rs:63-71,44-51  (history: hist_update_kernel)
 //   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
 #include "fir_core.cuh"
+#include "fir_pipe.cuh"
 #include "sgpu_common.cuh"
 
 namespace sgpu {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;  // +1: consecutive planes are skewed by 16 bytes
-    constexpr int TW = PACKED ? 2 : 1;
+    constexpr int TW = 1;
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)M * plane_f4);
 
     const int ch = blockIdx.y;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
 
     {  // taps image -> shared memory
-        const int n4 = M * Qpad * TW / 4;
+        const int n4 = M * (Qpad + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     for (int sidx = 0; sidx < Mp; ++sidx) {
         const int p = part * Mp + sidx;
         if (p < M)
-            fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * Qpad * TW,
+            fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew),
                                 npairs);
     }
     if constexpr (PS > 1) {  // butterfly over the PS lanes of a group: everyone ends with the full sums
@@ -234,10 +235,10 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;
-    constexpr int TW = PACKED ? 2 : 1;
+    constexpr int TW = 1;
     float *taps_s = reinterpret_cast<float *>(smem + plane_f4);
     // staging: NT*R*L outputs, thread t's run skewed by t float2 (bank spread)
-    float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * Qpad * TW);
+    float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * (Qpad + kTapSkew));
 
     const int ch = blockIdx.y;
     const long long n_base = (long long)blockIdx.x * (OT * R);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T - 1 = S samples kept
 
     {
-        const int n4 = L * Qpad * TW / 4;
+        const int n4 = L * (Qpad + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-        fir_core<R, PACKED>(acc, smem, RS, row0, taps_s + (size_t)p * Qpad * TW, npairs);
+        fir_core<R, PACKED>(acc, smem, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
 #pragma unroll
         for (int r = 0; r < R; ++r) my[r * L + p] = acc[r];  // no scale: pfb.rs:85-90
     }
@@ -326,7 +327,7 @@ __global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const f
     if (ch >= C) return;
     // window (newest first) = hist[S-1], hist[S-2], ..., hist[0]  with hist of S samples
     const float2 *h = hist + (long long)ch * S;
-    const float *g = taps + (size_t)phase * Qpad * tw;
+    const float *g = taps + (size_t)phase * (Qpad + kTapSkew) * tw;
     float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < S; ++j) {
         const float gj = g[j * tw];
@@ -367,17 +368,13 @@ bool packed_default() {
 // Host-side image of the taps as the kernels consume them: nsets phase filters of Qpad taps.
 void build_tap_image(const std::vector<float> &phase_taps /*[nsets][Q]*/, int nsets, int Q, int Qpad,
                      bool packed, std::vector<float> &img) {
-    const int tw = packed ? 2 : 1;
-    img.assign((size_t)nsets * Qpad * tw, 0.f);
+    const int tw = 1;
+    (void)packed;
+    img.assign((size_t)nsets * (Qpad + kTapSkew) * tw, 0.f);
     for (int p = 0; p < nsets; ++p)
         for (int q = 0; q < Q; ++q) {
             const float g = phase_taps[(size_t)p * Q + q];
-            if (packed) {
-                img[((size_t)p * Qpad + q) * 2] = g;
-                img[((size_t)p * Qpad + q) * 2 + 1] = g;
-            } else {
-                img[(size_t)p * Qpad + q] = g;
-            }
+            img[(size_t)p * (Qpad + kTapSkew) + q] = g;
         }
 }
 
@@ -536,18 +533,75 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (out_stride % 2 == 0);
     a.scale_re = (float)f->scale_re;
     a.scale_im = (float)f->scale_im;
-    const int tw = f->packed ? 2 : 1;
+    const int tw = 1;
+    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && env_int("SGPU_PIPE_DEC", 0)) {
+        // persistent multi-stage decimator (fir_pipe.cuh).  Measured SLOWER than the one-tile-per-block
+        // kernel below on B200 (257 vs 338 G input samples/s on config 3's shape: the ring spends shared
+        // memory on in-flight stages instead of resident warps), so it is opt-in for experiments only.
+        int PS = f->M >= 4 ? 4 : 2;
+        const int want = env_int("SGPU_DEC_PS", 0);
+        if ((want == 2 || want == 4) && want <= (int)f->M) PS = want;
+        int NS = env_int("SGPU_PIPE_STAGES", 3);
+        if (NS < 2 || NS > 3) NS = 3;
+        const int OT = kNT / PS;
+        const int rows = f->Qpad / kR + OT;
+        const int RS = rows | 1;
+        const size_t plane_f4 = (size_t)(kR / 2) * RS + 1;
+        const size_t taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * tw * sizeof(float);
+        auto smem_for = [&](int ns) { return (size_t)ns * f->M * plane_f4 * sizeof(float4) + taps_b; };
+        while (NS > 2 && smem_for(NS) > (size_t)kMaxSmem) --NS;
+        const long long tiles_total = ((n_out + (long long)OT * kR - 1) / ((long long)OT * kR)) * (long long)f->C;
+        if (smem_for(NS) <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
+            FirPipeArgs pa{};
+            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur]; pa.taps = f->d_taps;
+            pa.in_stride = in_stride; pa.out_stride = out_stride; pa.n_in = n_in; pa.n_out = n_out;
+            pa.tiles_per_ch = (int)((n_out + (long long)OT * kR - 1) / ((long long)OT * kR));
+            pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
+            pa.T = (int)f->T; pa.M = (int)f->M; pa.c0 = (int)f->current_item; pa.Qpad = f->Qpad; pa.RS = RS;
+            pa.vec_out = a.vec_out; pa.scale_re = (float)f->scale_re;
+            const size_t smem = smem_for(NS);
+            int st = SGPU_OK;
+            int per_sm = 0;
+#define LAUNCH_DPIPE(PK, PSV, NSV)                                                                     \
+    do {                                                                                               \
+        void (*kern)(const FirPipeArgs) = nullptr;                                                     \
+        switch ((int)f->M / PSV) {                                                                     \
+            case 1: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 1, NSV, 1>; break;                  \
+            case 2: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 2, NSV, 1>; break;                  \
+            default: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 4, NSV, 1>; break;                 \
+        }                                                                                              \
+        st = set_smem(kern, smem);                                                                     \
+        if (st) return st;                                                                             \
+        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smem));            \
+        long long blocks = (long long)f->sm_count * (per_sm > 0 ? per_sm : 1);                         \
+        if (blocks > pa.total_tiles) blocks = pa.total_tiles;                                          \
+        kern<<<(unsigned)blocks, kNT, smem, s>>>(pa);                                                  \
+    } while (0)
+#define LAUNCH_DPIPE_NS(PK, PSV)                      \
+    do {                                              \
+        if (NS == 2) LAUNCH_DPIPE(PK, PSV, 2);        \
+        else LAUNCH_DPIPE(PK, PSV, 3);                \
+    } while (0)
+            if (PS == 4) LAUNCH_DPIPE_NS(true, 4);
+            else LAUNCH_DPIPE_NS(true, 2);
+#undef LAUNCH_DPIPE_NS
+#undef LAUNCH_DPIPE
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+            return SGPU_OK;
+        }
+    }
     if (n_out > 0) {
         const bool m1 = f->M == 1;
         // phase split: as many lanes per output run as there are phases to share, up to 4
-        int PS = m1 ? 1 : (f->M >= 2 ? 2 : 1);  // measured: PS=2 beats 1 and 4 at M=8
+        int PS = m1 ? 1 : (f->M >= 4 ? 4 : (f->M >= 2 ? 2 : 1));  // measured at M=8: PS=4 338, PS=2 311, PS=1 192 G in-samp/s
         const int want = env_int("SGPU_DEC_PS", 0);
         if (!m1 && (want == 1 || want == 2 || want == 4) && want <= (int)f->M) PS = want;
         const int OT = kNT / PS;
         const int rows = f->Qpad / kR + OT;
         a.RS = rows | 1;
         const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
-        const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * f->Qpad * tw * sizeof(float);
+        const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * (f->Qpad + kTapSkew) * tw * sizeof(float);
         if (smem > (size_t)kMaxSmem)
             return fail(SGPU_ERR_UNSUPPORTED, "filter too long for one shared-memory tile (%zu bytes needed)", smem);
         const long long tiles = (n_out + (long long)OT * kR - 1) / ((long long)OT * kR);
@@ -837,7 +891,51 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     a.vec_in = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (istr % 2 == 0);
     a.vec_out = 0;
     a.scale_re = 1.f;
-    const int tw = f->packed ? 2 : 1;
+    const int tw = 1;
+    if (env_int("SGPU_PIPE", 1)) {
+        // persistent multi-stage interpolator (fir_pipe.cuh)
+        int PSp = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
+        const int wantp = env_int("SGPU_INT_PS", 0);
+        if ((wantp == 1 || wantp == 2 || wantp == 4) && wantp <= (int)f->L) PSp = wantp;
+        const int OTp = kNT / PSp;
+        const int rowsp = f->Qpad / kR + OTp;
+        const int RSp = rowsp | 1;
+        const size_t stage_f4 = (size_t)(kR / 2) * RSp + 1;
+        const size_t smemp = 3 * stage_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * tw * sizeof(float);
+        const long long tiles_total = ((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR)) * (long long)f->C;
+        if (smemp <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
+            FirPipeArgs pa{};
+            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur]; pa.taps = f->d_taps;
+            pa.in_stride = istr; pa.out_stride = ostr; pa.n_in = n_in; pa.n_out = n_out;
+            pa.tiles_per_ch = (int)((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR));
+            pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
+            pa.T = (int)f->S + 1; pa.M = (int)f->L; pa.c0 = 0; pa.Qpad = f->Qpad; pa.RS = RSp;
+            pa.vec_out = 0; pa.scale_re = 1.f;
+            int st = SGPU_OK;
+            int per_sm = 0;
+#define LAUNCH_IPIPE(PK, PSV)                                                                          \
+    do {                                                                                               \
+        auto kern = fir_interp_pipe_kernel<kR, PK, kNT, PSV, 3, 1>;                                    \
+        st = set_smem(kern, smemp);                                                                    \
+        if (st) return st;                                                                             \
+        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smemp));           \
+        long long blocks = (long long)f->sm_count * (per_sm > 0 ? per_sm : 1);                         \
+        if (blocks > pa.total_tiles) blocks = pa.total_tiles;                                          \
+        kern<<<(unsigned)blocks, kNT, smemp, s>>>(pa);                                                 \
+    } while (0)
+            if (PSp == 4) {
+                if (f->packed) LAUNCH_IPIPE(true, 4); else LAUNCH_IPIPE(false, 4);
+            } else if (PSp == 2) {
+                if (f->packed) LAUNCH_IPIPE(true, 2); else LAUNCH_IPIPE(false, 2);
+            } else {
+                if (f->packed) LAUNCH_IPIPE(true, 1); else LAUNCH_IPIPE(false, 1);
+            }
+#undef LAUNCH_IPIPE
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+            return SGPU_OK;
+        }
+    }
     int PS = f->L >= 2 ? 2 : 1;
     const int want = env_int("SGPU_INT_PS", 0);
     if ((want == 1 || want == 2 || want == 4) && want <= (int)f->L) PS = want;
@@ -845,7 +943,7 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     const int rows = f->Qpad / kR + OT;
     a.RS = rows | 1;
     const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
-    const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)f->Qpad * tw * sizeof(float) +
+    const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * tw * sizeof(float) +
                         (size_t)OT * (kR * f->L + 1) * sizeof(float2);
     if (smem > (size_t)kMaxSmem)
         return fail(SGPU_ERR_UNSUPPORTED, "interpolator tile needs %zu bytes of shared memory", smem);
@@ -934,7 +1032,7 @@ SGPU_EXPORT int sgpu_interp_execute_phase(sgpu_interp *f, size_t index, float *o
         if (st) return st;
         d_out = (float2 *)f->stage.out;
     }
-    const int tw = f->packed ? 2 : 1;
+    const int tw = 1;
     pfb_phase_kernel<<<(unsigned)ceil_div(f->C, 128), 128, 0, s>>>(f->d_hist[f->cur], (int)f->S, f->d_taps,
                                                                      f->Qpad, tw, (int)index, d_out, (int)f->C);
     SGPU_LAUNCH_CHECK();

@@ -13,7 +13,7 @@
 // -- and RS is odd so the tile loader's STS (8 lanes = one row's 8 pairs) is conflict-free too.
 //
 // Arithmetic: real taps on complex samples.  PACKED = true issues one fma.rn.f32x2 (SASS
-// FFMA2, new on sm_100) per complex MAC with the tap duplicated in a register pair;
+// FFMA2, new on sm_100) per complex MAC with the tap as its scalar-broadcast operand;
 // PACKED = false issues two scalar FFMA.  Accumulation order is newest sample first, as
 // dot_product/mod.rs:159-170 does.
 #pragma once
@@ -21,6 +21,10 @@
 #include <cuda_runtime.h>
 
 namespace sgpu {
+
+// Tap image rows (one per phase) are Qpad + kTapSkew floats apart: the 16-byte skew puts the PS
+// different tap rows that the lanes of a phase-split warp read into different banks.
+constexpr int kTapSkew = 4;
 
 template <bool PACKED>
 __device__ __forceinline__ void cmac_real(float2 &acc, const float2 w, const float gx, const float gy) {
@@ -44,35 +48,22 @@ __device__ __forceinline__ void load_row(float2 (&W)[2 * R], const float4 *__res
 }
 
 // One chunk of R taps.  OFF = 0 for even chunks, R for odd ones (see header comment).
-// taps: PACKED -> R float2 (g,g) pairs; else R floats.  16-byte aligned.
+// taps: R floats in shared memory, 16-byte aligned (one LDS.128 = 4 taps).  The packed path feeds
+// the tap as FFMA2's scalar-broadcast operand (SASS `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2`), so no
+// duplicated (g,g) pairs are needed in shared memory or registers.
 template <int R, bool PACKED, int OFF>
 __device__ __forceinline__ void fir_chunk(float2 (&acc)[R], const float2 (&W)[2 * R],
                                           const float *__restrict__ taps) {
-    if constexpr (PACKED) {
-        const float4 *t4 = reinterpret_cast<const float4 *>(taps);
+    const float4 *t4 = reinterpret_cast<const float4 *>(taps);
 #pragma unroll
-        for (int u2 = 0; u2 < R / 2; ++u2) {
-            const float4 g = t4[u2];  // (g_u, g_u, g_{u+1}, g_{u+1})
+    for (int u4 = 0; u4 < R / 4; ++u4) {
+        const float4 g = t4[u4];
+        const float gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
 #pragma unroll
             for (int r = 0; r < R; ++r)
-                cmac_real<true>(acc[r], W[(r - 2 * u2 + OFF + 4 * R) & (2 * R - 1)], g.x, g.y);
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                cmac_real<true>(acc[r], W[(r - 2 * u2 - 1 + OFF + 4 * R) & (2 * R - 1)], g.z, g.w);
-        }
-    } else {
-        const float4 *t4 = reinterpret_cast<const float4 *>(taps);
-#pragma unroll
-        for (int u4 = 0; u4 < R / 4; ++u4) {
-            const float4 g = t4[u4];
-            const float gs[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    cmac_real<false>(acc[r], W[(r - (4 * u4 + k) + OFF + 4 * R) & (2 * R - 1)],
-                                     gs[k], gs[k]);
-            }
+                cmac_real<PACKED>(acc[r], W[(r - (4 * u4 + k) + OFF + 4 * R) & (2 * R - 1)], gs[k], gs[k]);
         }
     }
 }
@@ -82,7 +73,7 @@ template <int R, bool PACKED>
 __device__ __forceinline__ void fir_core(float2 (&acc)[R], const float4 *__restrict__ plane,
                                          const int RS, const int row0,
                                          const float *__restrict__ taps, const int npairs) {
-    constexpr int TW = PACKED ? 2 : 1;  // floats per tap in shared memory
+    constexpr int TW = 1;  // floats per tap in shared memory
     float2 W[2 * R];
     load_row<R, 0>(W, plane, RS, row0);
     int row = row0;

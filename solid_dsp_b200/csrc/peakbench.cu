@@ -125,8 +125,18 @@ __global__ void __launch_bounds__(256) copy_kernel(const float4 *__restrict__ in
 // Runs `reps` timed launches (after one warm-up) of FMA variant `variant` with
 // blocks_per_sm * SMs blocks of 256 threads; returns the best time and the FP32 flop count of
 // one launch (2 flops per FMA lane-op).
+PB_EXPORT int sgpu_peak_fma_ex(int variant, int blocks_per_sm, int threads, int iters, int reps, double *best_ms,
+                               double *flops_per_launch);
+
 PB_EXPORT int sgpu_peak_fma(int variant, int blocks_per_sm, int iters, int reps, double *best_ms,
                             double *flops_per_launch) {
+    return sgpu_peak_fma_ex(variant, blocks_per_sm, 256, iters, reps, best_ms, flops_per_launch);
+}
+
+// same with an explicit block size (<= 256): occupancy sweeps (how many warps per SM sub-partition the
+// FMA pipe needs before it saturates)
+PB_EXPORT int sgpu_peak_fma_ex(int variant, int blocks_per_sm, int threads, int iters, int reps, double *best_ms,
+                               double *flops_per_launch) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     cudaDeviceProp p;
@@ -141,10 +151,10 @@ PB_EXPORT int sgpu_peak_fma(int variant, int blocks_per_sm, int iters, int reps,
     for (int r = 0; r <= reps; ++r) {
         cudaEventRecord(e0);
         switch (variant) {
-            case 0: fma_scalar_kernel<<<blocks, 256>>>(out, iters, 1.0000001f, 1e-7f); break;
-            case 1: fma_packed_kernel<<<blocks, 256>>>(out, iters, 1.0000001f, 1e-7f); break;
-            case 2: fma_packed_fir_kernel<<<blocks, 256>>>(out, iters, 1.0000001f, 1e-7f); break;
-            case 3: fma_scalar_fir_kernel<<<blocks, 256>>>(out, iters, 1.0000001f, 1e-7f); break;
+            case 0: fma_scalar_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+            case 1: fma_packed_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+            case 2: fma_packed_fir_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
+            case 3: fma_scalar_fir_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f); break;
             default: cudaFree(out); return -2;
         }
         cudaEventRecord(e1);
@@ -157,7 +167,7 @@ PB_EXPORT int sgpu_peak_fma(int variant, int blocks_per_sm, int iters, int reps,
     cudaEventDestroy(e1);
     cudaFree(out);
     // lane-FMAs per thread per iteration: 2*kAcc*kInner for every variant (packed = 2 lanes/instr)
-    const double fmas = (double)blocks * 256.0 * (double)iters * (2.0 * kAcc * kInner);
+    const double fmas = (double)blocks * (double)threads * (double)iters * (2.0 * kAcc * kInner);
     if (best_ms) *best_ms = best;
     if (flops_per_launch) *flops_per_launch = 2.0 * fmas;
     return 0;

@@ -44,6 +44,16 @@ def peaks():
     print(json.dumps({"peak": "copy", "ms": ms.value, "GBps": by.value / ms.value / 1e6}))
 
 
+def occ():
+    """FMA throughput vs resident warps per SM (128-thread blocks)."""
+    P = _ffi.peak_lib()
+    for v, nm in ((1, "ffma2_packed"), (2, "ffma2_fir_shape"), (0, "ffma_scalar")):
+        for bps in (1, 2, 3, 4, 6, 8):
+            ms, fl = C.c_double(), C.c_double()
+            P.sgpu_peak_fma_ex(v, bps, 128, 2000, 3, C.byref(ms), C.byref(fl))
+            print(json.dumps({"peak": nm, "warps_per_sm": bps * 4, "tflops": round(fl.value / ms.value / 1e9, 2)}))
+
+
 def fir(T=512, logn=26):
     from solid_dsp_b200.filter.fir import FIRFilter
     n = 1 << logn
