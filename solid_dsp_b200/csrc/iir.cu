@@ -16,6 +16,8 @@
 //           the carry kernel solves s_{p+1} = A^Lc s_p + z_p (A^Lc built on the host in f64,
 //           recurrence evaluated in f64 on the device, hierarchically); pass C re-runs every
 //           chunk from its true start state and writes the outputs.
+#include <cmath>
+
 #include "sgpu_common.cuh"
 
 using namespace sgpu;
@@ -41,6 +43,11 @@ struct IirArgs {
     int write_out;
     int factor, idx0;  // decimation / interpolation factor, decimator counter on entry
     int vec;           // 16-byte aligned pointers and even strides -> cp.async path
+    long long skip;    // scan pass A: samples skipped at the head of every chunk (see iir_run)
+    // scan layout: chunk slots [0, NP) are full chunks of Lc samples, the slot `tail_slot` (a
+    // multiple of 32, so it starts its own warp) holds the ragged tail, every other slot is empty
+    int NP, tail_slot;
+    long long tail_off, tail_len;
     SosCoefs k;
 };
 
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
 
     // affine row addressing for this warp (rows = 32 consecutive virtual channels)
     long long in_base, out_base, rstr_in, rstr_out, p0 = 0;
+    bool is_tail = false;
     if (a.P == 1) {
         in_base = vc0 * a.in_stride;
         out_base = vc0 * a.out_stride;
@@ -104,21 +112,26 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
     } else {
         const long long c = vc0 / a.P;
         p0 = vc0 - c * a.P;
-        in_base = c * a.in_stride + p0 * a.Lc;
-        out_base = c * a.out_stride + p0 * a.Lc;
+        is_tail = p0 == a.tail_slot;
+        const long long off = is_tail ? a.tail_off : p0 * a.Lc;
+        in_base = c * a.in_stride + off + (is_tail ? 0 : a.skip);
+        out_base = c * a.out_stride + off;
         rstr_in = a.Lc;
         rstr_out = a.Lc;
     }
-    // per-row length in "loop samples" (inputs for WRAP 0/1, outputs for WRAP 2)
+    // per-row length in "loop samples" (inputs for WRAP 0/1, outputs for WRAP 2).  Valid rows are
+    // always a prefix of the warp's 32 rows.
     const long long n_loop = WRAP == 2 ? a.n_in * a.factor : a.n_in;
     auto row_len = [&](int r) -> long long {
         if (vc0 + r >= VC) return 0;
         if (a.P == 1) return n_loop;
-        long long l = n_loop - (p0 + r) * a.Lc;
-        return l < 0 ? 0 : (l > a.Lc ? a.Lc : l);
+        if (is_tail) return r == 0 ? a.tail_len : 0;
+        return p0 + r < a.NP ? a.Lc - a.skip : 0;
     };
     const long long my_len = row_len(lane);
-    long long max_len = my_len, min_len = my_len;
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, my_len > 0));
+    if (nvalid == 0) return;
+    long long max_len = my_len, min_len = my_len > 0 ? my_len : 0x7fffffffffffffffLL;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const long long u = __shfl_xor_sync(0xffffffffu, max_len, o);
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         v1[s] = make_float2(0.f, 0.f);
         v2[s] = make_float2(0.f, 0.f);
     }
-    if (a.state_in && my_vc < VC) {
+    if (a.state_in && lane < nvalid) {
         const float4 *sp = reinterpret_cast<const float4 *>(a.state_in + my_vc * (2 * NSEC));
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) {
@@ -154,14 +167,16 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
 
     // ------------------------------------------------------------------ fast path: full tiles
     if (full_tiles > 0) {
-        const float2 *ld_ptr = a.in + in_base + (long long)lrow * rstr_in + 2 * lj;
+        // rows past the valid prefix re-read the last valid row (never out of bounds, never stored)
+        const float2 *ld_ptr = a.in + in_base + 2 * lj;
         float2 *st_ptr = a.out + out_base + (long long)lrow * rstr_out + 2 * lj;
-        const long long ld_step = 4 * rstr_in, st_step = 4 * rstr_out;
+        const long long st_step = 4 * rstr_out;
         auto prefetch = [&](float4 *dst) {
-            const float2 *src = ld_ptr;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = lrow + 4 * i;
+                const int rl = r < nvalid ? r : nvalid - 1;
+                const float2 *src = ld_ptr + (long long)rl * rstr_in;
                 float4 *d = dst + r * 8 + (lj ^ (r & 7));
                 if (a.vec) {
                     cp_async16(d, src);
@@ -169,7 +184,6 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
                     cp_async8(d, src);
                     cp_async8(reinterpret_cast<float2 *>(d) + 1, src + 1);
                 }
-                src += ld_step;
             }
             cp_async_commit();
             ld_ptr += kTile;
@@ -194,13 +208,13 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
                 for (int s = 0; s < NSEC; ++s)
                     y0 = biquad<PACKED>(y0, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
                 if constexpr (WRAP == 1) {
-                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y0; ++dec_ptr; }
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y0; ++dec_ptr; }
                 }
 #pragma unroll
                 for (int s = 0; s < NSEC; ++s)
                     y1 = biquad<PACKED>(y1, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
                 if constexpr (WRAP == 1) {
-                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y1; ++dec_ptr; }
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y1; ++dec_ptr; }
                 }
                 if constexpr (WRAP == 0) *cell = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
@@ -212,11 +226,13 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
                     for (int i = 0; i < 8; ++i) {
                         const int r = lrow + 4 * i;
                         const float4 v = cur[r * 8 + (lj ^ (r & 7))];
-                        if (a.vec) {
-                            *reinterpret_cast<float4 *>(dst) = v;
-                        } else {
-                            dst[0] = make_float2(v.x, v.y);
-                            dst[1] = make_float2(v.z, v.w);
+                        if (r < nvalid) {
+                            if (a.vec) {
+                                *reinterpret_cast<float4 *>(dst) = v;
+                            } else {
+                                dst[0] = make_float2(v.x, v.y);
+                                dst[1] = make_float2(v.z, v.w);
+                            }
                         }
                         dst += st_step;
                     }
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         }
     }
 
-    if (a.state_out && my_vc < VC) {
+    if (a.state_out && lane < nvalid) {
         float4 *sp = reinterpret_cast<float4 *>(a.state_out + my_vc * (2 * NSEC));
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) sp[s] = make_float4(v1[s].x, v1[s].y, v2[s].x, v2[s].y);
@@ -298,10 +314,13 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
 // mode 0: zero start over the group's chunks           -> gagg[c*G+g]
 // mode 1: one warp per channel over groups (Mat = A^(Lc*CH)): Sg[c*G+g] = start state of group g
 // mode 2: from Sg[c*G+g] (or state0[c] when Sg == nullptr): sbuf[c*P+p] = start state of chunk p
+// Lane i owns row i of Mat (registers); the state vector lives in shared memory.  The additive term
+// of step p+1 is fetched from global memory while step p is being evaluated, and the dot product runs
+// as four independent DFMA chains, so a step costs ~one shared-memory round trip.
 __global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__restrict__ Mat, int D,
                                                     const float2 *__restrict__ z, double2 *gagg, double2 *Sg,
                                                     float2 *__restrict__ sbuf, const float2 *__restrict__ state0,
-                                                    int P, int CH, int G, int n_units) {
+                                                    int P, int NP, int tail_slot, int CH, int G, int n_units) {
     __shared__ double2 sh[4][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int unit = blockIdx.x * 4 + w;
@@ -310,18 +329,21 @@ __global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__re
 #pragma unroll
     for (int j = 0; j < 32; ++j) m[j] = (lane < D && j < D) ? Mat[lane * D + j] : 0.0;
     double2 *s = sh[w];
+    const int DQ = (D + 3) & ~3;
     auto step = [&](double2 add) {
-        double2 acc = add;
+        double2 a0 = add, a1 = make_double2(0., 0.), a2 = a1, a3 = a1;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < D) {
-                const double2 sj = s[j];
-                acc.x = fma(m[j], sj.x, acc.x);
-                acc.y = fma(m[j], sj.y, acc.y);
+        for (int j = 0; j < 32; j += 4) {
+            if (j < DQ) {
+                const double2 s0 = s[j], s1 = s[j + 1], s2 = s[j + 2], s3 = s[j + 3];
+                a0.x = fma(m[j], s0.x, a0.x);         a0.y = fma(m[j], s0.y, a0.y);
+                a1.x = fma(m[j + 1], s1.x, a1.x);     a1.y = fma(m[j + 1], s1.y, a1.y);
+                a2.x = fma(m[j + 2], s2.x, a2.x);     a2.y = fma(m[j + 2], s2.y, a2.y);
+                a3.x = fma(m[j + 3], s3.x, a3.x);     a3.y = fma(m[j + 3], s3.y, a3.y);
             }
         }
         __syncwarp();
-        s[lane] = acc;
+        s[lane] = make_double2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
         __syncwarp();
     };
     if (mode == 1) {
@@ -329,15 +351,18 @@ __global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__re
         const float2 i0 = lane < D ? state0[(long long)c * D + lane] : make_float2(0.f, 0.f);
         s[lane] = make_double2(i0.x, i0.y);
         __syncwarp();
+        const double2 *ga = gagg + (long long)c * G * D + lane;
+        double2 nxt = (lane < D && G > 0) ? ga[0] : make_double2(0., 0.);
         for (int g = 0; g < G; ++g) {
+            const double2 add = nxt;
+            if (lane < D && g + 1 < G) nxt = ga[(long long)(g + 1) * D];
             if (lane < D) Sg[((long long)c * G + g) * D + lane] = s[lane];
-            const double2 add = lane < D ? gagg[((long long)c * G + g) * D + lane] : make_double2(0., 0.);
             step(add);
         }
         return;
     }
     const int c = unit / G, g = unit - c * G;
-    const int p_lo = g * CH, p_hi = min(P, p_lo + CH);
+    const int p_lo = g * CH, p_hi = min(NP, p_lo + CH);  // chunk slots [0, NP) are scanned; P is the slot stride
     if (mode == 0) {
         s[lane] = make_double2(0., 0.);
     } else {
@@ -352,14 +377,43 @@ __global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__re
         s[lane] = st;
     }
     __syncwarp();
-    for (int p = p_lo; p < p_hi; ++p) {
-        const long long vc = (long long)c * P + p;
-        if (mode == 2 && lane < D) sbuf[vc * D + lane] = make_float2((float)s[lane].x, (float)s[lane].y);
-        float2 zz = make_float2(0.f, 0.f);
-        if (lane < D) zz = z[vc * D + lane];
-        step(make_double2(zz.x, zz.y));
+    // software prefetch of z, four steps ahead
+    constexpr int PF = 4;
+    float2 zq[PF];
+    const float2 *zp = z + ((long long)c * P + p_lo) * D + lane;
+#pragma unroll
+    for (int k = 0; k < PF; ++k) zq[k] = (lane < D && p_lo + k < p_hi) ? zp[(long long)k * D] : make_float2(0.f, 0.f);
+    for (int p = p_lo; p < p_hi; p += PF) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            if (p + k < p_hi) {
+                const long long vc = (long long)c * P + p + k;
+                if (mode == 2 && lane < D) sbuf[vc * D + lane] = make_float2((float)s[lane].x, (float)s[lane].y);
+                const float2 zz = zq[k];
+                zq[k] = (lane < D && p + k + PF < p_hi) ? zp[(long long)(p - p_lo + k + PF) * D] : make_float2(0.f, 0.f);
+                step(make_double2(zz.x, zz.y));
+            }
+        }
     }
     if (mode == 0 && lane < D) gagg[((long long)c * G + g) * D + lane] = s[lane];
+    // the state after the last full chunk starts the ragged tail chunk
+    if (mode == 2 && p_hi == NP && tail_slot >= 0 && lane < D)
+        sbuf[((long long)c * P + tail_slot) * D + lane] = make_float2((float)s[lane].x, (float)s[lane].y);
+}
+
+// Decaying filters (||A^Lc|| < 1e-12): the start state of chunk p is simply the zero-state end state
+// of chunk p-1, so the carry recurrence degenerates into a shift.
+__global__ void shift_states_kernel(const float2 *__restrict__ z, const float2 *__restrict__ state0,
+                                    float2 *__restrict__ sbuf, int D, int P, int NP, int tail_slot, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over C * (NP + 1) * D
+    if (i >= total) return;
+    const int d = (int)(i % D);
+    const long long q = i / D;
+    const int p = (int)(q % (NP + 1));
+    const long long c = q / (NP + 1);
+    const float2 v = p == 0 ? state0[c * D + d] : z[(c * P + p - 1) * D + d];
+    if (p < NP) sbuf[(c * P + p) * D + d] = v;
+    else if (tail_slot >= 0) sbuf[(c * P + tail_slot) * D + d] = v;
 }
 
 // ---- Normal mode: one direct-form II of arbitrary order (iir/mod.rs:98-130,272-280) ---------
@@ -463,6 +517,7 @@ struct sgpu_iir {
     double *d_mat = nullptr;  // [2][D*D]: A^Lc, A^(Lc*CH)
     size_t scratch_vc = 0, scratch_units = 0;
     long long mat_Lc = -1, mat_CH = -1;
+    long long decay_len = -1;  // samples after which ||A^k||_inf < 1e-12 (scan pass A window), -1 = never
     Staging stage;
     HostPipe pipe;
 };
@@ -575,6 +630,23 @@ int ensure_scan_scratch(sgpu_iir *f, size_t vc, size_t units, long long Lc, long
     if (f->mat_Lc != Lc || f->mat_CH != CH) {
         std::vector<double> A, ALc, AG;
         build_transition(f, A);
+        {   // decay length: smallest multiple of 16 with ||A^k||_inf < 1e-12, searched up to Lc
+            std::vector<double> A16, Pk;
+            mat_pow(A, 16, A16, D);
+            Pk = A16;
+            f->decay_len = -1;
+            for (long long k = 16; k <= Lc; k += 16) {
+                double nrm = 0.0;
+                for (int i = 0; i < D; ++i) {
+                    double rs = 0.0;
+                    for (int j = 0; j < D; ++j) rs += std::fabs(Pk[(size_t)i * D + j]);
+                    nrm = rs > nrm ? rs : nrm;
+                }
+                if (!(nrm == nrm) || nrm > 1e30) break;  // unstable filter: no truncation
+                if (nrm < 1e-12) { f->decay_len = k; break; }
+                mat_mul(Pk, A16, Pk, D);
+            }
+        }
         mat_pow(A, Lc, ALc, D);
         mat_pow(ALc, CH, AG, D);
         SGPU_CUDA(cudaMemcpy(f->d_mat, ALc.data(), (size_t)D * D * sizeof(double), cudaMemcpyHostToDevice));
@@ -609,6 +681,7 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
     a.C = (int)f->C; a.factor = (int)f->factor; a.idx0 = (int)f->index;
     a.vec = vec ? 1 : 0;
     a.k = f->k;
+    a.skip = 0; a.NP = 0; a.tail_slot = -1; a.tail_off = 0; a.tail_len = 0;
     // strategy: scan when there are too few channels to fill the chip and the stream is long
     const long long target_threads = (long long)f->sm_count * 1024;
     bool scan = f->wrap == SGPU_IIR_PLAIN &&
@@ -618,49 +691,71 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
         a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
         return launch_sos(f, a, f->wrap, s);
     }
-    // ---- chunked scan
-    long long P = ceil_div((size_t)target_threads, f->C);
-    long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)P), kTile);
+    // ---- chunked scan.  Virtual channels fill whole waves of the batch kernel: 3 blocks of 256
+    // threads per SM (launch bounds of iir_sos_kernel), so P*C is about sm_count*768.
+    const long long wave = (long long)f->sm_count * 768;
+    long long P0 = ceil_div((size_t)wave, f->C);
+    long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)P0), kTile);
     if (Lc < 256) Lc = 256;
-    const long long P_real = (n_in + Lc - 1) / Lc;
-    P = (long long)round_up((size_t)P_real, 32);
+    const long long NP = n_in / Lc;          // full chunks
+    const long long tail = n_in - NP * Lc;   // ragged tail chunk (its own warp)
+    if (NP == 0) {
+        a.P = 1; a.Lc = n_in;
+        a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
+        return launch_sos(f, a, f->wrap, s);
+    }
+    const long long Pw = (long long)round_up((size_t)NP, 32);
+    const long long P = Pw + (tail ? 32 : 0);
+    const int tail_slot = tail ? (int)Pw : -1;
     const long long CH = 256;
-    const long long G = (P + CH - 1) / CH;
+    const long long G = (NP + CH - 1) / CH;
     const int D = 2 * f->nsec_pad;
     int st = ensure_scan_scratch(f, (size_t)f->C * P, (size_t)f->C * G, Lc, CH);
     if (st) return st;
-    a.P = (int)P; a.Lc = Lc;
-    // pass A: zero-state end states
-    a.state_in = nullptr; a.state_out = f->d_z; a.write_out = 0;
+    a.P = (int)P; a.Lc = Lc; a.NP = (int)NP; a.tail_slot = tail_slot; a.tail_off = NP * Lc;
+    const bool decays = f->decay_len > 0 && f->decay_len <= Lc && !getenv("SGPU_IIR_NO_TRUNC");
+    // pass A: zero-state end state of every full chunk.  That state depends on the chunk's last
+    // `decay_len` samples only, to within ||A^decay_len|| < 1e-12 (far below f32 resolution), so a
+    // decaying filter's pass A reads just that tail; other filters run the whole chunk.
+    a.state_in = nullptr; a.state_out = f->d_z; a.write_out = 0; a.tail_len = 0;
+    a.skip = decays ? Lc - f->decay_len : 0;
     st = launch_sos(f, a, 0, s);
     if (st) return st;
-    // carries
-    if (G > 1) {
-        const int units = (int)(f->C * G);
-        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(0, f->d_mat, D, f->d_z, f->d_gagg, nullptr,
-                                                                         nullptr, nullptr, (int)P, (int)CH, (int)G, units);
+    a.skip = 0;
+    if (decays) {
+        // ||A^Lc|| < 1e-12 as well: start state of chunk p = end state of chunk p-1
+        const long long total = (long long)f->C * (NP + 1) * D;
+        shift_states_kernel<<<(unsigned)ceil_div((size_t)total, 256), 256, 0, s>>>(f->d_z, f->d_state, f->d_s, D, (int)P,
+                                                                                 (int)NP, tail_slot, total);
         SGPU_LAUNCH_CHECK();
-        carry_kernel<<<(unsigned)ceil_div(f->C, 4), 128, 0, s>>>(1, f->d_mat + (size_t)D * D, D, nullptr, f->d_gagg,
-                                                                 f->d_Sg, nullptr, f->d_state, (int)P, (int)CH, (int)G,
+        count_launch();
+    } else if (G > 1) {
+        const int units = (int)(f->C * G);
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(0, f->d_mat, D, f->d_z, f->d_gagg, nullptr, nullptr,
+                                                                         nullptr, (int)P, (int)NP, tail_slot, (int)CH, (int)G, units);
+        SGPU_LAUNCH_CHECK();
+        carry_kernel<<<(unsigned)ceil_div(f->C, 4), 128, 0, s>>>(1, f->d_mat + (size_t)D * D, D, nullptr, f->d_gagg, f->d_Sg,
+                                                                 nullptr, f->d_state, (int)P, (int)NP, tail_slot, (int)CH, (int)G,
                                                                  (int)f->C);
         SGPU_LAUNCH_CHECK();
-        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, f->d_Sg,
-                                                                         f->d_s, f->d_state, (int)P, (int)CH, (int)G, units);
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, f->d_Sg, f->d_s,
+                                                                         f->d_state, (int)P, (int)NP, tail_slot, (int)CH, (int)G, units);
         SGPU_LAUNCH_CHECK();
         count_launch(3);
     } else {
         const int units = (int)f->C;
-        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, nullptr,
-                                                                         f->d_s, f->d_state, (int)P, (int)CH, 1, units);
+        carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(2, f->d_mat, D, f->d_z, nullptr, nullptr, f->d_s,
+                                                                         f->d_state, (int)P, (int)NP, tail_slot, (int)CH, 1, units);
         SGPU_LAUNCH_CHECK();
         count_launch();
     }
     // pass C: true start states, outputs, end states
-    a.state_in = f->d_s; a.state_out = f->d_z; a.write_out = 1;
+    a.state_in = f->d_s; a.state_out = f->d_z; a.write_out = 1; a.tail_len = tail;
     st = launch_sos(f, a, 0, s);
     if (st) return st;
-    // the handle's new state = end state of the last non-empty chunk of every channel
-    SGPU_CUDA(cudaMemcpy2DAsync(f->d_state, (size_t)D * sizeof(float2), f->d_z + (size_t)(P_real - 1) * D,
+    // the handle's new state = end state of the last chunk of every channel
+    const long long last = tail ? (long long)tail_slot : NP - 1;
+    SGPU_CUDA(cudaMemcpy2DAsync(f->d_state, (size_t)D * sizeof(float2), f->d_z + (size_t)last * D,
                                 (size_t)P * D * sizeof(float2), (size_t)D * sizeof(float2), f->C,
                                 cudaMemcpyDeviceToDevice, s));
     return SGPU_OK;
