@@ -61,7 +61,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // planes; their partial sums meet in a warp-shuffle butterfly.  This keeps R = 16 (one LDS.128 per
 // 16 complex MACs) while a tile needs only NT/PS * R * M input samples of shared memory, so 3-6
 // blocks of 4 warps stay resident per SM and tile loads overlap other blocks' arithmetic.
-template <int R, bool PACKED, bool M1, int NT, int MINB, int PS>
+template <int R, bool PACKED, bool M1, int NT, int MINB, int PS, bool CT = false>
 __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     static_assert(M1 ? PS == 1 : true, "the plain FIR has a single phase");
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;  // +1: consecutive planes are skewed by 16 bytes
-    constexpr int TW = 1;
+    constexpr int TW = CT ? 2 : 1;
+    constexpr int NACC = CT ? 2 * R : R;
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)M * plane_f4);
 
     const int ch = blockIdx.y;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
 
     {  // taps image -> shared memory
-        const int n4 = M * (Qpad + kTapSkew) / 4;
+        const int n4 = M * (Qpad * TW + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
@@ -171,9 +172,9 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     __syncthreads();
 
     // ---- compute
-    float2 acc[R];
+    float2 acc[NACC];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < NACC; ++r) acc[r] = make_float2(0.f, 0.f);
     const int ot = tid / PS, part = tid % PS;
     const int row0 = HR + ot;
     const int npairs = Qpad / (2 * R);
@@ -181,28 +182,36 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     for (int sidx = 0; sidx < Mp; ++sidx) {
         const int p = part * Mp + sidx;
         if (p < M)
-            fir_core<R, PACKED>(acc, smem + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew),
-                                npairs);
+            fir_core<R, PACKED, CT>(acc, smem + (size_t)p * plane_f4, RS, row0,
+                                    taps_s + (size_t)p * (Qpad * TW + kTapSkew), npairs);
     }
     if constexpr (PS > 1) {  // butterfly over the PS lanes of a group: everyone ends with the full sums
 #pragma unroll
         for (int o = 1; o < PS; o <<= 1) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int r = 0; r < NACC; ++r) {
                 acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
                 acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
             }
         }
     }
-
-    // ---- epilogue: scale (fir/mod.rs:211), stage through plane 0, coalesced store
+    // ---- epilogue: scale (fir/mod.rs:211: Out * Coef), stage through plane 0, coalesced store
+    float2 yv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if constexpr (CT) {
+            // (a+bi)(c+di) sums: re = sum(ac) - sum(bd), im = sum(ad) + sum(bc); then the complex scale
+            const float yr = acc[r].x - acc[R + r].y, yi = acc[r].y + acc[R + r].x;
+            yv[r] = make_float2(yr * a.scale_re - yi * a.scale_im, yr * a.scale_im + yi * a.scale_re);
+        } else {
+            yv[r] = make_float2(acc[r].x * a.scale_re, acc[r].y * a.scale_re);
+        }
+    }
     __syncthreads();
-    const float s = a.scale_re;
 #pragma unroll
     for (int jj = 0; jj < R / 2; ++jj)
         if (jj / (R / 2 / PS) == part)  // each lane of a group stages its share of the run
-            smem[jj * RS + ot] = make_float4(acc[2 * jj].x * s, acc[2 * jj].y * s, acc[2 * jj + 1].x * s,
-                                             acc[2 * jj + 1].y * s);
+            smem[jj * RS + ot] = make_float4(yv[2 * jj].x, yv[2 * jj].y, yv[2 * jj + 1].x, yv[2 * jj + 1].y);
     __syncthreads();
     float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
     for (int idx = tid; idx < OT * R / 2; idx += NT) {
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
 // One input plane, L tap sets; a thread runs the L phases one after the other over the same
 // R input positions and stages the interleaved outputs in shared memory.  a.M carries L.
 // PS adjacent lanes share one run of R input positions and split the L output phases.
-template <int R, bool PACKED, int NT, int MINB, int PS>
+template <int R, bool PACKED, int NT, int MINB, int PS, bool CT = false>
 __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
@@ -235,10 +244,11 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const int rows = HR + OT;
     const int RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1;
-    constexpr int TW = 1;
+    constexpr int TW = CT ? 2 : 1;
+    constexpr int NACC = CT ? 2 * R : R;
     float *taps_s = reinterpret_cast<float *>(smem + plane_f4);
     // staging: NT*R*L outputs, thread t's run skewed by t float2 (bank spread)
-    float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * (Qpad + kTapSkew));
+    float2 *stage = reinterpret_cast<float2 *>(taps_s + (size_t)L * (Qpad * TW + kTapSkew));
 
     const int ch = blockIdx.y;
     const long long n_base = (long long)blockIdx.x * (OT * R);
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T - 1 = S samples kept
 
     {
-        const int n4 = L * (Qpad + kTapSkew) / 4;
+        const int n4 = L * (Qpad * TW + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
@@ -281,12 +291,15 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     for (int sidx = 0; sidx < Lp; ++sidx) {
         const int p = part * Lp + sidx;
         if (p >= L) break;
-        float2 acc[R];
+        float2 acc[NACC];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-        fir_core<R, PACKED>(acc, smem, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
+        for (int r = 0; r < NACC; ++r) acc[r] = make_float2(0.f, 0.f);
+        fir_core<R, PACKED, CT>(acc, smem, RS, row0, taps_s + (size_t)p * (Qpad * TW + kTapSkew), npairs);
 #pragma unroll
-        for (int r = 0; r < R; ++r) my[r * L + p] = acc[r];  // no scale: pfb.rs:85-90
+        for (int r = 0; r < R; ++r) {  // no scale: pfb.rs:85-90
+            if constexpr (CT) my[r * L + p] = make_float2(acc[r].x - acc[R + r].y, acc[r].y + acc[R + r].x);
+            else my[r * L + p] = acc[r];
+        }
     }
     __syncthreads();
     float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
@@ -327,13 +340,19 @@ __global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const f
     if (ch >= C) return;
     // window (newest first) = hist[S-1], hist[S-2], ..., hist[0]  with hist of S samples
     const float2 *h = hist + (long long)ch * S;
-    const float *g = taps + (size_t)phase * (Qpad + kTapSkew) * tw;
+    const float *g = taps + (size_t)phase * (Qpad * tw + kTapSkew);
     float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < S; ++j) {
-        const float gj = g[j * tw];
         const float2 w = h[S - 1 - j];
-        acc.x = fmaf(gj, w.x, acc.x);
-        acc.y = fmaf(gj, w.y, acc.y);
+        if (tw == 2) {  // complex taps
+            const float ga = g[2 * j], gb = g[2 * j + 1];
+            acc.x = fmaf(ga, w.x, fmaf(-gb, w.y, acc.x));
+            acc.y = fmaf(ga, w.y, fmaf(gb, w.x, acc.y));
+        } else {
+            const float gj = g[j];
+            acc.x = fmaf(gj, w.x, acc.x);
+            acc.y = fmaf(gj, w.y, acc.y);
+        }
     }
     out[ch] = acc;
 }
@@ -365,17 +384,15 @@ bool packed_default() {
     return v == 1;
 }
 
-// Host-side image of the taps as the kernels consume them: nsets phase filters of Qpad taps.
-void build_tap_image(const std::vector<float> &phase_taps /*[nsets][Q]*/, int nsets, int Q, int Qpad,
-                     bool packed, std::vector<float> &img) {
-    const int tw = 1;
-    (void)packed;
-    img.assign((size_t)nsets * (Qpad + kTapSkew) * tw, 0.f);
+// Host-side image of the taps as the kernels consume them: nsets phase filters of Qpad taps, tw
+// floats per tap (1 real, 2 complex), rows Qpad*tw + kTapSkew floats apart.
+void build_tap_image(const std::vector<float> &phase_taps /*[nsets][Q][tw]*/, int nsets, int Q, int Qpad, int tw,
+                     std::vector<float> &img) {
+    const size_t rs = (size_t)Qpad * tw + kTapSkew;
+    img.assign((size_t)nsets * rs, 0.f);
     for (int p = 0; p < nsets; ++p)
-        for (int q = 0; q < Q; ++q) {
-            const float g = phase_taps[(size_t)p * Q + q];
-            img[(size_t)p * (Qpad + kTapSkew) + q] = g;
-        }
+        for (int q = 0; q < Q; ++q)
+            for (int c = 0; c < tw; ++c) img[p * rs + (size_t)q * tw + c] = phase_taps[((size_t)p * Q + q) * tw + c];
 }
 
 }  // namespace
@@ -395,15 +412,19 @@ struct sgpu_fir {
     HostPipe pipe;
 };
 
+static int fir_R(const sgpu_fir *f) { return f->complex_taps ? 8 : kR; }
+
 static int fir_upload_taps(sgpu_fir *f) {
-    const int T = (int)f->T, M = (int)f->M;
+    const int T = (int)f->T, M = (int)f->M, tw = f->complex_taps ? 2 : 1;
     f->Q = (T + M - 1) / M;
-    f->Qpad = (int)round_up((size_t)f->Q, 2 * kR);
+    f->Qpad = (int)round_up((size_t)f->Q, 2 * fir_R(f));
     // g[k] = h[T-1-k] (REVERSE, fir/mod.rs:86); phase p filter: g_p[q] = g[q*M + p]
-    std::vector<float> ph((size_t)M * f->Q, 0.f);
-    for (int k = 0; k < T; ++k) ph[(size_t)(k % M) * f->Q + k / M] = f->taps_f32[T - 1 - k];
+    std::vector<float> ph((size_t)M * f->Q * tw, 0.f);
+    for (int k = 0; k < T; ++k)
+        for (int c = 0; c < tw; ++c)
+            ph[((size_t)(k % M) * f->Q + k / M) * tw + c] = f->taps_f32[(size_t)(T - 1 - k) * tw + c];
     std::vector<float> img;
-    build_tap_image(ph, M, f->Q, f->Qpad, f->packed, img);
+    build_tap_image(ph, M, f->Q, f->Qpad, tw, img);
     if (f->d_taps) cudaFree(f->d_taps);
     f->d_taps = nullptr;
     SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
@@ -421,8 +442,6 @@ SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind 
     if (is_decimator && decimation < 1)  // decim.rs:30-31
         return fail(SGPU_ERR_FIR_DECIMATION_LESS_THAN_ONE, "FIR Filter Error DecimationLessThanOne");
     if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "fir_create: n_channels == 0");
-    if (kind == SGPU_TAPS_COMPLEX)
-        return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet (real taps only)");
     if (n_taps > (1u << 20) || (is_decimator && decimation > 4096))
         return fail(SGPU_ERR_UNSUPPORTED, "fir_create: n_taps/decimation beyond supported range");
     int dev = 0, sms = 0;
@@ -438,9 +457,11 @@ SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind 
     f->M = f->is_decim ? decimation : 1;
     f->scale_re = scale_re;
     f->scale_im = scale_im;
-    f->packed = packed_default();
-    f->taps_f32.resize(n_taps);
-    for (size_t i = 0; i < n_taps; ++i) f->taps_f32[i] = (float)taps[i];
+    f->complex_taps = kind == SGPU_TAPS_COMPLEX;
+    f->packed = f->complex_taps ? true : packed_default();
+    const size_t tw = f->complex_taps ? 2 : 1;
+    f->taps_f32.resize(n_taps * tw);
+    for (size_t i = 0; i < n_taps * tw; ++i) f->taps_f32[i] = (float)taps[i];
     st = fir_upload_taps(f);
     if (st) { sgpu_fir_destroy(f); return st; }
     const size_t hbytes = n_channels * (n_taps > 1 ? n_taps - 1 : 1) * sizeof(float2);
@@ -489,7 +510,9 @@ SGPU_EXPORT int sgpu_fir_get_scale(const sgpu_fir *f, double *re, double *im) {
 }
 SGPU_EXPORT int sgpu_fir_coefficients(const sgpu_fir *f, double *out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
-    for (size_t i = 0; i < f->T; ++i) out[i] = (double)f->taps_f32[f->T - 1 - i];  // stored order
+    const size_t tw = f->complex_taps ? 2 : 1;
+    for (size_t i = 0; i < f->T; ++i)  // stored (reversed) order
+        for (size_t c = 0; c < tw; ++c) out[i * tw + c] = (double)f->taps_f32[(f->T - 1 - i) * tw + c];
     return SGPU_OK;
 }
 
@@ -534,7 +557,8 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     a.scale_re = (float)f->scale_re;
     a.scale_im = (float)f->scale_im;
     const int tw = 1;
-    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && env_int("SGPU_PIPE_DEC", 0)) {
+    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps &&
+        env_int("SGPU_PIPE_DEC", 0)) {
         // persistent multi-stage decimator (fir_pipe.cuh).  Measured SLOWER than the one-tile-per-block
         // kernel below on B200 (257 vs 338 G input samples/s on config 3's shape: the ring spends shared
         // memory on in-flight stages instead of resident warps), so it is opt-in for experiments only.
@@ -593,39 +617,46 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     }
     if (n_out > 0) {
         const bool m1 = f->M == 1;
+        const int R = fir_R(f);
+        const int twc = f->complex_taps ? 2 : 1;
         // phase split: as many lanes per output run as there are phases to share, up to 4
         int PS = m1 ? 1 : (f->M >= 4 ? 4 : (f->M >= 2 ? 2 : 1));  // measured at M=8: PS=4 338, PS=2 311, PS=1 192 G in-samp/s
         const int want = env_int("SGPU_DEC_PS", 0);
         if (!m1 && (want == 1 || want == 2 || want == 4) && want <= (int)f->M) PS = want;
         const int OT = kNT / PS;
-        const int rows = f->Qpad / kR + OT;
+        const int rows = f->Qpad / R + OT;
         a.RS = rows | 1;
-        const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
-        const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * (f->Qpad + kTapSkew) * tw * sizeof(float);
+        const size_t plane_f4 = (size_t)(R / 2) * a.RS + 1;
+        const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * (f->Qpad * twc + kTapSkew) * sizeof(float);
         if (smem > (size_t)kMaxSmem)
             return fail(SGPU_ERR_UNSUPPORTED, "filter too long for one shared-memory tile (%zu bytes needed)", smem);
-        const long long tiles = (n_out + (long long)OT * kR - 1) / ((long long)OT * kR);
+        const long long tiles = (n_out + (long long)OT * R - 1) / ((long long)OT * R);
         dim3 grid((unsigned)tiles, (unsigned)f->C);
         int st;
-#define LAUNCH_FIR(PK, M1, MINB, PSV)                                                       \
+#define LAUNCH_FIR(RV, PK, M1, MINB, PSV, CTV)                                              \
     do {                                                                                    \
-        auto kern = fir_decim_kernel<kR, PK, M1, kNT, MINB, PSV>;                           \
+        auto kern = fir_decim_kernel<RV, PK, M1, kNT, MINB, PSV, CTV>;                      \
         st = set_smem(kern, smem);                                                          \
         if (st) return st;                                                                  \
         kern<<<grid, kNT, smem, s>>>(a);                                                    \
     } while (0)
-        if (m1) {
-            if (f->packed) LAUNCH_FIR(true, true, 4, 1);
-            else LAUNCH_FIR(false, true, 4, 1);
+        if (f->complex_taps) {
+            if (m1) LAUNCH_FIR(8, true, true, 4, 1, true);
+            else if (PS == 4) LAUNCH_FIR(8, true, false, 4, 4, true);
+            else if (PS == 2) LAUNCH_FIR(8, true, false, 3, 2, true);
+            else LAUNCH_FIR(8, true, false, 1, 1, true);
+        } else if (m1) {
+            if (f->packed) LAUNCH_FIR(kR, true, true, 4, 1, false);
+            else LAUNCH_FIR(kR, false, true, 4, 1, false);
         } else if (PS == 4) {
-            if (f->packed) LAUNCH_FIR(true, false, 4, 4);
-            else LAUNCH_FIR(false, false, 4, 4);
+            if (f->packed) LAUNCH_FIR(kR, true, false, 4, 4, false);
+            else LAUNCH_FIR(kR, false, false, 4, 4, false);
         } else if (PS == 2) {
-            if (f->packed) LAUNCH_FIR(true, false, 3, 2);
-            else LAUNCH_FIR(false, false, 3, 2);
+            if (f->packed) LAUNCH_FIR(kR, true, false, 3, 2, false);
+            else LAUNCH_FIR(kR, false, false, 3, 2, false);
         } else {
-            if (f->packed) LAUNCH_FIR(true, false, 1, 1);
-            else LAUNCH_FIR(false, false, 1, 1);
+            if (f->packed) LAUNCH_FIR(kR, true, false, 1, 1, false);
+            else LAUNCH_FIR(kR, false, false, 1, 1, false);
         }
 #undef LAUNCH_FIR
         SGPU_LAUNCH_CHECK();
@@ -725,11 +756,11 @@ SGPU_EXPORT int sgpu_fir_reset(sgpu_fir *f) {
 SGPU_EXPORT int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(f->device);
-    std::vector<double> taps(f->T);
-    for (size_t i = 0; i < f->T; ++i) taps[i] = (double)f->taps_f32[i];
+    std::vector<double> taps(f->taps_f32.size());
+    for (size_t i = 0; i < taps.size(); ++i) taps[i] = (double)f->taps_f32[i];
     sgpu_fir *c = nullptr;
-    int st = sgpu_fir_create(taps.data(), f->T, SGPU_TAPS_REAL, f->C, f->scale_re, f->scale_im, f->is_decim,
-                             f->M, &c);
+    int st = sgpu_fir_create(taps.data(), f->T, f->complex_taps ? SGPU_TAPS_COMPLEX : SGPU_TAPS_REAL, f->C,
+                             f->scale_re, f->scale_im, f->is_decim, f->M, &c);
     if (st) return st;
     if (f->T > 1) {
         SGPU_CUDA(cudaDeviceSynchronize());
@@ -747,9 +778,9 @@ SGPU_EXPORT int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out) {
 struct sgpu_interp {
     int device = 0, sm_count = 0;
     size_t T = 0, C = 0, L = 1, S = 0;  // S = sub-filter length
-    bool packed = true;
+    bool packed = true, complex_taps = false;
     double scale_re = 1.0, scale_im = 0.0;  // stored, never applied (pfb.rs:85-90)
-    std::vector<float> phase_taps;           // [L][S]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first)
+    std::vector<float> phase_taps;           // [L][S][tw]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first)
     int Qpad = 0;
     float *d_taps = nullptr;
     float2 *d_hist[2] = {nullptr, nullptr};  // S samples per channel: the PFB window (oldest first)
@@ -758,14 +789,16 @@ struct sgpu_interp {
     HostPipe pipe;
 };
 
-static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S values */) {
-    const int L = (int)f->L, S = (int)f->S;
-    f->phase_taps.assign((size_t)L * S, 0.f);
+static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S (complex: x2) values */) {
+    const int L = (int)f->L, S = (int)f->S, tw = f->complex_taps ? 2 : 1;
+    f->phase_taps.assign((size_t)L * S * tw, 0.f);
     for (int p = 0; p < L; ++p)
-        for (int j = 0; j < S; ++j) f->phase_taps[(size_t)p * S + j] = (float)taps_eff[p + (size_t)(S - 1 - j) * L];
-    f->Qpad = (int)round_up((size_t)S, 2 * kR);
+        for (int j = 0; j < S; ++j)
+            for (int c = 0; c < tw; ++c)
+                f->phase_taps[((size_t)p * S + j) * tw + c] = (float)taps_eff[(p + (size_t)(S - 1 - j) * L) * tw + c];
+    f->Qpad = (int)round_up((size_t)S, 2 * (f->complex_taps ? 8 : kR));
     std::vector<float> img;
-    build_tap_image(f->phase_taps, L, S, f->Qpad, f->packed, img);
+    build_tap_image(f->phase_taps, L, S, f->Qpad, tw, img);
     SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
     SGPU_CUDA(cudaMemcpy(f->d_taps, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
     // window of S samples; kernels treat the last S-1 as "history" (T-1 with T = S)
@@ -778,7 +811,7 @@ static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S values */)
 }
 
 static int interp_create_common(const double *taps_eff, size_t n_eff, size_t n_taps, size_t n_channels,
-                                size_t L, size_t S, double sre, double sim, sgpu_interp **out) {
+                                size_t L, size_t S, double sre, double sim, bool complex_taps, sgpu_interp **out) {
     (void)n_eff;
     if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels == 0");
     if (L > 4096 || S > (1u << 20)) return fail(SGPU_ERR_UNSUPPORTED, "interpolation/sub-filter too large");
@@ -795,7 +828,8 @@ static int interp_create_common(const double *taps_eff, size_t n_eff, size_t n_t
     f->S = S;
     f->scale_re = sre;
     f->scale_im = sim;
-    f->packed = packed_default();
+    f->complex_taps = complex_taps;
+    f->packed = complex_taps ? true : packed_default();
     st = interp_build(f, taps_eff);
     if (st) { sgpu_interp_destroy(f); return st; }
     *out = f;
@@ -810,14 +844,14 @@ SGPU_EXPORT int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapki
         return fail(SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO, "FIR Filter Error CoefficientsLengthZero");
     if (interpolation < 1)  // interp.rs:30-31
         return fail(SGPU_ERR_FIR_INTERPOLATION_LESS_THAN_ONE, "FIR Filter Error InterpolationLessThanOne");
-    if (kind == SGPU_TAPS_COMPLEX) return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet");
+    const size_t tw = kind == SGPU_TAPS_COMPLEX ? 2 : 1;
     // interp.rs:35-40: sub-filter length through an f32 quotient
     const float q = (float)n_taps / (float)interpolation;
     const size_t S = (q == floorf(q)) ? (size_t)q : (size_t)ceilf(q);
     const size_t eff = S * interpolation;  // interp.rs:43
-    std::vector<double> padded(eff > n_taps ? eff : n_taps, 0.0);
-    for (size_t i = 0; i < n_taps; ++i) padded[i] = taps[i];
-    return interp_create_common(padded.data(), eff, n_taps, n_channels, interpolation, S, 1.0, 0.0, out);
+    std::vector<double> padded((eff > n_taps ? eff : n_taps) * tw, 0.0);
+    for (size_t i = 0; i < n_taps * tw; ++i) padded[i] = taps[i];
+    return interp_create_common(padded.data(), eff, n_taps, n_channels, interpolation, S, 1.0, 0.0, tw == 2, out);
 }
 
 SGPU_EXPORT int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
@@ -828,11 +862,11 @@ SGPU_EXPORT int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind 
         return fail(SGPU_ERR_FIR_NOT_ENOUGH_FILTERS, "FIR Filter Error NotEnoughFilters");
     if (n_taps == 0 || !taps)  // pfb.rs:27-28
         return fail(SGPU_ERR_FIR_COEFFICIENTS_LENGTH_ZERO, "FIR Filter Error CoefficientsLengthZero");
-    if (kind == SGPU_TAPS_COMPLEX) return fail(SGPU_ERR_UNSUPPORTED, "complex taps are not implemented yet");
     const size_t S = n_taps / filters;  // pfb.rs:32 (truncating)
     if (S == 0)  // reference: Window::new(0) assertion panic (window/mod.rs:18)
         return fail(SGPU_ERR_FIR_NOT_ENOUGH_FILTERS, "FIR Filter Error NotEnoughFilters (filters > taps)");
-    return interp_create_common(taps, S * filters, n_taps, n_channels, filters, S, scale_re, scale_im, out);
+    return interp_create_common(taps, S * filters, n_taps, n_channels, filters, S, scale_re, scale_im,
+                                kind == SGPU_TAPS_COMPLEX, out);
 }
 
 SGPU_EXPORT int sgpu_interp_destroy(sgpu_interp *f) {
@@ -866,7 +900,7 @@ SGPU_EXPORT int sgpu_interp_coefficients(const sgpu_interp *f, double *out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     // pfb.rs:71-73: each DotProduct's stored order = rev_sub_coefs; rev_sub[S-1-idx] = h[p + idx*L]
     // so stored[i] = h[p + (S-1-i)*L] = phase_taps[p][i]
-    for (size_t i = 0; i < f->L * f->S; ++i) out[i] = (double)f->phase_taps[i];
+    for (size_t i = 0; i < f->phase_taps.size(); ++i) out[i] = (double)f->phase_taps[i];
     return SGPU_OK;
 }
 
@@ -891,8 +925,8 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     a.vec_in = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (istr % 2 == 0);
     a.vec_out = 0;
     a.scale_re = 1.f;
-    const int tw = 1;
-    if (env_int("SGPU_PIPE", 1)) {
+    const int tw = f->complex_taps ? 2 : 1;
+    if (!f->complex_taps && env_int("SGPU_PIPE", 1)) {
         // persistent multi-stage interpolator (fir_pipe.cuh)
         int PSp = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
         const int wantp = env_int("SGPU_INT_PS", 0);
@@ -939,30 +973,35 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     int PS = f->L >= 2 ? 2 : 1;
     const int want = env_int("SGPU_INT_PS", 0);
     if ((want == 1 || want == 2 || want == 4) && want <= (int)f->L) PS = want;
+    const int R = f->complex_taps ? 8 : kR;
     const int OT = kNT / PS;
-    const int rows = f->Qpad / kR + OT;
+    const int rows = f->Qpad / R + OT;
     a.RS = rows | 1;
-    const size_t plane_f4 = (size_t)(kR / 2) * a.RS + 1;
-    const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * tw * sizeof(float) +
-                        (size_t)OT * (kR * f->L + 1) * sizeof(float2);
+    const size_t plane_f4 = (size_t)(R / 2) * a.RS + 1;
+    const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad * tw + kTapSkew) * sizeof(float) +
+                        (size_t)OT * (R * f->L + 1) * sizeof(float2);
     if (smem > (size_t)kMaxSmem)
         return fail(SGPU_ERR_UNSUPPORTED, "interpolator tile needs %zu bytes of shared memory", smem);
-    const long long tiles = ((long long)n_in + (long long)OT * kR - 1) / ((long long)OT * kR);
+    const long long tiles = ((long long)n_in + (long long)OT * R - 1) / ((long long)OT * R);
     dim3 grid((unsigned)tiles, (unsigned)f->C);
     int st;
-#define LAUNCH_INT(PK, PSV)                                     \
-    do {                                                        \
-        auto kern = fir_interp_kernel<kR, PK, kNT, 4, PSV>;     \
-        st = set_smem(kern, smem);                              \
-        if (st) return st;                                      \
-        kern<<<grid, kNT, smem, s>>>(a);                        \
+#define LAUNCH_INT(RV, PK, PSV, CTV)                                    \
+    do {                                                                \
+        auto kern = fir_interp_kernel<RV, PK, kNT, 4, PSV, CTV>;        \
+        st = set_smem(kern, smem);                                      \
+        if (st) return st;                                              \
+        kern<<<grid, kNT, smem, s>>>(a);                                \
     } while (0)
-    if (PS == 4) {
-        if (f->packed) LAUNCH_INT(true, 4); else LAUNCH_INT(false, 4);
+    if (f->complex_taps) {
+        if (PS == 4) LAUNCH_INT(8, true, 4, true);
+        else if (PS == 2) LAUNCH_INT(8, true, 2, true);
+        else LAUNCH_INT(8, true, 1, true);
+    } else if (PS == 4) {
+        if (f->packed) LAUNCH_INT(kR, true, 4, false); else LAUNCH_INT(kR, false, 4, false);
     } else if (PS == 2) {
-        if (f->packed) LAUNCH_INT(true, 2); else LAUNCH_INT(false, 2);
+        if (f->packed) LAUNCH_INT(kR, true, 2, false); else LAUNCH_INT(kR, false, 2, false);
     } else {
-        if (f->packed) LAUNCH_INT(true, 1); else LAUNCH_INT(false, 1);
+        if (f->packed) LAUNCH_INT(kR, true, 1, false); else LAUNCH_INT(kR, false, 1, false);
     }
 #undef LAUNCH_INT
     SGPU_LAUNCH_CHECK();
@@ -1032,7 +1071,7 @@ SGPU_EXPORT int sgpu_interp_execute_phase(sgpu_interp *f, size_t index, float *o
         if (st) return st;
         d_out = (float2 *)f->stage.out;
     }
-    const int tw = 1;
+    const int tw = f->complex_taps ? 2 : 1;
     pfb_phase_kernel<<<(unsigned)ceil_div(f->C, 128), 128, 0, s>>>(f->d_hist[f->cur], (int)f->S, f->d_taps,
                                                                      f->Qpad, tw, (int)index, d_out, (int)f->C);
     SGPU_LAUNCH_CHECK();
@@ -1075,11 +1114,15 @@ SGPU_EXPORT int sgpu_interp_clone(const sgpu_interp *f, sgpu_interp **out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(f->device);
     // rebuild the effective tap vector hpad[p + (S-1-j)*L] = phase_taps[p][j]
-    std::vector<double> eff(f->L * f->S);
+    const size_t tw = f->complex_taps ? 2 : 1;
+    std::vector<double> eff(f->L * f->S * tw);
     for (size_t p = 0; p < f->L; ++p)
-        for (size_t j = 0; j < f->S; ++j) eff[p + (f->S - 1 - j) * f->L] = (double)f->phase_taps[p * f->S + j];
+        for (size_t j = 0; j < f->S; ++j)
+            for (size_t c2 = 0; c2 < tw; ++c2)
+                eff[(p + (f->S - 1 - j) * f->L) * tw + c2] = (double)f->phase_taps[(p * f->S + j) * tw + c2];
     sgpu_interp *c = nullptr;
-    int st = interp_create_common(eff.data(), eff.size(), f->T, f->C, f->L, f->S, f->scale_re, f->scale_im, &c);
+    int st = interp_create_common(eff.data(), f->L * f->S, f->T, f->C, f->L, f->S, f->scale_re, f->scale_im,
+                                  f->complex_taps, &c);
     if (st) return st;
     SGPU_CUDA(cudaDeviceSynchronize());
     SGPU_CUDA(cudaMemcpy(c->d_hist[c->cur], f->d_hist[f->cur], f->C * f->S * sizeof(float2),

@@ -48,40 +48,59 @@ __device__ __forceinline__ void load_row(float2 (&W)[2 * R], const float4 *__res
 }
 
 // One chunk of R taps.  OFF = 0 for even chunks, R for odd ones (see header comment).
-// taps: R floats in shared memory, 16-byte aligned (one LDS.128 = 4 taps).  The packed path feeds
-// the tap as FFMA2's scalar-broadcast operand (SASS `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2`), so no
-// duplicated (g,g) pairs are needed in shared memory or registers.
-template <int R, bool PACKED, int OFF>
-__device__ __forceinline__ void fir_chunk(float2 (&acc)[R], const float2 (&W)[2 * R],
+// taps: R floats (real taps) or R (re, im) pairs (CT, complex taps) in shared memory, 16-byte
+// aligned.  The packed path feeds the tap as FFMA2's scalar-broadcast operand (SASS
+// `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2`), so no duplicated (g,g) pairs are needed.
+// Complex taps (a+bi)(c+di): accA += (c,d)*a, accB += (c,d)*b; the caller combines
+// re = accA.x - accB.y, im = accA.y + accB.x once at the end.  acc holds accA in [0,R), accB in [R,2R).
+template <int R, bool PACKED, int OFF, bool CT>
+__device__ __forceinline__ void fir_chunk(float2 (&acc)[CT ? 2 * R : R], const float2 (&W)[2 * R],
                                           const float *__restrict__ taps) {
     const float4 *t4 = reinterpret_cast<const float4 *>(taps);
+    if constexpr (CT) {
 #pragma unroll
-    for (int u4 = 0; u4 < R / 4; ++u4) {
-        const float4 g = t4[u4];
-        const float gs[4] = {g.x, g.y, g.z, g.w};
+        for (int u2 = 0; u2 < R / 2; ++u2) {
+            const float4 g = t4[u2];  // (a_u, b_u, a_{u+1}, b_{u+1})
+            const float ga[2] = {g.x, g.z}, gb[2] = {g.y, g.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                cmac_real<PACKED>(acc[r], W[(r - (4 * u4 + k) + OFF + 4 * R) & (2 * R - 1)], gs[k], gs[k]);
+                for (int r = 0; r < R; ++r) {
+                    const float2 w = W[(r - (2 * u2 + k) + OFF + 4 * R) & (2 * R - 1)];
+                    cmac_real<PACKED>(acc[r], w, ga[k], ga[k]);
+                    cmac_real<PACKED>(acc[R + r], w, gb[k], gb[k]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u4 = 0; u4 < R / 4; ++u4) {
+            const float4 g = t4[u4];
+            const float gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    cmac_real<PACKED>(acc[r], W[(r - (4 * u4 + k) + OFF + 4 * R) & (2 * R - 1)], gs[k], gs[k]);
+            }
         }
     }
 }
 
 // acc[r] += sum_{k < 2*R*npairs} g[k] * seq[R*row0 + r - k]   (seq = the plane's sample sequence)
-template <int R, bool PACKED>
-__device__ __forceinline__ void fir_core(float2 (&acc)[R], const float4 *__restrict__ plane,
+template <int R, bool PACKED, bool CT = false>
+__device__ __forceinline__ void fir_core(float2 (&acc)[CT ? 2 * R : R], const float4 *__restrict__ plane,
                                          const int RS, const int row0,
                                          const float *__restrict__ taps, const int npairs) {
-    constexpr int TW = 1;  // floats per tap in shared memory
+    constexpr int TW = CT ? 2 : 1;  // floats per tap in shared memory
     float2 W[2 * R];
     load_row<R, 0>(W, plane, RS, row0);
     int row = row0;
     for (int cp = 0; cp < npairs; ++cp) {
         load_row<R, R>(W, plane, RS, row - 1);
-        fir_chunk<R, PACKED, 0>(acc, W, taps);
+        fir_chunk<R, PACKED, 0, CT>(acc, W, taps);
         load_row<R, 0>(W, plane, RS, row - 2);
-        fir_chunk<R, PACKED, R>(acc, W, taps + R * TW);
+        fir_chunk<R, PACKED, R, CT>(acc, W, taps + R * TW);
         row -= 2;
         taps += 2 * R * TW;
     }

@@ -205,8 +205,11 @@ class _InterpHandle(_FirHandle):
         return lib.sgpu_interp_sub_len(self._h)
 
     def _phase_coefs(self):
-        out = np.zeros(self.len() * self.sub_len())
+        cx = getattr(self, "_complex", False)
+        out = np.zeros(self.len() * self.sub_len() * (2 if cx else 1))
         check(lib.sgpu_interp_coefficients(self._h, dptr(out)))
+        if cx:
+            out = out.view(np.complex128)
         return out.reshape(self.len(), self.sub_len())
 
     def get_state(self):
@@ -239,6 +242,7 @@ class PolyPhaseFilterBank(_InterpHandle):
         _FirHandle.__init__(self)
         cv, kind, n, _ = as_doubles(coefficients)
         self._C = n_channels
+        self._complex = kind == _ffi.TAPS_COMPLEX
         _check_ctor(lib.sgpu_pfb_create(dptr(cv), n, kind, n_channels, max(filters, 0),
                                         *_scale_parts(scale), C.byref(self._h)))
 
@@ -262,6 +266,7 @@ class InterpolatingFIRFilter(_InterpHandle):
         _FirHandle.__init__(self)
         cv, kind, n, _ = as_doubles(coefficents)
         self._C = n_channels
+        self._complex = kind == _ffi.TAPS_COMPLEX
         _check_ctor(lib.sgpu_interp_create(dptr(cv), n, kind, n_channels, max(interpolation, 0),
                                            C.byref(self._h)))
 

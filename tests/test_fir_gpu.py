@@ -262,3 +262,55 @@ def test_pfb_push_execute(fir):
         ref.push(s)
         for p in range(4):
             assert abs(bank.execute(p) - ref.execute(p)) <= TOL * 5
+
+
+# ------------------------------------------------------------------ complex taps (Coef = Complex<f64>)
+def _ctaps(rng, T):
+    return f32_taps(rng.uniform(-1, 1, T)) + 1j * f32_taps(rng.uniform(-1, 1, T))
+
+
+@pytest.mark.parametrize("T", [1, 3, 16, 17, 64, 200])
+def test_fir_complex_taps(fir, T):
+    """FIRFilter<Complex<f64>, Complex<f64>> is a legal instantiation (fir/mod.rs:181-186):
+    complex taps, complex scale (Out * Coef, fir/mod.rs:211)."""
+    rng = np.random.default_rng(T)
+    h = _ctaps(rng, T)
+    x = rand_cf32(rng, (2, 3001))
+    scale = 0.5 - 0.25j
+    f = fir.FIRFilter(h, scale, n_channels=2)
+    got = np.concatenate([f.execute_block(x[:, :1000]), f.execute_block(x[:, 1000:])], axis=1)
+    for c in range(2):
+        assert nerr(got[c], O.fir_fast(h, x[c], scale)) <= TOL
+    assert np.array_equal(f.coefficients(), h[::-1]) and f.get_scale() == scale
+    g = f.clone()
+    y = rand_cf32(rng, (2, 100))
+    assert np.array_equal(f.execute_block(y), g.execute_block(y))
+
+
+@pytest.mark.parametrize("M", [2, 4, 8, 5])
+def test_decim_complex_taps(fir, M):
+    rng = np.random.default_rng(M)
+    h = _ctaps(rng, 96)
+    x = rand_cf32(rng, 5003)
+    got = fir.DecimatingFIRFilter(h, 1.0 + 0.5j, M).execute_block(x)
+    ref = O.fir_fast(h, x, 1.0 + 0.5j, M)
+    assert len(got) == len(ref) and nerr(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("L", [1, 2, 4, 3])
+def test_interp_complex_taps(fir, L):
+    rng = np.random.default_rng(L)
+    h = _ctaps(rng, 50)
+    x = rand_cf32(rng, (2, 1500))
+    f = fir.InterpolatingFIRFilter(h, L, n_channels=2)
+    got = np.concatenate([f.execute_block(x[:, :7]), f.execute_block(x[:, 7:])], axis=1)
+    for c in range(2):
+        assert nerr(got[c], O.firinterp_fast(h, L, x[c])) <= TOL
+    bank = fir.PolyPhaseFilterBank(h, 4, 1.0)
+    ref = O.PolyPhaseFilterBank(h, 4, 1.0)
+    assert np.array_equal(bank.coefficents(), ref.coefficents())
+    for s_ in x[0, :6]:
+        bank.push(s_)
+        ref.push(s_)
+        for p_ in range(4):
+            assert abs(bank.execute(p_) - ref.execute(p_)) <= TOL * 20
