@@ -202,7 +202,9 @@ int sgpu_iir_get_state(sgpu_iir *f, float *state, uint64_t *index);
 int sgpu_iir_set_state(sgpu_iir *f, const float *state, uint64_t index);
 int sgpu_iir_reset(sgpu_iir *f);
 size_t sgpu_iir_state_len(const sgpu_iir *f); /* complex values per channel */
-/* Execution strategy: -1 auto, 0 one-channel-per-thread batch, 1 long-stream chunked scan. */
+/* Execution strategy: -1 auto, 0 one channel per thread (batch), 1 chunked scan (fused warm-up scan
+ * when the filter's memory decays within 2^16 samples, else the three-pass scan), 2 three-pass scan
+ * (zero-state pass, f64 carry recurrence, output pass) regardless of the decay. */
 int sgpu_iir_set_mode(sgpu_iir *f, int mode);
 
 /* ---- DotProduct ----------------------------------------------------------------------

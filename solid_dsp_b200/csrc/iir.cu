@@ -25,7 +25,9 @@ using namespace sgpu;
 namespace {
 
 constexpr int kMaxSec = 16;
-constexpr int kTile = 16;  // samples per channel per tile (128 bytes)
+// Shared-memory tile: 32 rows (one per lane) of TILE samples = TILE/2 float4 + 1 float4 of padding.
+// With the odd pitch the lanes' LDS.128/STS.128 at a fixed column and the loader's rows of TILE/2
+// consecutive float4 are both bank-conflict free, and every access is base + immediate.
 
 struct SosCoefs {  // normalised by a0 (sos.rs:62-68); na* are the negated feedback taps
     float b0[kMaxSec], b1[kMaxSec], b2[kMaxSec], na1[kMaxSec], na2[kMaxSec];
@@ -43,11 +45,25 @@ struct IirArgs {
     int write_out;
     int factor, idx0;  // decimation / interpolation factor, decimator counter on entry
     int vec;           // 16-byte aligned pointers and even strides -> cp.async path
-    long long skip;    // scan pass A: samples skipped at the head of every chunk (see iir_run)
-    // scan layout: chunk slots [0, NP) are full chunks of Lc samples, the slot `tail_slot` (a
-    // multiple of 32, so it starts its own warp) holds the ragged tail, every other slot is empty
+    // Row layouts (a warp owns 32 rows with affine addressing; lane = row):
+    //   0 plain     : row = channel.
+    //   1 three-pass: per channel P slots; chunk p (Lc samples) in slot p < NP, the ragged tail chunk
+    //                 alone in the warp that starts at slot `tail_slot`.  Start states come from
+    //                 state_in[slot], end states go to state_out[slot].
+    //   2 fused scan, chunks of one channel side by side (C < 32): warp 0 = chunk 0 of every channel,
+    //                 then per channel Pm/32 warps with chunks 1 .. NPt-2, last warp = chunk NPt-1 of
+    //                 every channel.
+    //   3 fused scan, channels side by side (C >= 32): warp (p, cb) = chunk p of channels 32cb .. 32cb+31.
+    //   Fused: chunk 0 starts from the channel's state; chunk p >= 1 starts from zero state `warm`
+    //   samples early and discards those outputs (the filter's memory has decayed below 1e-10 by
+    //   then); the last chunk (NPt-1, `last_len` samples) leaves the channel's new state in state_out[channel].
+    int layout;
+    long long n_warps;  // warps that have rows (the grid is rounded up to whole blocks)
     int NP, tail_slot;
     long long tail_off, tail_len;
+    int NPt, Pm, CW;
+    long long last_len;
+    long long warm;    // multiple of the tile length
     SosCoefs k;
 };
 
@@ -65,25 +81,37 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// one biquad on one complex sample, direct form II, real coefficients
-template <bool PACKED>
+// one biquad on one complex sample, direct form II, real coefficients.  UNIT_B0: the section's b0
+// has been folded into the cascade gain (b0 == 1), which saves the multiply: 4 FMA-pipe operations
+// per real component instead of 5.
+template <bool UNIT_B0>
 __device__ __forceinline__ float2 biquad(float2 x, float2 &v1, float2 &v2, const float b0, const float b1,
                                          const float b2, const float na1, const float na2) {
-    float2 v0, y;
-    if constexpr (PACKED) {
-        v0 = __ffma2_rn(v1, make_float2(na1, na1), x);
-        v0 = __ffma2_rn(v2, make_float2(na2, na2), v0);
+    // packed: one fma.rn.f32x2 (SASS FFMA2, coefficient as the scalar-broadcast operand) per complex FMA
+    float2 v0 = __ffma2_rn(v1, make_float2(na1, na1), x), y;
+    v0 = __ffma2_rn(v2, make_float2(na2, na2), v0);
+    if constexpr (UNIT_B0) {
+        y = __ffma2_rn(v1, make_float2(b1, b1), v0);
+        y = __ffma2_rn(v2, make_float2(b2, b2), y);
+    } else {
         y = __fmul2_rn(v2, make_float2(b2, b2));
         y = __ffma2_rn(v1, make_float2(b1, b1), y);
         y = __ffma2_rn(v0, make_float2(b0, b0), y);
-    } else {
-        v0.x = fmaf(na2, v2.x, fmaf(na1, v1.x, x.x));
-        v0.y = fmaf(na2, v2.y, fmaf(na1, v1.y, x.y));
-        y.x = fmaf(b0, v0.x, fmaf(b1, v1.x, b2 * v2.x));
-        y.y = fmaf(b0, v0.y, fmaf(b1, v1.y, b2 * v2.y));
     }
     v2 = v1;
     v1 = v0;
+    return y;
+}
+
+// the whole cascade on one sample.  FOLD: sections 0 .. NSEC-2 have b0 == 1 and the last section
+// carries the product of all b0 (see fold_sections on the host side).
+template <int NSEC, bool FOLD>
+__device__ __forceinline__ float2 cascade(float2 y, float2 (&v1)[NSEC], float2 (&v2)[NSEC], const SosCoefs &k) {
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        if (FOLD && s < NSEC - 1) y = biquad<true>(y, v1[s], v2[s], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
+        else y = biquad<false>(y, v1[s], v2[s], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
+    }
     return y;
 }
 
@@ -92,66 +120,103 @@ __device__ __forceinline__ float2 biquad(float2 x, float2 &v1, float2 &v2, const
 // Full tiles (every row of the warp has 16 more samples) take the fast path: cp.async prefetch of
 // the next tile, unpredicated fully unrolled cascade, 16-byte coalesced stores.  The ragged tail
 // (and every tile of the interpolating wrapper) takes the guarded path.
-template <int NSEC, bool PACKED, int WRAP>
-__global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const IirArgs a) {
+template <int NSEC, int WRAP, bool FOLD, int TILE, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a) {
     extern __shared__ float4 smem[];
+    constexpr int kTile = TILE;          // samples per channel per tile (TILE * 8 bytes)
+    constexpr int LPR = TILE / 2;        // loader lanes per row (16 bytes each)
+    constexpr int RPI = 32 / LPR;        // rows per loader instruction
+    static_assert(LPR * RPI == 32, "TILE must be 16, 32 or 64");
+    constexpr int kRowF4 = LPR + 1;
+    constexpr int kTileF4 = 32 * kRowF4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long VC = (long long)a.C * a.P;
-    const long long vc0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
-    if (vc0 >= VC) return;
-    float4 *buf = smem + warp * (2 * 32 * 8);
+    const long long wi = (long long)blockIdx.x * (blockDim.x >> 5) + warp;  // global warp index
+    const long long vc0 = wi * 32;
+    float4 *buf = smem + warp * (2 * kTileF4);
 
-    // affine row addressing for this warp (rows = 32 consecutive virtual channels)
-    long long in_base, out_base, rstr_in, rstr_out, p0 = 0;
-    bool is_tail = false;
-    if (a.P == 1) {
+    // affine row addressing for this warp; len0 = length of a valid row, nrows = valid rows (a prefix)
+    long long in_base, out_base, rstr_in, rstr_out, warm = 0, len0 = 0;
+    long long st_in = -1, st_out = -1;  // this lane's row in state_in / state_out, -1 = zero / discard
+    int nrows = 0;
+    const long long n_loop = WRAP == 2 ? a.n_in * a.factor : a.n_in;
+    bool is_tail = false;  // layout 1
+    long long p0 = 0;      // layout 1
+    if (a.layout == 0) {
+        if (vc0 >= a.C) return;
         in_base = vc0 * a.in_stride;
         out_base = vc0 * a.out_stride;
         rstr_in = a.in_stride;
         rstr_out = a.out_stride;
-    } else {
-        const long long c = vc0 / a.P;
-        p0 = vc0 - c * a.P;
+        nrows = (int)min(32LL, (long long)a.C - vc0);
+        len0 = n_loop;
+        st_in = st_out = vc0 + lane;
+    } else if (a.layout == 1) {
+        if (vc0 >= (long long)a.C * a.P) return;
+        const long long chan = vc0 / a.P;
+        p0 = vc0 - chan * a.P;
         is_tail = p0 == a.tail_slot;
         const long long off = is_tail ? a.tail_off : p0 * a.Lc;
-        in_base = c * a.in_stride + off + (is_tail ? 0 : a.skip);
-        out_base = c * a.out_stride + off;
-        rstr_in = a.Lc;
-        rstr_out = a.Lc;
+        in_base = chan * a.in_stride + off;
+        out_base = chan * a.out_stride + off;
+        rstr_in = rstr_out = a.Lc;
+        nrows = is_tail ? 1 : (int)max(0LL, min(32LL, (long long)a.NP - p0));
+        len0 = is_tail ? a.tail_len : a.Lc;
+        st_in = st_out = vc0 + lane;
+    } else {
+        // fused scan: (first chunk index, first channel, row stride) of the warp
+        long long chunk, chan;
+        bool by_channel;  // rows = consecutive channels (true) or consecutive chunks (false)
+        if (a.layout == 3) {
+            if (wi >= (long long)a.NPt * a.CW) return;
+            chunk = wi / a.CW;
+            chan = (wi - chunk * a.CW) * 32;
+            by_channel = true;
+        } else {
+            const long long mid = (long long)a.C * (a.Pm / 32);
+            if (wi > mid + 1) return;
+            by_channel = wi == 0 || wi == mid + 1;
+            if (wi == 0) { chunk = 0; chan = 0; }
+            else if (wi == mid + 1) { chunk = a.NPt - 1; chan = 0; }
+            else {
+                chan = (wi - 1) / (a.Pm / 32);
+                chunk = 1 + ((wi - 1) - chan * (a.Pm / 32)) * 32;
+            }
+        }
+        warm = chunk > 0 ? a.warm : 0;
+        const long long off = chunk * a.Lc - warm;
+        in_base = chan * a.in_stride + off;
+        out_base = chan * a.out_stride + off;  // the first `warm` outputs of a row are never stored
+        if (by_channel) {
+            rstr_in = a.in_stride;
+            rstr_out = a.out_stride;
+            nrows = (int)min(32LL, (long long)a.C - chan);
+            len0 = (chunk == a.NPt - 1 ? a.last_len : a.Lc) + warm;
+            if (chunk == 0) st_in = chan + lane;
+            if (chunk == a.NPt - 1) st_out = chan + lane;
+        } else {
+            rstr_in = rstr_out = a.Lc;
+            nrows = (int)max(0LL, min(32LL, (long long)(a.NPt - 1) - chunk));  // chunks 1 .. NPt-2
+            len0 = a.Lc + warm;
+        }
     }
-    // per-row length in "loop samples" (inputs for WRAP 0/1, outputs for WRAP 2).  Valid rows are
-    // always a prefix of the warp's 32 rows.
-    const long long n_loop = WRAP == 2 ? a.n_in * a.factor : a.n_in;
-    auto row_len = [&](int r) -> long long {
-        if (vc0 + r >= VC) return 0;
-        if (a.P == 1) return n_loop;
-        if (is_tail) return r == 0 ? a.tail_len : 0;
-        return p0 + r < a.NP ? a.Lc - a.skip : 0;
-    };
+    if (nrows <= 0) return;
+    auto row_len = [&](int r) -> long long { return r < nrows ? len0 : 0; };
     const long long my_len = row_len(lane);
-    const int nvalid = __popc(__ballot_sync(0xffffffffu, my_len > 0));
-    if (nvalid == 0) return;
-    long long max_len = my_len, min_len = my_len > 0 ? my_len : 0x7fffffffffffffffLL;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long u = __shfl_xor_sync(0xffffffffu, max_len, o);
-        const long long v = __shfl_xor_sync(0xffffffffu, min_len, o);
-        max_len = u > max_len ? u : max_len;
-        min_len = v < min_len ? v : min_len;
-    }
+    const int nvalid = nrows;
+    const long long max_len = len0, min_len = len0;
     const long long ntiles = (max_len + kTile - 1) / kTile;
     const long long full_tiles = WRAP == 2 ? 0 : min_len / kTile;
+    const long long warm_tiles = warm / kTile;  // <= full_tiles: every valid row is longer than `warm`
 
     // state
     float2 v1[NSEC], v2[NSEC];
-    const long long my_vc = vc0 + lane;
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
         v1[s] = make_float2(0.f, 0.f);
         v2[s] = make_float2(0.f, 0.f);
     }
-    if (a.state_in && lane < nvalid) {
-        const float4 *sp = reinterpret_cast<const float4 *>(a.state_in + my_vc * (2 * NSEC));
+    if (a.state_in && lane < nvalid && st_in >= 0) {
+        const float4 *sp = reinterpret_cast<const float4 *>(a.state_in + st_in * (2 * NSEC));
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) {
             const float4 t = sp[s];
@@ -160,29 +225,47 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         }
     }
 
-    const int lrow = lane >> 3, lj = lane & 7;  // loader role: rows lrow + 4*i, chunk lj
-    const int swz = lane & 7;
+    // loader role: a tile is 32 * LPR 16-byte chunks; the lane moves chunks i*32 + lane, i < LPR
+    const int lrow = lane / LPR, lj = lane % LPR;  // rows lrow + RPI * i, chunk lj
+    auto role_r = [&](int i) { return lrow + RPI * i; };
+    auto role_c = [&](int) { return lj; };
     int dec_cnt = a.idx0;                          // decimator phase (WRAP 1)
     float2 *dec_ptr = a.out + out_base + (long long)lane * rstr_out;  // next decimated output (WRAP 1)
 
     // ------------------------------------------------------------------ fast path: full tiles
     if (full_tiles > 0) {
-        // rows past the valid prefix re-read the last valid row (never out of bounds, never stored)
-        const float2 *ld_ptr = a.in + in_base + 2 * lj;
-        float2 *st_ptr = a.out + out_base + (long long)lrow * rstr_out + 2 * lj;
-        const long long st_step = 4 * rstr_out;
+        // loader / storer role: the lane's i-th 16-byte chunk of a tile is chunk role_c(i) of row
+        // role_r(i).  `whole` (warp-uniform): all 32 rows valid and 16-byte accesses allowed -> no
+        // per-row predicates or clamps.
+        const bool whole = a.vec && nvalid == 32;
+        const float2 *ld_ptr = a.in + in_base;
+        float2 *st_ptr = a.out + out_base;
+        const long long ld_step = RPI * rstr_in, st_step = RPI * rstr_out;
+        const long long ld_role = (long long)lrow * rstr_in + 2 * lj, st_role = (long long)lrow * rstr_out + 2 * lj;
+        const int role_off = lrow * kRowF4 + lj;
         auto prefetch = [&](float4 *dst) {
+            if (whole) {
+                const float2 *src = ld_ptr + ld_role;
+                float4 *d = dst + role_off;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = lrow + 4 * i;
-                const int rl = r < nvalid ? r : nvalid - 1;
-                const float2 *src = ld_ptr + (long long)rl * rstr_in;
-                float4 *d = dst + r * 8 + (lj ^ (r & 7));
-                if (a.vec) {
-                    cp_async16(d, src);
-                } else {
-                    cp_async8(d, src);
-                    cp_async8(reinterpret_cast<float2 *>(d) + 1, src + 1);
+                for (int i = 0; i < LPR; ++i) {
+                    cp_async16(d + i * RPI * kRowF4, src);
+                    src += ld_step;
+                }
+            } else {
+                // rows past the valid prefix re-read the last valid row (never out of bounds, never stored)
+#pragma unroll
+                for (int i = 0; i < LPR; ++i) {
+                    const int r = role_r(i), c = role_c(i);
+                    const int rl = r < nvalid ? r : nvalid - 1;
+                    const float2 *src = ld_ptr + (long long)rl * rstr_in + 2 * c;
+                    float4 *d = dst + r * kRowF4 + c;
+                    if (a.vec) {
+                        cp_async16(d, src);
+                    } else {
+                        cp_async8(d, src);
+                        cp_async8(reinterpret_cast<float2 *>(d) + 1, src + 1);
+                    }
                 }
             }
             cp_async_commit();
@@ -190,51 +273,55 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         };
         prefetch(buf);
         for (long long t = 0; t < full_tiles; ++t) {
-            float4 *cur = buf + (t & 1) * (32 * 8);
+            float4 *cur = buf + (t & 1) * kTileF4;
             if (t + 1 < full_tiles) {
-                prefetch(buf + ((t + 1) & 1) * (32 * 8));
+                prefetch(buf + ((t + 1) & 1) * kTileF4);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
             __syncwarp();
-            float4 *myrow = cur + lane * 8;
+            float4 *myrow = cur + lane * kRowF4;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 *cell = myrow + (j ^ swz);
-                const float4 xin = *cell;
+            for (int j = 0; j < LPR; ++j) {
+                const float4 xin = myrow[j];
                 float2 y0 = make_float2(xin.x, xin.y), y1 = make_float2(xin.z, xin.w);
-#pragma unroll
-                for (int s = 0; s < NSEC; ++s)
-                    y0 = biquad<PACKED>(y0, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                y0 = cascade<NSEC, FOLD>(y0, v1, v2, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y0; ++dec_ptr; }
                 }
-#pragma unroll
-                for (int s = 0; s < NSEC; ++s)
-                    y1 = biquad<PACKED>(y1, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                y1 = cascade<NSEC, FOLD>(y1, v1, v2, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y1; ++dec_ptr; }
                 }
-                if constexpr (WRAP == 0) *cell = make_float4(y0.x, y0.y, y1.x, y1.y);
+                if constexpr (WRAP == 0) myrow[j] = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
             if constexpr (WRAP == 0) {
                 __syncwarp();
-                if (a.write_out) {
-                    float2 *dst = st_ptr;
+                if (a.write_out && t >= warm_tiles) {
+                    if (whole) {
+                        float2 *dst = st_ptr + st_role;
+                        const float4 *src = cur + role_off;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = lrow + 4 * i;
-                        const float4 v = cur[r * 8 + (lj ^ (r & 7))];
-                        if (r < nvalid) {
-                            if (a.vec) {
-                                *reinterpret_cast<float4 *>(dst) = v;
-                            } else {
-                                dst[0] = make_float2(v.x, v.y);
-                                dst[1] = make_float2(v.z, v.w);
+                        for (int i = 0; i < LPR; ++i) {
+                            *reinterpret_cast<float4 *>(dst) = src[i * RPI * kRowF4];
+                            dst += st_step;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < LPR; ++i) {
+                            const int r = role_r(i), c = role_c(i);
+                            const float4 v = cur[r * kRowF4 + c];
+                            float2 *dst = st_ptr + (long long)r * rstr_out + 2 * c;
+                            if (r < nvalid) {
+                                if (a.vec) {
+                                    *reinterpret_cast<float4 *>(dst) = v;
+                                } else {
+                                    dst[0] = make_float2(v.x, v.y);
+                                    dst[1] = make_float2(v.z, v.w);
+                                }
                             }
                         }
-                        dst += st_step;
                     }
                 }
                 st_ptr += kTile;
@@ -252,22 +339,22 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         for (long long t = full_tiles; t < ntiles; ++t) {
             const long long s0 = t * kTile;
             if constexpr (WRAP != 2) {
-                for (int i = 0; i < 8; ++i) {
-                    const int r = lrow + 4 * i;
+                for (int i = 0; i < LPR; ++i) {
+                    const int r = role_r(i), lj = role_c(i);
                     const long long rl = row_len(r);
                     const long long sidx = s0 + 2 * lj;
                     const float2 *src = a.in + in_base + (long long)r * rstr_in + sidx;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (sidx < rl) { const float2 q = src[0]; v.x = q.x; v.y = q.y; }
                     if (sidx + 1 < rl) { const float2 q = src[1]; v.z = q.x; v.w = q.y; }
-                    cur[r * 8 + (lj ^ (r & 7))] = v;
+                    cur[r * kRowF4 + lj] = v;
                 }
                 __syncwarp();
             }
-            float2 *myrow2 = reinterpret_cast<float2 *>(cur + lane * 8);
+            float2 *myrow2 = reinterpret_cast<float2 *>(cur + lane * kRowF4);
             for (int n = 0; n < kTile; ++n) {
                 if (s0 + n >= my_len) break;
-                float2 *cell = myrow2 + (((n >> 1) ^ swz) << 1) + (n & 1);
+                float2 *cell = myrow2 + n;
                 float2 y;
                 if constexpr (WRAP == 2) {
                     y = make_float2(0.f, 0.f);
@@ -276,9 +363,7 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
                 } else {
                     y = *cell;
                 }
-#pragma unroll
-                for (int s = 0; s < NSEC; ++s)
-                    y = biquad<PACKED>(y, v1[s], v2[s], a.k.b0[s], a.k.b1[s], a.k.b2[s], a.k.na1[s], a.k.na2[s]);
+                y = cascade<NSEC, FOLD>(y, v1, v2, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y; ++dec_ptr; }
                 } else {
@@ -288,11 +373,11 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
             if constexpr (WRAP != 1) {
                 __syncwarp();
                 if (a.write_out) {
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = lrow + 4 * i;
+                    for (int i = 0; i < LPR; ++i) {
+                        const int r = role_r(i), lj = role_c(i);
                         const long long rl = row_len(r);
                         const long long sidx = s0 + 2 * lj;
-                        const float4 v = cur[r * 8 + (lj ^ (r & 7))];
+                        const float4 v = cur[r * kRowF4 + lj];
                         float2 *dst = a.out + out_base + (long long)r * rstr_out + sidx;
                         if (sidx < rl) dst[0] = make_float2(v.x, v.y);
                         if (sidx + 1 < rl) dst[1] = make_float2(v.z, v.w);
@@ -303,8 +388,8 @@ __global__ void __launch_bounds__(256, (NSEC > 8 ? 2 : 3)) iir_sos_kernel(const 
         }
     }
 
-    if (a.state_out && lane < nvalid) {
-        float4 *sp = reinterpret_cast<float4 *>(a.state_out + my_vc * (2 * NSEC));
+    if (a.state_out && lane < nvalid && st_out >= 0) {
+        float4 *sp = reinterpret_cast<float4 *>(a.state_out + st_out * (2 * NSEC));
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) sp[s] = make_float4(v1[s].x, v1[s].y, v2[s].x, v2[s].y);
     }
@@ -401,21 +486,6 @@ __global__ void __launch_bounds__(128) carry_kernel(int mode, const double *__re
         sbuf[((long long)c * P + tail_slot) * D + lane] = make_float2((float)s[lane].x, (float)s[lane].y);
 }
 
-// Decaying filters (||A^Lc|| < 1e-12): the start state of chunk p is simply the zero-state end state
-// of chunk p-1, so the carry recurrence degenerates into a shift.
-__global__ void shift_states_kernel(const float2 *__restrict__ z, const float2 *__restrict__ state0,
-                                    float2 *__restrict__ sbuf, int D, int P, int NP, int tail_slot, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over C * (NP + 1) * D
-    if (i >= total) return;
-    const int d = (int)(i % D);
-    const long long q = i / D;
-    const int p = (int)(q % (NP + 1));
-    const long long c = q / (NP + 1);
-    const float2 v = p == 0 ? state0[c * D + d] : z[(c * P + p - 1) * D + d];
-    if (p < NP) sbuf[(c * P + p) * D + d] = v;
-    else if (tail_slot >= 0) sbuf[(c * P + tail_slot) * D + d] = v;
-}
-
 // ---- Normal mode: one direct-form II of arbitrary order (iir/mod.rs:98-130,272-280) ---------
 constexpr int kMaxOrder = 64;
 struct NormalArgs {
@@ -478,15 +548,6 @@ __global__ void __launch_bounds__(128) iir_normal_kernel(const NormalArgs a) {
     for (int i = 0; i < W; ++i) a.state[(long long)c * W + i] = w[(head + i) % W];
 }
 
-bool iir_packed_default() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SGPU_IIR_PACKED");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
 int pad_sections(int nsec) {
     const int opts[] = {1, 2, 4, 8, 16};
     for (int o : opts)
@@ -505,11 +566,12 @@ struct sgpu_iir {
     int W = 0, nb = 0, na = 0;        // Normal
     uint64_t index = 0;               // decimator counter (iir/decim.rs:9)
     int mode = -1;
-    bool packed = false;
+    bool fold = false;           // b0 of every section folded into the last one (see fold_sections)
+    std::vector<double> gpre;    // [nsec_pad] product of b0 over the sections in front of s: v_ref = v_dev * gpre[s]
     std::vector<double> ff_raw, fb_raw;  // as given (numerator_coefs()/denominator_coefs() in SOS mode)
     std::vector<double> num_norm, den_norm;  // Normal mode: ff/a0, fb[1..]/a0
     SosCoefs k{};
-    std::vector<double> kd;  // f32-rounded normalised coefs as doubles [nsec][5] = b0,b1,b2,a1,a2
+    std::vector<double> kd;  // the kernel's f32 coefs as doubles [nsec_pad][5] = b0,b1,b2,a1,a2
     float2 *d_state = nullptr;  // SOS: [C][nsec_pad][2]; Normal: [C][W]
     // scan scratch
     float2 *d_z = nullptr, *d_s = nullptr;
@@ -517,7 +579,7 @@ struct sgpu_iir {
     double *d_mat = nullptr;  // [2][D*D]: A^Lc, A^(Lc*CH)
     size_t scratch_vc = 0, scratch_units = 0;
     long long mat_Lc = -1, mat_CH = -1;
-    long long decay_len = -1;  // samples after which ||A^k||_inf < 1e-12 (scan pass A window), -1 = never
+    long long decay_len = -2;  // see decay_length(); -2 = not computed yet, -1 = does not decay
     Staging stage;
     HostPipe pipe;
 };
@@ -537,11 +599,8 @@ void build_transition(const sgpu_iir *f, std::vector<double> &A) {
         st[col] = 1.0;
         double y = 0.0;  // zero input
         for (int s = 0; s < f->nsec_pad; ++s) {
-            double b0 = 1, b1 = 0, b2 = 0, a1 = 0, a2 = 0;
-            if (s < f->nsec) {
-                b0 = f->kd[s * 5 + 0]; b1 = f->kd[s * 5 + 1]; b2 = f->kd[s * 5 + 2];
-                a1 = f->kd[s * 5 + 3]; a2 = f->kd[s * 5 + 4];
-            }
+            const double b0 = f->kd[s * 5 + 0], b1 = f->kd[s * 5 + 1], b2 = f->kd[s * 5 + 2];
+            const double a1 = f->kd[s * 5 + 3], a2 = f->kd[s * 5 + 4];
             const double v1 = st[2 * s], v2 = st[2 * s + 1];
             const double v0 = y - (a1 * v1 + a2 * v2);
             y = b0 * v0 + b1 * v1 + b2 * v2;
@@ -573,37 +632,71 @@ void mat_pow(std::vector<double> A, long long e, std::vector<double> &R, int D) 
     }
 }
 
-template <int NSEC, bool PACKED, int WRAP>
+// Tile shapes (measured on B200, 65536 channels x 2^14, profiles/r1f_iir_tiles.md): 32-sample tiles
+// (256-byte row segments, 4 warps x 3 blocks = 12 warps/SM) reach 5.5 TB/s where 16-sample tiles
+// (128-byte segments, 24 warps/SM) stop at 4.5 TB/s; 64-sample tiles leave too few warps (6/SM).
+constexpr int kScanTile = 32;
+constexpr int kWarpsPerSm = 12;  // resident warps per SM of the plain kernel (smem-limited)
+
+template <int NSEC, int WRAP, bool FOLD>
 int launch_sos_t(const IirArgs &a, cudaStream_t s) {
-    const long long VC = (long long)a.C * a.P;
-    const int warps_per_block = 8;
-    const long long warps = (VC + 31) / 32;
-    const unsigned blocks = (unsigned)((warps + warps_per_block - 1) / warps_per_block);
-    const size_t smem = (size_t)warps_per_block * 2 * 32 * 8 * sizeof(float4);
-    auto kern = iir_sos_kernel<NSEC, PACKED, WRAP>;
+    constexpr int TILE = WRAP == 0 ? kScanTile : 16;
+    constexpr int NW = WRAP == 0 ? 4 : 8;
+    constexpr int MINB = WRAP == 0 ? 3 : (NSEC > 8 ? 2 : 3);
+    const unsigned blocks = (unsigned)((a.n_warps + NW - 1) / NW);
+    const size_t smem = (size_t)NW * 2 * 32 * (TILE / 2 + 1) * sizeof(float4);
+    auto kern = iir_sos_kernel<NSEC, WRAP, FOLD, TILE, NW, MINB>;
     SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, warps_per_block * 32, smem, s>>>(a);
+    kern<<<blocks, NW * 32, smem, s>>>(a);
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
 }
 
-template <int NSEC>
-int launch_sos_n(const IirArgs &a, bool packed, int wrap, cudaStream_t s) {
-    if (wrap == 1) return launch_sos_t<NSEC, false, 1>(a, s);
-    if (wrap == 2) return launch_sos_t<NSEC, false, 2>(a, s);
-    return packed ? launch_sos_t<NSEC, true, 0>(a, s) : launch_sos_t<NSEC, false, 0>(a, s);
+template <int NSEC, bool FOLD>
+int launch_sos_n(const IirArgs &a, int wrap, cudaStream_t s) {
+    if (wrap == 1) return launch_sos_t<NSEC, 1, FOLD>(a, s);
+    if (wrap == 2) return launch_sos_t<NSEC, 2, FOLD>(a, s);
+    return launch_sos_t<NSEC, 0, FOLD>(a, s);
 }
 
 int launch_sos(const sgpu_iir *f, const IirArgs &a, int wrap, cudaStream_t s) {
+#define SGPU_SOS_CASE(N) \
+    case N: return f->fold ? launch_sos_n<N, true>(a, wrap, s) : launch_sos_n<N, false>(a, wrap, s);
     switch (f->nsec_pad) {
-        case 1: return launch_sos_n<1>(a, f->packed, wrap, s);
-        case 2: return launch_sos_n<2>(a, f->packed, wrap, s);
-        case 4: return launch_sos_n<4>(a, f->packed, wrap, s);
-        case 8: return launch_sos_n<8>(a, f->packed, wrap, s);
-        case 16: return launch_sos_n<16>(a, f->packed, wrap, s);
+        SGPU_SOS_CASE(1)
+        SGPU_SOS_CASE(2)
+        SGPU_SOS_CASE(4)
+        SGPU_SOS_CASE(8)
+        SGPU_SOS_CASE(16)
     }
+#undef SGPU_SOS_CASE
     return fail(SGPU_ERR_UNSUPPORTED, "unsupported section count");
+}
+
+// Smallest multiple of 32 with ||A^k||_inf < 1e-10 (A = one-sample zero-input transition of the
+// cascade), searched up to 2^16 samples; -1 = the filter does not decay (or is unstable).  Past that
+// many samples the influence of an older state is 3 orders of magnitude below f32 resolution.
+long long decay_length(sgpu_iir *f) {
+    if (f->decay_len != -2) return f->decay_len;
+    const int D = 2 * f->nsec_pad;
+    std::vector<double> A, A32, Pk;
+    build_transition(f, A);
+    mat_pow(A, 32, A32, D);
+    Pk = A32;
+    f->decay_len = -1;
+    for (long long k = 32; k <= 65536; k += 32) {
+        double nrm = 0.0;
+        for (int i = 0; i < D; ++i) {
+            double rs = 0.0;
+            for (int j = 0; j < D; ++j) rs += std::fabs(Pk[(size_t)i * D + j]);
+            nrm = rs > nrm ? rs : nrm;
+        }
+        if (!(nrm == nrm) || nrm > 1e30) break;
+        if (nrm < 1e-10) { f->decay_len = k; break; }
+        mat_mul(Pk, A32, Pk, D);
+    }
+    return f->decay_len;
 }
 
 int ensure_scan_scratch(sgpu_iir *f, size_t vc, size_t units, long long Lc, long long CH) {
@@ -617,7 +710,7 @@ int ensure_scan_scratch(sgpu_iir *f, size_t vc, size_t units, long long Lc, long
         SGPU_CUDA(cudaMalloc(&f->d_s, vc * D * sizeof(float2)));
         f->scratch_vc = vc;
     }
-    if (units > f->scratch_units) {
+    if (units > f->scratch_units && units > 0) {
         if (f->d_gagg) cudaFree(f->d_gagg);
         if (f->d_Sg) cudaFree(f->d_Sg);
         f->d_gagg = f->d_Sg = nullptr;
@@ -626,27 +719,11 @@ int ensure_scan_scratch(sgpu_iir *f, size_t vc, size_t units, long long Lc, long
         SGPU_CUDA(cudaMalloc(&f->d_Sg, units * D * sizeof(double2)));
         f->scratch_units = units;
     }
+    if (Lc < 0) return SGPU_OK;  // fused scan: state scratch only
     if (!f->d_mat) SGPU_CUDA(cudaMalloc(&f->d_mat, 2 * (size_t)D * D * sizeof(double)));
     if (f->mat_Lc != Lc || f->mat_CH != CH) {
         std::vector<double> A, ALc, AG;
         build_transition(f, A);
-        {   // decay length: smallest multiple of 16 with ||A^k||_inf < 1e-12, searched up to Lc
-            std::vector<double> A16, Pk;
-            mat_pow(A, 16, A16, D);
-            Pk = A16;
-            f->decay_len = -1;
-            for (long long k = 16; k <= Lc; k += 16) {
-                double nrm = 0.0;
-                for (int i = 0; i < D; ++i) {
-                    double rs = 0.0;
-                    for (int j = 0; j < D; ++j) rs += std::fabs(Pk[(size_t)i * D + j]);
-                    nrm = rs > nrm ? rs : nrm;
-                }
-                if (!(nrm == nrm) || nrm > 1e30) break;  // unstable filter: no truncation
-                if (nrm < 1e-12) { f->decay_len = k; break; }
-                mat_mul(Pk, A16, Pk, D);
-            }
-        }
         mat_pow(A, Lc, ALc, D);
         mat_pow(ALc, CH, AG, D);
         SGPU_CUDA(cudaMemcpy(f->d_mat, ALc.data(), (size_t)D * D * sizeof(double), cudaMemcpyHostToDevice));
@@ -681,55 +758,75 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
     a.C = (int)f->C; a.factor = (int)f->factor; a.idx0 = (int)f->index;
     a.vec = vec ? 1 : 0;
     a.k = f->k;
-    a.skip = 0; a.NP = 0; a.tail_slot = -1; a.tail_off = 0; a.tail_len = 0;
-    // strategy: scan when there are too few channels to fill the chip and the stream is long
-    const long long target_threads = (long long)f->sm_count * 1024;
-    bool scan = f->wrap == SGPU_IIR_PLAIN &&
-                (f->mode == 1 || (f->mode == -1 && (long long)f->C * 8 <= target_threads && n_in >= 16384));
-    if (!scan) {
-        a.P = 1; a.Lc = n_in;
+    a.layout = 0; a.P = 1; a.Lc = n_in;
+    a.NP = 0; a.tail_slot = -1; a.tail_off = 0; a.tail_len = 0;
+    a.NPt = 0; a.Pm = 0; a.CW = 0; a.last_len = 0; a.warm = 0;
+    auto plain = [&]() {
+        a.layout = 0; a.P = 1; a.Lc = n_in; a.n_warps = (long long)ceil_div(f->C, 32);
         a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
         return launch_sos(f, a, f->wrap, s);
+    };
+    // ---- strategy.  One lane per channel needs about sm_count * 12 * 32 channels to fill the chip;
+    // with fewer, every channel's stream is cut into chunks that run side by side (scan).
+    const long long lanes = (long long)f->sm_count * kWarpsPerSm * 32;
+    const bool want_scan = f->wrap == SGPU_IIR_PLAIN &&
+                           (f->mode >= 1 || (f->mode == -1 && (long long)f->C * 2 <= lanes && n_in >= 4096));
+    if (!want_scan) return plain();
+    const int D = 2 * f->nsec_pad;
+    const long long decay = (f->mode == 2 || getenv("SGPU_IIR_NO_TRUNC")) ? -1 : decay_length(f);
+    const long long chunks_wanted = std::max<long long>(2, lanes / (long long)f->C);
+    if (decay > 0) {
+        // ---- fused scan: one launch, every chunk but the first warms up over the `decay` samples in
+        // front of it.  Chunks are at least 2 * decay long (re-read <= 50 % of the input) unless the
+        // scan is forced (mode 1: at least `decay`).
+        const long long warm = (long long)round_up((size_t)decay, kScanTile);
+        const long long lc_min = f->mode == 1 ? warm : 2 * warm;
+        long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)chunks_wanted), kScanTile);
+        if (Lc < lc_min) Lc = lc_min;
+        const long long NPt = (long long)ceil_div((size_t)n_in, (size_t)Lc);
+        if (NPt < 2) return plain();
+        a.Lc = Lc; a.warm = warm; a.NPt = (int)NPt; a.last_len = n_in - (NPt - 1) * Lc;
+        long long warps;
+        if (f->C >= 32) {
+            a.layout = 3;
+            a.CW = (int)ceil_div(f->C, 32);
+            warps = NPt * a.CW;
+        } else {
+            a.layout = 2;
+            a.Pm = (int)round_up((size_t)(NPt - 2), 32);
+            warps = 2 + (long long)f->C * (a.Pm / 32);
+        }
+        a.n_warps = warps;
+        if (f->scratch_vc < f->C) {
+            int st = ensure_scan_scratch(f, f->C, 0, -1, -1);
+            if (st) return st;
+        }
+        a.state_in = f->d_state; a.state_out = f->d_z; a.write_out = 1;
+        int st = launch_sos(f, a, 0, s);
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpyAsync(f->d_state, f->d_z, f->C * (size_t)D * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+        return SGPU_OK;
     }
-    // ---- chunked scan.  Virtual channels fill whole waves of the batch kernel: 3 blocks of 256
-    // threads per SM (launch bounds of iir_sos_kernel), so P*C is about sm_count*768.
-    const long long wave = (long long)f->sm_count * 768;
-    long long P0 = ceil_div((size_t)wave, f->C);
-    long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)P0), kTile);
+    // ---- three-pass scan for filters whose memory does not decay within 2^16 samples.
+    long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)chunks_wanted), kScanTile);
     if (Lc < 256) Lc = 256;
     const long long NP = n_in / Lc;          // full chunks
     const long long tail = n_in - NP * Lc;   // ragged tail chunk (its own warp)
-    if (NP == 0) {
-        a.P = 1; a.Lc = n_in;
-        a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
-        return launch_sos(f, a, f->wrap, s);
-    }
+    if (NP == 0) return plain();
     const long long Pw = (long long)round_up((size_t)NP, 32);
     const long long P = Pw + (tail ? 32 : 0);
     const int tail_slot = tail ? (int)Pw : -1;
     const long long CH = 256;
     const long long G = (NP + CH - 1) / CH;
-    const int D = 2 * f->nsec_pad;
     int st = ensure_scan_scratch(f, (size_t)f->C * P, (size_t)f->C * G, Lc, CH);
     if (st) return st;
+    a.layout = 1; a.n_warps = (long long)f->C * P / 32;
     a.P = (int)P; a.Lc = Lc; a.NP = (int)NP; a.tail_slot = tail_slot; a.tail_off = NP * Lc;
-    const bool decays = f->decay_len > 0 && f->decay_len <= Lc && !getenv("SGPU_IIR_NO_TRUNC");
-    // pass A: zero-state end state of every full chunk.  That state depends on the chunk's last
-    // `decay_len` samples only, to within ||A^decay_len|| < 1e-12 (far below f32 resolution), so a
-    // decaying filter's pass A reads just that tail; other filters run the whole chunk.
+    // pass A: zero-state end state of every full chunk
     a.state_in = nullptr; a.state_out = f->d_z; a.write_out = 0; a.tail_len = 0;
-    a.skip = decays ? Lc - f->decay_len : 0;
     st = launch_sos(f, a, 0, s);
     if (st) return st;
-    a.skip = 0;
-    if (decays) {
-        // ||A^Lc|| < 1e-12 as well: start state of chunk p = end state of chunk p-1
-        const long long total = (long long)f->C * (NP + 1) * D;
-        shift_states_kernel<<<(unsigned)ceil_div((size_t)total, 256), 256, 0, s>>>(f->d_z, f->d_state, f->d_s, D, (int)P,
-                                                                                 (int)NP, tail_slot, total);
-        SGPU_LAUNCH_CHECK();
-        count_launch();
-    } else if (G > 1) {
+    if (G > 1) {
         const int units = (int)(f->C * G);
         carry_kernel<<<(unsigned)ceil_div((size_t)units, 4), 128, 0, s>>>(0, f->d_mat, D, f->d_z, f->d_gagg, nullptr, nullptr,
                                                                          nullptr, (int)P, (int)NP, tail_slot, (int)CH, (int)G, units);
@@ -759,6 +856,57 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
                                 (size_t)P * D * sizeof(float2), (size_t)D * sizeof(float2), f->C,
                                 cudaMemcpyDeviceToDevice, s));
     return SGPU_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// Kernel coefficients.  Unfolded: the normalised coefficients as they are.  Folded: section s < last
+// runs with (1, b1/b0, b2/b0) and the last section is multiplied by the product of the b0 in front
+// of it, so the cascade output is unchanged while every section but one saves a multiply per real
+// component (the cascade is linear: scaling a section's output scales everything behind it).  The
+// states of section s are then kept divided by gpre[s] = prod_{k<s} b0_k; get/set_state convert.
+// Folding needs every b0 != 0 and the running product within 2^+-40 (f32 range to spare).
+void fold_sections(sgpu_iir *f, const double (&nc)[kMaxSec][5]) {
+    const int NP = f->nsec_pad;
+    f->gpre.assign((size_t)NP, 1.0);
+    bool ok = NP > 1 && !getenv("SGPU_IIR_NO_FOLD");
+    double g = 1.0;
+    for (int s = 0; s + 1 < NP && ok; ++s) {
+        const double b0 = nc[s][0];
+        g *= b0;
+        if (!(b0 != 0.0) || !std::isfinite(g) || std::fabs(g) > 0x1p40 || std::fabs(g) < 0x1p-40) ok = false;
+        f->gpre[s + 1] = g;
+    }
+    if (ok) {
+        const float chk[3] = {(float)(g * nc[NP - 1][0]), (float)(g * nc[NP - 1][1]), (float)(g * nc[NP - 1][2])};
+        for (float c : chk)
+            if (!std::isfinite(c)) ok = false;
+    }
+    f->fold = ok;
+    if (!ok) f->gpre.assign((size_t)NP, 1.0);
+    f->kd.assign((size_t)NP * 5, 0.0);
+    for (int s = 0; s < kMaxSec; ++s) {
+        float b0 = (float)nc[s][0], b1 = (float)nc[s][1], b2 = (float)nc[s][2];
+        if (ok && s < NP) {
+            if (s + 1 < NP) {
+                b1 = (float)(nc[s][1] / nc[s][0]);
+                b2 = (float)(nc[s][2] / nc[s][0]);
+                b0 = 1.f;
+            } else {
+                b0 = (float)(g * nc[s][0]);
+                b1 = (float)(g * nc[s][1]);
+                b2 = (float)(g * nc[s][2]);
+            }
+        }
+        f->k.b0[s] = b0; f->k.b1[s] = b1; f->k.b2[s] = b2;
+        f->k.na1[s] = -(float)nc[s][3]; f->k.na2[s] = -(float)nc[s][4];
+        if (s < NP) {
+            f->kd[s * 5 + 0] = b0; f->kd[s * 5 + 1] = b1; f->kd[s * 5 + 2] = b2;
+            f->kd[s * 5 + 3] = (float)nc[s][3]; f->kd[s * 5 + 4] = (float)nc[s][4];
+        }
+    }
 }
 
 }  // namespace
@@ -801,24 +949,22 @@ SGPU_EXPORT int sgpu_iir_create(sgpu_iirtype type, const double *ff, size_t n_ff
     f->wrap = wrap;
     f->factor = wrap == SGPU_IIR_PLAIN ? 1 : factor;
     f->C = n_channels;
-    f->packed = iir_packed_default();
     f->ff_raw.assign(ff, ff + n_ff);
     f->fb_raw.assign(fb, fb + n_fb);
     if (type == SGPU_IIR_SECOND_ORDER) {
         f->nsec = (int)(n_ff / 3);
         f->nsec_pad = pad_sections(f->nsec);
-        f->kd.assign((size_t)f->nsec * 5, 0.0);
+        double nc[kMaxSec][5];  // normalised by a0 (sos.rs:62-68), rounded to f32: b0, b1, b2, a1, a2
         for (int s = 0; s < kMaxSec; ++s) {  // identity padding: y = x
-            f->k.b0[s] = 1.f; f->k.b1[s] = 0.f; f->k.b2[s] = 0.f; f->k.na1[s] = 0.f; f->k.na2[s] = 0.f;
+            nc[s][0] = 1.0; nc[s][1] = nc[s][2] = nc[s][3] = nc[s][4] = 0.0;
         }
         for (int s = 0; s < f->nsec; ++s) {
-            const double a0 = fb[3 * s];  // sos.rs:62-68
-            const float b0 = (float)(ff[3 * s] / a0), b1 = (float)(ff[3 * s + 1] / a0), b2 = (float)(ff[3 * s + 2] / a0);
-            const float a1 = (float)(fb[3 * s + 1] / a0), a2 = (float)(fb[3 * s + 2] / a0);
-            f->k.b0[s] = b0; f->k.b1[s] = b1; f->k.b2[s] = b2; f->k.na1[s] = -a1; f->k.na2[s] = -a2;
-            f->kd[s * 5 + 0] = b0; f->kd[s * 5 + 1] = b1; f->kd[s * 5 + 2] = b2;
-            f->kd[s * 5 + 3] = a1; f->kd[s * 5 + 4] = a2;
+            const double a0 = fb[3 * s];
+            for (int i = 0; i < 3; ++i) nc[s][i] = (double)(float)(ff[3 * s + i] / a0);
+            nc[s][3] = (double)(float)(fb[3 * s + 1] / a0);
+            nc[s][4] = (double)(float)(fb[3 * s + 2] / a0);
         }
+        fold_sections(f, nc);
     } else {
         f->nb = (int)n_ff;
         f->na = (int)n_fb;
@@ -866,7 +1012,7 @@ SGPU_EXPORT size_t sgpu_iir_state_len(const sgpu_iir *f) {
     return f->type == SGPU_IIR_SECOND_ORDER ? (size_t)f->nsec * 2 : (size_t)f->W;
 }
 SGPU_EXPORT int sgpu_iir_set_mode(sgpu_iir *f, int mode) {
-    if (!f || mode < -1 || mode > 1) return fail(SGPU_ERR_INVALID_ARGUMENT, "bad mode");
+    if (!f || mode < -1 || mode > 2) return fail(SGPU_ERR_INVALID_ARGUMENT, "bad mode");
     f->mode = mode;
     return SGPU_OK;
 }
@@ -922,6 +1068,13 @@ SGPU_EXPORT int sgpu_iir_get_state(sgpu_iir *f, float *state, uint64_t *index) {
         const size_t api = sgpu_iir_state_len(f), dev = state_len_dev(f);
         SGPU_CUDA(cudaMemcpy2D(state, api * sizeof(float2), f->d_state, dev * sizeof(float2), api * sizeof(float2),
                                f->C, cudaMemcpyDeviceToHost));
+        if (f->fold)  // device states of section s are v / gpre[s]
+            for (size_t c = 0; c < f->C; ++c)
+                for (size_t i = 0; i < api; ++i) {
+                    float *v = state + 2 * (c * api + i);
+                    v[0] = (float)(v[0] * f->gpre[i / 2]);
+                    v[1] = (float)(v[1] * f->gpre[i / 2]);
+                }
     }
     if (index) *index = f->index;
     return SGPU_OK;
@@ -933,6 +1086,17 @@ SGPU_EXPORT int sgpu_iir_set_state(sgpu_iir *f, const float *state, uint64_t ind
         SGPU_CUDA(cudaDeviceSynchronize());
         const size_t api = sgpu_iir_state_len(f), dev = state_len_dev(f);
         SGPU_CUDA(cudaMemset(f->d_state, 0, f->C * dev * sizeof(float2)));
+        std::vector<float> scaled;
+        if (f->fold) {
+            scaled.assign(state, state + 2 * f->C * api);
+            for (size_t c = 0; c < f->C; ++c)
+                for (size_t i = 0; i < api; ++i) {
+                    float *v = scaled.data() + 2 * (c * api + i);
+                    v[0] = (float)(v[0] / f->gpre[i / 2]);
+                    v[1] = (float)(v[1] / f->gpre[i / 2]);
+                }
+            state = scaled.data();
+        }
         SGPU_CUDA(cudaMemcpy2D(f->d_state, dev * sizeof(float2), state, api * sizeof(float2), api * sizeof(float2),
                                f->C, cudaMemcpyHostToDevice));
     }

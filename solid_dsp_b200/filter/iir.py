@@ -108,7 +108,7 @@ class IIRFilter(Filter):
         return lib.sgpu_iir_type(self._h)
 
     def set_mode(self, mode: int):
-        """-1 auto, 0 one-channel-per-thread batch, 1 long-stream chunked scan"""
+        """-1 auto, 0 one-channel-per-thread batch, 1 chunked scan (fused when the filter decays), 2 three-pass scan"""
         check(lib.sgpu_iir_set_mode(self._h, mode))
 
     def execute_block(self, samples):  # iir/mod.rs:310

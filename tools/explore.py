@@ -104,6 +104,31 @@ def iir(Cn=65536, logn=12, nsec=8):
                       "Gsamp_s": tot / best / 1e6, "GBps": tot * 16 / best / 1e6}))
 
 
+def iirn(Cn=65536, n=16400, nsec=8):
+    """batch IIR with an arbitrary (non power of two) row length"""
+    from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
+    from solid_dsp_b200.filter.iirdes import stable_lowpass_sections
+    ff, fb = stable_lowpass_sections(nsec)
+    x = torch.randn((Cn, n), dtype=torch.complex64, device="cuda")
+    f = IIRFilter(ff, fb, IIRFilterType.SecondOrder, n_channels=Cn)
+    best, med = ev_time(lambda: f.execute_block(x))
+    tot = Cn * n
+    print(json.dumps({"kernel": "iirn", "C": Cn, "n": n, "nsec": nsec, "best_ms": best, "med_ms": med,
+                      "Gsamp_s": tot / best / 1e6, "GBps": tot * 16 / best / 1e6}))
+
+
+def iirscan(logn=26, nsec=8):
+    from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
+    from solid_dsp_b200.filter.iirdes import stable_lowpass_sections
+    n = 1 << logn
+    ff, fb = stable_lowpass_sections(nsec)
+    x = torch.randn(n, dtype=torch.complex64, device="cuda")
+    f = IIRFilter(ff, fb, IIRFilterType.SecondOrder)
+    best, med = ev_time(lambda: f.execute_block(x))
+    print(json.dumps({"kernel": "iirscan", "n": n, "nsec": nsec, "best_ms": best, "med_ms": med,
+                      "Gsamp_s": n / best / 1e6, "GBps": n * 16 / best / 1e6}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["peaks", "fir"]
     print(json.dumps({"device": torch.cuda.get_device_name(0), "info": str(_ffi.device_info())}))
