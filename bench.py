@@ -369,7 +369,7 @@ def run_gpu_arm(args):
             "traffic": traffic,
             "kernel": {"fir": "fir_decim_kernel<R=16,M1>", "decim": "fir_decim_kernel<R=16>",
                        "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
-                       "iir_scan": "iir_sos_kernel<8> (pass A + pass C)"}[name],
+                       "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)"}[name],
             "kernel_ms_per_launch": ms_kernel,
             "algorithmic": {"flop_per_unit": W["flop_per_unit"], "bytes_per_unit": W["bytes_per_unit"], "unit": W["unit"],
                             "units_per_launch": units_rank},

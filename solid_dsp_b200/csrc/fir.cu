@@ -357,6 +357,8 @@ __global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const f
     out[ch] = acc;
 }
 
+#include "fir_walk.cuh"
+
 }  // namespace
 }  // namespace sgpu
 
@@ -926,6 +928,32 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
+    if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8) &&
+        env_int("SGPU_WALK", 1)) {
+        // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase
+        constexpr int K = 7;
+        const int G = kNT / (int)f->L;
+        const int rows = 2 + G * K;
+        a.RS = rows | 1;
+        const size_t smem = ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * sizeof(float);
+        const long long tile = (long long)G * K * kR;
+        dim3 grid((unsigned)((n_in + tile - 1) / tile), (unsigned)f->C);
+        int st;
+#define LAUNCH_IWALK(LV, MB)                                         \
+    do {                                                             \
+        auto kern = fir_interp_walk_kernel<kR, LV, K, kNT, MB>;      \
+        st = set_smem(kern, smem);                                   \
+        if (st) return st;                                           \
+        kern<<<grid, kNT, smem, s>>>(a);                             \
+    } while (0)
+        if (f->L == 2) LAUNCH_IWALK(2, 3);
+        else if (f->L == 4) { if (env_int("SGPU_WALK_MINB", 3) == 4) LAUNCH_IWALK(4, 4); else LAUNCH_IWALK(4, 3); }
+        else LAUNCH_IWALK(8, 3);
+#undef LAUNCH_IWALK
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+        return SGPU_OK;
+    }
     if (!f->complex_taps && env_int("SGPU_PIPE", 1)) {
         // persistent multi-stage interpolator (fir_pipe.cuh)
         int PSp = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
