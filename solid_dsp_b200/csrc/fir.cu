@@ -617,6 +617,49 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
             return SGPU_OK;
         }
     }
+    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps && env_int("SGPU_DEC_WARP", 1)) {
+        // warp-private tiles (fir_walk.cuh)
+        int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
+        if (PS != 1 && PS != 2 && PS != 4) PS = 4;
+        if (PS > (int)f->M) PS = (int)f->M;
+        const int G = 32 / PS;
+        const int rows = f->Qpad / kR + G;
+        a.RS = rows | 1;
+        const size_t stage_b = (size_t)f->M * ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4);
+        const size_t taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * sizeof(float);
+        constexpr int TPW = 8;
+        int st = SGPU_OK;
+        bool done = false;
+#define LAUNCH_DWARP(MV, PSV, NWV, MB)                                                        \
+    do {                                                                                      \
+        const size_t smem = (size_t)NWV * stage_b + taps_b;                                   \
+        if (smem <= (size_t)kMaxSmem) {                                                       \
+            auto kern = fir_decim_warp_kernel<kR, MV, PSV, NWV, MB, TPW>;                     \
+            st = set_smem(kern, smem);                                                        \
+            if (st) return st;                                                                \
+            const long long per_block = (long long)(32 / PSV) * kR * TPW * NWV;               \
+            dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);       \
+            kern<<<grid, NWV * 32, smem, s>>>(a);                                             \
+            done = true;                                                                      \
+        }                                                                                     \
+    } while (0)
+#define LAUNCH_DWARP_M(MV)                                                                    \
+    do {                                                                                      \
+        if (PS == 1) LAUNCH_DWARP(MV, 1, 1, 4);                                               \
+        else if (PS == 2) LAUNCH_DWARP(MV, 2, 2, 4);                                          \
+        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 3);                                       \
+    } while (0)
+        if (f->M == 8) LAUNCH_DWARP_M(8);
+        else if (f->M == 4) LAUNCH_DWARP_M(4);
+        else LAUNCH_DWARP_M(2);
+#undef LAUNCH_DWARP_M
+#undef LAUNCH_DWARP
+        if (done) {
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+            return SGPU_OK;
+        }
+    }
     if (n_out > 0) {
         const bool m1 = f->M == 1;
         const int R = fir_R(f);
@@ -930,25 +973,40 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     const int tw = f->complex_taps ? 2 : 1;
     if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8) &&
         env_int("SGPU_WALK", 1)) {
-        // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase
-        constexpr int K = 7;
-        const int G = kNT / (int)f->L;
+        // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase, warp-private tiles
+        const int K = env_int("SGPU_WALK_K", 7);
+        const int mb = env_int("SGPU_WALK_MINB", 3);
+        const int G = 32 / (int)f->L;
         const int rows = 2 + G * K;
         a.RS = rows | 1;
-        const size_t smem = ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * sizeof(float);
-        const long long tile = (long long)G * K * kR;
-        dim3 grid((unsigned)((n_in + tile - 1) / tile), (unsigned)f->C);
+        const size_t smem = (size_t)(kNT / 32) * 2 * ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4) +
+                            f->L * (size_t)(f->Qpad + kTapSkew) * sizeof(float);
+        const long long tile = (long long)G * K * kR;  // per warp
+        constexpr int TPW = 8;
+        const long long per_block = tile * TPW * (kNT / 32);
+        dim3 grid((unsigned)((n_in + per_block - 1) / per_block), (unsigned)f->C);
         int st;
-#define LAUNCH_IWALK(LV, MB)                                         \
-    do {                                                             \
-        auto kern = fir_interp_walk_kernel<kR, LV, K, kNT, MB>;      \
-        st = set_smem(kern, smem);                                   \
-        if (st) return st;                                           \
-        kern<<<grid, kNT, smem, s>>>(a);                             \
+#define LAUNCH_IWALK(LV, KV, MB)                                          \
+    do {                                                                  \
+        auto kern = fir_interp_walk_kernel<kR, LV, KV, kNT, MB, TPW>;     \
+        st = set_smem(kern, smem);                                        \
+        if (st) return st;                                                \
+        kern<<<grid, kNT, smem, s>>>(a);                                  \
     } while (0)
-        if (f->L == 2) LAUNCH_IWALK(2, 3);
-        else if (f->L == 4) { if (env_int("SGPU_WALK_MINB", 3) == 4) LAUNCH_IWALK(4, 4); else LAUNCH_IWALK(4, 3); }
-        else LAUNCH_IWALK(8, 3);
+#define LAUNCH_IWALK_T(LV)                                                \
+    do {                                                                  \
+        if (K == 5) LAUNCH_IWALK(LV, 5, 3);                               \
+        else if (K == 3) LAUNCH_IWALK(LV, 3, 3);                          \
+        else if (K == 1) LAUNCH_IWALK(LV, 1, 3);                          \
+        else if (K == 9) LAUNCH_IWALK(LV, 9, 3);                          \
+        else if (K == 11) LAUNCH_IWALK(LV, 11, 3);                        \
+        else if (mb == 4) LAUNCH_IWALK(LV, 7, 4);                         \
+        else LAUNCH_IWALK(LV, 7, 3);                                      \
+    } while (0)
+        if (f->L == 2) LAUNCH_IWALK_T(2);
+        else if (f->L == 4) LAUNCH_IWALK_T(4);
+        else LAUNCH_IWALK_T(8);
+#undef LAUNCH_IWALK_T
 #undef LAUNCH_IWALK
         SGPU_LAUNCH_CHECK();
         count_launch();

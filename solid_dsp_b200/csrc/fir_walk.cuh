@@ -31,73 +31,219 @@ __device__ __forceinline__ void walk_run(float2 (&acc)[R], float2 (&W)[2 * R], c
 // --------------------------------------------------------------------------------------------
 // Interpolator, L phases = L lanes per group (L in {2, 4, 8}), sub-filter length S <= 2R.
 //   y[n*L + p] = sum_{j<S} hp[p][j] * x[n-j]   (fir/pfb.rs:85-90, fir/interp.rs:102-111; no scale)
-// Block = NT threads = NT/L groups; group g owns input positions [g*K*R, (g+1)*K*R) of the tile and
-// its lane p produces phase p of their outputs.
-template <int R, int L, int K, int NT, int MINB>
+// Every WARP runs its own software pipeline over TPW consecutive tiles of its channel: two private
+// shared-memory stages filled with cp.async, __syncwarp only -- no block barrier after the taps are
+// in, so the warps of an SM drift apart and the FMA pipe always finds one in its arithmetic phase.
+// A warp tile = 32/L groups x K runs x R input positions; group g owns positions [g*K*R, (g+1)*K*R)
+// and its lane p produces phase p of their outputs.
+template <int R, int L, int K, int NT, int MINB, int TPW>
 __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     static_assert(K % 2 == 1, "K must be odd (bank conflicts, parity of the last run)");
-    constexpr int G = NT / L, HR = 2, ROWS = HR + G * K, QP = 2 * R;
-    const int tid = threadIdx.x;
-    const int RS = a.RS;
-    float *taps_s = reinterpret_cast<float *>(smem + (R / 2) * RS + 1);
+    constexpr int G = 32 / L, HR = 2, ROWS = HR + G * K, QP = 2 * R, TILE = G * K * R, NW = NT / 32;
+    constexpr int RS = ROWS | 1, STAGE_F4 = (R / 2) * RS + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *taps_s = reinterpret_cast<float *>(smem + NW * 2 * STAGE_F4);
     {
         const int n4 = L * (QP + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
     }
+    __syncthreads();
     const int ch = blockIdx.y;
-    const long long n_base = (long long)blockIdx.x * (G * K * R);  // first input position of the tile
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
-    {   // tile load: ROWS * R consecutive samples from n_base - QP on, pairs -> transposed rows
+    float4 *stage0 = smem + warp * 2 * STAGE_F4;
+    auto issue = [&](const long long n_base, float4 *plane) {
+        // ROWS * R consecutive samples from n_base - QP on, pairs -> transposed rows
         const long long i_lo = n_base - QP;
         constexpr int total_pairs = ROWS * R / 2;
         if (i_lo >= 0 && i_lo + (long long)ROWS * R <= a.n_in && a.vec_in) {
             const float2 *src = x + i_lo;
-            for (int pe = tid; pe < total_pairs; pe += NT)
-                cp_async16(smem + (pe % (R / 2)) * RS + pe / (R / 2), src + 2 * pe);
+#pragma unroll 4
+            for (int pe = lane; pe < total_pairs; pe += 32)
+                cp_async16(plane + (pe % (R / 2)) * RS + pe / (R / 2), src + 2 * pe);
         } else {
             const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
-            for (int pe = tid; pe < total_pairs; pe += NT) {
+            for (int pe = lane; pe < total_pairs; pe += 32) {
                 const long long i = i_lo + 2 * pe;
                 const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
                 const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
-                smem[(pe % (R / 2)) * RS + pe / (R / 2)] = make_float4(s0.x, s0.y, s1.x, s1.y);
+                plane[(pe % (R / 2)) * RS + pe / (R / 2)] = make_float4(s0.x, s0.y, s1.x, s1.y);
+            }
+        }
+    };
+    const int g = lane / L, p = lane % L;
+    const float *tp = taps_s + p * (QP + kTapSkew);
+    // first input position of the warp's current tile
+    long long n_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    if (n_base >= a.n_in) return;
+    issue(n_base, stage0);
+#pragma unroll 1
+    for (int t = 0; t < TPW && n_base < a.n_in; ++t, n_base += TILE) {
+        cp_async_wait_all();
+        __syncwarp();  // tile t landed; every lane is done with the other stage
+        const float4 *plane = stage0 + (t & 1) * STAGE_F4;
+        if (t + 1 < TPW && n_base + TILE < a.n_in) issue(n_base + TILE, stage0 + ((t + 1) & 1) * STAGE_F4);
+        int row = HR + g * K + (K - 1);                          // newest row of the group's newest run
+        long long n0 = n_base + (long long)(g * K + (K - 1)) * R;  // its first input position
+        float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0 * L + p;
+        float2 W[2 * R], acc[R];
+        load_row<R, 0>(W, plane, RS, row);
+        load_row<R, R>(W, plane, RS, row - 1);
+        auto store = [&]() {
+            if (n0 + R <= a.n_in) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) yp[r * L] = acc[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (n0 + r < a.n_in) yp[r * L] = acc[r];
+            }
+            n0 -= R;
+            yp -= R * L;
+        };
+#pragma unroll 1
+        for (int it = 0; it < (K - 1) / 2; ++it) {
+            walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);
+            store();
+            walk_run<R, 1>(acc, W, plane, RS, row - 3, tp);
+            store();
+            row -= 2;
+        }
+        walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);  // rows 0/1 of the plane are the halo: row - 2 >= 0
+        store();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Decimator with warp-private tiles (M in {2, 4, 8}, any sub-filter length that fits).
+//   y[m] = scale * sum_p sum_q g[q*M+p] * x[(m-q)*M + (M-1-c0) - p]          (fir/decim.rs:221-228)
+// Same phase decomposition as fir_decim_kernel, but every warp owns its tiles: a private stage of
+// M phase planes filled by 8-byte cp.async (the de-interleave), __syncwarp only, so the warps of an
+// SM drift apart and tile loads hide behind other warps' arithmetic.  PS adjacent lanes share a run
+// of R outputs and each walks M/PS planes.  The partial sums meet in shared memory (the stage is
+// free by then): a lane writes its R sums as R/2 float4, then reads and adds the PS partials of
+// the pieces it stores -- every PS-th 16-byte piece of the run, so each store instruction writes
+// whole 32-byte sectors.  8 STS + 8 LDS + 12 FADD2 instead of the 128 SHFL/FADD of a butterfly.
+template <int R, int M, int PS, int NW, int MINB, int TPW>
+__global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const FirArgs a) {
+    extern __shared__ float4 smem[];
+    constexpr int G = 32 / PS, MP = M / PS, RM = R * M, LPRW = RM / 32;  // LPRW: loader steps per row of all planes
+    constexpr int NPC = R / 2 / PS;                                     // 16-byte pieces a lane stores
+    static_assert(RM % 32 == 0 && M % PS == 0 && (R / 2) % PS == 0, "shape");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Qpad = a.Qpad, HR = Qpad / R, rows = HR + G, RS = a.RS;
+    const int plane_f4 = (R / 2) * RS + 1, stage_f4 = M * plane_f4;  // >= 32 * (R/2 + 1): room for the reduction
+    float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * stage_f4);
+    {
+        const int n4 = M * (Qpad + kTapSkew) / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        float4 *dst = reinterpret_cast<float4 *>(taps_s);
+        for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int ch = blockIdx.y;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    float4 *stage = smem + (size_t)warp * stage_f4;
+    // loader role: element e = k*32 + lane of a row-of-all-planes (RM consecutive input samples)
+    // goes to plane M-1-(e%M), position e/M of the row; the next row is 16 bytes further on
+    unsigned sdst[LPRW];  // shared-space byte addresses, row 0
+    int eoff[LPRW];       // float2 offsets, for the guarded path
+#pragma unroll
+    for (int k = 0; k < LPRW; ++k) {
+        const int e = k * 32 + lane, rem = e % M, j = e / M, p = M - 1 - rem;
+        eoff[k] = ((p * plane_f4 + (j >> 1) * RS) << 1) + (j & 1);
+        sdst[k] = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float2 *>(stage) + eoff[k]);
+    }
+    auto issue = [&](const long long m_base) {
+        const long long i_lo = (m_base - Qpad) * M - a.c0;
+        if (i_lo >= 0 && i_lo + (long long)rows * RM <= a.n_in) {
+            const float2 *src = x + i_lo + lane;
+#pragma unroll 2
+            for (int rho = 0; rho < rows; ++rho) {
+#pragma unroll
+                for (int k = 0; k < LPRW; ++k)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst[k] + 16u * rho), "l"(src + k * 32)
+                                 : "memory");
+                src += RM;
+            }
+        } else {
+            const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
+            float2 *base = reinterpret_cast<float2 *>(stage);
+            long long i = i_lo + lane;
+            for (int rho = 0; rho < rows; ++rho) {
+#pragma unroll
+                for (int k = 0; k < LPRW; ++k) {
+                    const long long ii = i + k * 32;
+                    if (ii >= 0 && ii < a.n_in) cp_async8(base + eoff[k] + 2 * rho, x + ii);
+                    else base[eoff[k] + 2 * rho] = fetch_sample(x, hist, ii, a.n_in, a.T);
+                }
+                i += RM;
+            }
+        }
+    };
+    const int g = lane / PS, part = lane % PS;
+    const int npairs = Qpad / (2 * R);
+    constexpr int TILE = G * R;  // outputs per warp tile
+    constexpr int RED = R / 2 + 1;  // float4 pitch of a lane's partial sums
+    long long m_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    if (m_base >= a.n_out) return;
+    issue(m_base);
+#pragma unroll 1
+    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += TILE) {
+        cp_async_wait_all();
+        __syncwarp();
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int sidx = 0; sidx < MP; ++sidx) {
+            const int p = part * MP + sidx;
+            fir_core<R, true>(acc, stage + (size_t)p * plane_f4, RS, HR + g, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
+        }
+        float4 out[NPC];
+        if constexpr (PS > 1) {
+            __syncwarp();  // every lane is done reading the planes
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q)
+                stage[lane * RED + q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < NPC; ++k) {
+                float2 lo = make_float2(0.f, 0.f), hi = lo;
+#pragma unroll
+                for (int sl = 0; sl < PS; ++sl) {
+                    const float4 v = stage[(g * PS + sl) * RED + k * PS + part];
+                    lo = __fadd2_rn(lo, make_float2(v.x, v.y));
+                    hi = __fadd2_rn(hi, make_float2(v.z, v.w));
+                }
+                out[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPC; ++k) out[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
+        }
+        __syncwarp();  // the stage is free again
+        if (t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE);
+        // lane `part` stores the pieces k*PS + part, k < NPC: sector-complete per instruction
+        const long long o0 = m_base + (long long)g * R;
+        float2 *__restrict__ y = a.out + (long long)ch * a.out_stride + o0;
+        const float s = a.scale_re;
+        if (a.vec_out && o0 + R <= a.n_out) {
+#pragma unroll
+            for (int k = 0; k < NPC; ++k) {
+                const float4 v = out[k];
+                *reinterpret_cast<float4 *>(y + 2 * (k * PS + part)) = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NPC; ++k) {
+                const float4 v = out[k];
+                const int q = 2 * (k * PS + part);
+                if (o0 + q < a.n_out) y[q] = make_float2(v.x * s, v.y * s);
+                if (o0 + q + 1 < a.n_out) y[q + 1] = make_float2(v.z * s, v.w * s);
             }
         }
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    const int g = tid / L, p = tid % L;
-    const float *tp = taps_s + p * (QP + kTapSkew);
-    int row = HR + g * K + (K - 1);                          // newest row of the group's newest run
-    long long n0 = n_base + (long long)(g * K + (K - 1)) * R;  // its first input position
-    float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0 * L + p;
-    float2 W[2 * R], acc[R];
-    load_row<R, 0>(W, smem, RS, row);
-    load_row<R, R>(W, smem, RS, row - 1);
-    auto store = [&]() {
-        if (n0 + R <= a.n_in) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) yp[r * L] = acc[r];
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (n0 + r < a.n_in) yp[r * L] = acc[r];
-        }
-        n0 -= R;
-        yp -= R * L;
-    };
-#pragma unroll 1
-    for (int it = 0; it < (K - 1) / 2; ++it) {
-        walk_run<R, 0>(acc, W, smem, RS, row - 2, tp);
-        store();
-        walk_run<R, 1>(acc, W, smem, RS, row - 3, tp);
-        store();
-        row -= 2;
-    }
-    walk_run<R, 0>(acc, W, smem, RS, row - 2, tp);  // rows 0/1 of the plane are the halo: row - 2 >= 0
-    store();
 }
