@@ -617,6 +617,39 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
             return SGPU_OK;
         }
     }
+    if (n_out > 0 && f->M == 1 && f->packed && !f->complex_taps && env_int("SGPU_FIR_WARP", 1)) {
+        // plain FIR, warp-private tiles (fir_walk.cuh)
+        const int rows = f->Qpad / kR + 32;
+        a.RS = rows | 1;
+        const size_t stage_b = std::max<size_t>((size_t)(kR / 2) * a.RS + 1, 32 * (kR / 2 + 1)) * sizeof(float4);
+        const size_t taps_b = (size_t)(f->Qpad + kTapSkew) * sizeof(float);
+        constexpr int TPW = 8;
+        const int ns = env_int("SGPU_FIR_NS", 1);
+        int st = SGPU_OK;
+        bool done = false;
+#define LAUNCH_FWARP(NWV, MB, NSV)                                                            \
+    do {                                                                                      \
+        const size_t smem = (size_t)NWV * NSV * stage_b + taps_b;                             \
+        if (smem <= (size_t)kMaxSmem) {                                                       \
+            auto kern = fir_warp_kernel<kR, NWV, MB, TPW, NSV>;                               \
+            st = set_smem(kern, smem);                                                        \
+            if (st) return st;                                                                \
+            const long long per_block = 32LL * kR * TPW * NWV;                                \
+            dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);       \
+            kern<<<grid, NWV * 32, smem, s>>>(a);                                             \
+            done = true;                                                                      \
+        }                                                                                     \
+    } while (0)
+        if (ns == 2) LAUNCH_FWARP(4, 3, 2);
+        else LAUNCH_FWARP(4, 4, 1);
+        if (!done) LAUNCH_FWARP(1, 1, 1);  // very long filters: one warp per block
+#undef LAUNCH_FWARP
+        if (done) {
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+            return SGPU_OK;
+        }
+    }
     if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps && env_int("SGPU_DEC_WARP", 1)) {
         // warp-private tiles (fir_walk.cuh)
         int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
@@ -625,7 +658,7 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         const int G = 32 / PS;
         const int rows = f->Qpad / kR + G;
         a.RS = rows | 1;
-        const size_t stage_b = (size_t)f->M * ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4);
+        const size_t stage_b = std::max<size_t>((size_t)f->M * ((size_t)(kR / 2) * a.RS + 1), 32 * (kR / 2 + 1)) * sizeof(float4);
         const size_t taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * sizeof(float);
         constexpr int TPW = 8;
         int st = SGPU_OK;
@@ -974,8 +1007,7 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8) &&
         env_int("SGPU_WALK", 1)) {
         // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase, warp-private tiles
-        const int K = env_int("SGPU_WALK_K", 7);
-        const int mb = env_int("SGPU_WALK_MINB", 3);
+        const int K = env_int("SGPU_WALK_K", 5) == 7 ? 7 : 5;  // measured (L=4, 1024 ch): K=1 408, 3 412, 5 434, 7 421, 9 404 G out-samp/s
         const int G = 32 / (int)f->L;
         const int rows = 2 + G * K;
         a.RS = rows | 1;
@@ -995,13 +1027,8 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     } while (0)
 #define LAUNCH_IWALK_T(LV)                                                \
     do {                                                                  \
-        if (K == 5) LAUNCH_IWALK(LV, 5, 3);                               \
-        else if (K == 3) LAUNCH_IWALK(LV, 3, 3);                          \
-        else if (K == 1) LAUNCH_IWALK(LV, 1, 3);                          \
-        else if (K == 9) LAUNCH_IWALK(LV, 9, 3);                          \
-        else if (K == 11) LAUNCH_IWALK(LV, 11, 3);                        \
-        else if (mb == 4) LAUNCH_IWALK(LV, 7, 4);                         \
-        else LAUNCH_IWALK(LV, 7, 3);                                      \
+        if (K == 7) LAUNCH_IWALK(LV, 7, 3);                               \
+        else LAUNCH_IWALK(LV, 5, 3);                                      \
     } while (0)
         if (f->L == 2) LAUNCH_IWALK_T(2);
         else if (f->L == 4) LAUNCH_IWALK_T(4);

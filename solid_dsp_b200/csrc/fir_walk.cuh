@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
     static_assert(RM % 32 == 0 && M % PS == 0 && (R / 2) % PS == 0, "shape");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Qpad = a.Qpad, HR = Qpad / R, rows = HR + G, RS = a.RS;
-    const int plane_f4 = (R / 2) * RS + 1, stage_f4 = M * plane_f4;  // >= 32 * (R/2 + 1): room for the reduction
+    const int plane_f4 = (R / 2) * RS + 1, stage_f4 = max(M * plane_f4, 32 * (R / 2 + 1));  // room for the reduction
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * stage_f4);
     {
         const int n4 = M * (Qpad + kTapSkew) / 4;
@@ -244,6 +244,102 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
                 if (o0 + q < a.n_out) y[q] = make_float2(v.x * s, v.y * s);
                 if (o0 + q + 1 < a.n_out) y[q + 1] = make_float2(v.z * s, v.w * s);
             }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Plain FIR (M = 1, real taps) with warp-private tiles.
+//   y[n] = scale * sum_i h[T-1-i] * x[n-i]                                   (fir/mod.rs:209-212)
+// A warp tile is 32 runs of R outputs (one per lane) plus the Qpad-sample halo in front of them; NS
+// private stages filled by 16-byte cp.async, __syncwarp only.  The R outputs of a lane are turned
+// into coalesced 16-byte stores through the stage the warp has just finished reading.
+template <int R, int NW, int MINB, int TPW, int NS>
+__global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a) {
+    extern __shared__ float4 smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Qpad = a.Qpad, HR = Qpad / R, rows = HR + 32, RS = a.RS;
+    const int stage_f4 = max((R / 2) * RS + 1, 32 * (R / 2 + 1));  // room for the output transpose
+    float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * NS * stage_f4);
+    {
+        const int n4 = (Qpad + kTapSkew) / 4;
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        float4 *dst = reinterpret_cast<float4 *>(taps_s);
+        for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int ch = blockIdx.y;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    float4 *stage0 = smem + (size_t)warp * NS * stage_f4;
+    const int total_pairs = rows * (R / 2);
+    // loader role: pair pe = it*32 + lane -> row pe / (R/2), piece pe % (R/2)
+    const int role = (lane % (R / 2)) * RS + lane / (R / 2);
+    constexpr int ROWS_PER_IT = 32 / (R / 2);
+    auto issue = [&](const long long m_base, float4 *plane) {
+        const long long i_lo = m_base - Qpad;
+        if (i_lo >= 0 && i_lo + (long long)rows * R <= a.n_in && a.vec_in) {
+            const float2 *src = x + i_lo + 2 * lane;
+            float4 *dst = plane + role;
+#pragma unroll 4
+            for (int pe = lane; pe < total_pairs; pe += 32) {
+                cp_async16(dst, src);
+                dst += ROWS_PER_IT;
+                src += 64;
+            }
+        } else {
+            const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
+            for (int pe = lane; pe < total_pairs; pe += 32) {
+                const long long i = i_lo + 2 * pe;
+                const float2 s0 = fetch_sample(x, hist, i, a.n_in, a.T);
+                const float2 s1 = fetch_sample(x, hist, i + 1, a.n_in, a.T);
+                plane[(pe % (R / 2)) * RS + pe / (R / 2)] = make_float4(s0.x, s0.y, s1.x, s1.y);
+            }
+        }
+    };
+    const int npairs = Qpad / (2 * R);
+    constexpr int TILE = 32 * R;
+    constexpr int RED = R / 2 + 1;
+    long long m_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    if (m_base >= a.n_out) return;
+    issue(m_base, stage0);
+#pragma unroll 1
+    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += TILE) {
+        cp_async_wait_all();
+        __syncwarp();
+        float4 *st = stage0 + (NS == 2 ? (t & 1) * stage_f4 : 0);
+        if (NS == 2 && t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE, stage0 + ((t + 1) & 1) * stage_f4);
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+        fir_core<R, true>(acc, st, RS, HR + lane, taps_s, npairs);
+        // transpose: lane's R outputs -> rows of the stage -> 16-byte pieces, 4 runs (512 bytes) per instruction
+        __syncwarp();
+        const float s = a.scale_re;
+#pragma unroll
+        for (int q = 0; q < R / 2; ++q)
+            st[lane * RED + q] = make_float4(acc[2 * q].x * s, acc[2 * q].y * s, acc[2 * q + 1].x * s, acc[2 * q + 1].y * s);
+        __syncwarp();
+        float2 *__restrict__ y = a.out + (long long)ch * a.out_stride + m_base;
+        const int prow = lane / (R / 2), pq = lane % (R / 2);
+        if (a.vec_out && m_base + TILE <= a.n_out) {
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) {
+                const int run = i * ROWS_PER_IT + prow;
+                *reinterpret_cast<float4 *>(y + run * R + 2 * pq) = st[run * RED + pq];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) {
+                const int run = i * ROWS_PER_IT + prow;
+                const float4 v = st[run * RED + pq];
+                const long long o = m_base + run * R + 2 * pq;
+                if (o < a.n_out) y[run * R + 2 * pq] = make_float2(v.x, v.y);
+                if (o + 1 < a.n_out) y[run * R + 2 * pq + 1] = make_float2(v.z, v.w);
+            }
+        }
+        if (NS == 1) {
+            __syncwarp();  // the stage is free again
+            if (t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE, stage0);
         }
     }
 }
