@@ -76,15 +76,18 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs
     const int g = lane / L, p = lane % L;
     const float *tp = taps_s + p * (QP + kTapSkew);
     // first input position of the warp's current tile
-    long long n_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    // the block covers NW * TPW consecutive tiles; its warps take them round-robin, so neighbouring tiles
+    // (which share the halo) are in flight at the same time and the halo is an L2 hit
+    constexpr long long STEP = (long long)NW * TILE;
+    long long n_base = ((long long)blockIdx.x * NW * TPW + warp) * (long long)TILE;
     if (n_base >= a.n_in) return;
     issue(n_base, stage0);
 #pragma unroll 1
-    for (int t = 0; t < TPW && n_base < a.n_in; ++t, n_base += TILE) {
+    for (int t = 0; t < TPW && n_base < a.n_in; ++t, n_base += STEP) {
         cp_async_wait_all();
         __syncwarp();  // tile t landed; every lane is done with the other stage
         const float4 *plane = stage0 + (t & 1) * STAGE_F4;
-        if (t + 1 < TPW && n_base + TILE < a.n_in) issue(n_base + TILE, stage0 + ((t + 1) & 1) * STAGE_F4);
+        if (t + 1 < TPW && n_base + STEP < a.n_in) issue(n_base + STEP, stage0 + ((t + 1) & 1) * STAGE_F4);
         int row = HR + g * K + (K - 1);                          // newest row of the group's newest run
         long long n0 = n_base + (long long)(g * K + (K - 1)) * R;  // its first input position
         float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0 * L + p;
@@ -187,11 +190,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
     const int npairs = Qpad / (2 * R);
     constexpr int TILE = G * R;  // outputs per warp tile
     constexpr int RED = R / 2 + 1;  // float4 pitch of a lane's partial sums
-    long long m_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    constexpr long long STEP = (long long)NW * TILE;  // warps take the block's tiles round-robin (halo = L2 hit)
+    long long m_base = ((long long)blockIdx.x * NW * TPW + warp) * (long long)TILE;
     if (m_base >= a.n_out) return;
     issue(m_base);
 #pragma unroll 1
-    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += TILE) {
+    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += STEP) {
         cp_async_wait_all();
         __syncwarp();
         float2 acc[R];
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
             for (int k = 0; k < NPC; ++k) out[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
         }
         __syncwarp();  // the stage is free again
-        if (t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE);
+        if (t + 1 < TPW && m_base + STEP < a.n_out) issue(m_base + STEP);
         // lane `part` stores the pieces k*PS + part, k < NPC: sector-complete per instruction
         const long long o0 = m_base + (long long)g * R;
         float2 *__restrict__ y = a.out + (long long)ch * a.out_stride + o0;
@@ -299,15 +303,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
     const int npairs = Qpad / (2 * R);
     constexpr int TILE = 32 * R;
     constexpr int RED = R / 2 + 1;
-    long long m_base = ((long long)blockIdx.x * NW + warp) * ((long long)TPW * TILE);
+    constexpr long long STEP = (long long)NW * TILE;  // warps take the block's tiles round-robin (halo = L2 hit)
+    long long m_base = ((long long)blockIdx.x * NW * TPW + warp) * (long long)TILE;
     if (m_base >= a.n_out) return;
     issue(m_base, stage0);
 #pragma unroll 1
-    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += TILE) {
+    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += STEP) {
         cp_async_wait_all();
         __syncwarp();
         float4 *st = stage0 + (NS == 2 ? (t & 1) * stage_f4 : 0);
-        if (NS == 2 && t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE, stage0 + ((t + 1) & 1) * stage_f4);
+        if (NS == 2 && t + 1 < TPW && m_base + STEP < a.n_out) issue(m_base + STEP, stage0 + ((t + 1) & 1) * stage_f4);
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
         }
         if (NS == 1) {
             __syncwarp();  // the stage is free again
-            if (t + 1 < TPW && m_base + TILE < a.n_out) issue(m_base + TILE, stage0);
+            if (t + 1 < TPW && m_base + STEP < a.n_out) issue(m_base + STEP, stage0);
         }
     }
 }

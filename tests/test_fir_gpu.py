@@ -314,3 +314,55 @@ def test_interp_complex_taps(fir, L):
         ref.push(s_)
         for p_ in range(4):
             assert abs(bank.execute(p_) - ref.execute(p_)) <= TOL * 20
+
+
+# ------------------------------------------------------------------ warp-private tile kernels (fir_walk.cuh)
+@pytest.mark.parametrize("T", [33, 64, 512])
+def test_fir_many_warp_tiles(fir, T):
+    """Streams that span several warps, blocks and TPW groups of fir_warp_kernel, ragged end, split
+    calls whose boundaries fall inside tiles; two channels with a row stride."""
+    rng = np.random.default_rng(T)
+    h = f32_taps(rng.uniform(-1, 1, T))
+    n = 4 * 4096 * 4 + 777
+    x = rand_cf32(rng, (2, n))
+    f = fir.FIRFilter(h, 0.75, n_channels=2)
+    cuts = [0, 5000, 5001, 40000, n]
+    got = np.concatenate([f.execute_block(x[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    for c in range(2):
+        assert nerr(got[c], O.fir_fast(h, x[c], 0.75)) <= TOL
+
+
+@pytest.mark.parametrize("M,T", [(2, 40), (4, 128), (8, 256), (8, 700)])
+def test_decim_many_warp_tiles(fir, M, T):
+    rng = np.random.default_rng(M * 1000 + T)
+    h = f32_taps(rng.uniform(-1, 1, T))
+    n = 150001
+    x = rand_cf32(rng, (3, n))
+    f = fir.DecimatingFIRFilter(h, 1.25, M, n_channels=3)
+    cuts = [0, 3, 50003, 50004, n]
+    got = np.concatenate([f.execute_block(x[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert got.shape == (3, n // M)
+    for c in range(3):
+        assert nerr(got[c], O.fir_fast(h, x[c], 1.25, M)) <= TOL
+
+
+@pytest.mark.parametrize("L,T", [(2, 64), (4, 128), (8, 256), (4, 100), (8, 17)])
+def test_interp_many_warp_tiles(fir, L, T):
+    """Sub-filters of <= 32 taps take fir_interp_walk_kernel: several warps / blocks / tiles per warp,
+    ragged end inside a run, split calls."""
+    rng = np.random.default_rng(L * 1000 + T)
+    h = f32_taps(rng.uniform(-1, 1, T))
+    n = 60001
+    x = rand_cf32(rng, (2, n))
+    f = fir.InterpolatingFIRFilter(h, L, n_channels=2)
+    cuts = [0, 7, 20000, 20013, n]
+    got = np.concatenate([f.execute_block(x[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert got.shape == (2, n * L)
+    for c in range(2):
+        assert nerr(got[c], O.firinterp_fast(h, L, x[c])) <= TOL
+    # phase alignment: an impulse at input n0 must put hpad[p + j*L] at output (n0 + j)*L + p
+    imp = np.zeros(2000, dtype=np.complex64)
+    imp[777] = 1.0
+    y = fir.InterpolatingFIRFilter(h, L).execute_block(imp)
+    ref = O.firinterp_fast(h, L, imp)
+    assert np.array_equal(np.nonzero(y)[0], np.nonzero(ref)[0]) and nerr(y, ref) <= 1e-7

@@ -258,3 +258,57 @@ def test_dot_product(golden):
     got = DotProduct(cc, Direction.FORWARD).execute(xv)
     for v in range(4):
         assert abs(got[v] - O.DotProduct(cc, O.DotProduct.FORWARD).execute(xv[v])) <= 1e-4
+
+
+# ------------------------------------------------------------------ gain folding / strategy selection
+def test_sos_sections_that_cannot_be_folded(iir):
+    """A section with b0 == 0 (pure delay numerator) and one with a tiny b0 (running product leaves
+    2^-40): the kernel must fall back to the 5-operation biquad; states still in reference scaling."""
+    rng = np.random.default_rng(77)
+    x = rand_cf32(rng, (33, 2000))
+    for ff, fb in (([0.0, 1.0, 0.5, 0.3, 0.2, 0.1], [1.0, -0.5, 0.25, 1.0, 0.3, 0.1]),
+                   ([1e-7, 2e-7, 1e-7, 1e-7, 2e-7, 1e-7, 0.2, 0.1, 0.3], [1.0, -1.2, 0.5, 1.0, -0.9, 0.4, 1.0, 0.1, 0.2])):
+        ff, fb = f32_taps(ff), f32_taps(fb)
+        f = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder, n_channels=33)
+        got = f.execute_block(x)
+        for c in (0, 32):
+            ref, ost = O.sos_cascade_fast(ff, fb, x[c])
+            assert nerr(got[c], ref) <= TOL
+        st, _ = f.get_state()
+        assert nerr(st[32], ost.ravel()) <= 1e-4
+
+
+def test_sos_folded_states_cross_the_abi_in_reference_scaling(iir):
+    """get_state after a folded run == the oracle's (v1, v2); set_state of those values resumes."""
+    rng = np.random.default_rng(78)
+    ff, fb = _sections(8)
+    x = rand_cf32(rng, (4, 1500))
+    f = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder, n_channels=4)
+    f.execute_block(x[:, :700])
+    st, _ = f.get_state()
+    for c in range(4):
+        _, ost = O.sos_cascade_fast(ff, fb, x[c, :700])
+        assert nerr(st[c], ost.ravel()) <= 1e-4
+    g = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder, n_channels=4)
+    g.set_state(st)
+    tail = g.execute_block(x[:, 700:])
+    for c in range(4):
+        ref, _ = O.sos_cascade_fast(ff, fb, x[c])
+        assert nerr(tail[c], ref[700:]) <= TOL
+
+
+@pytest.mark.parametrize("C,n", [(100, 30000), (8, 20000), (33, 4096), (1, 300000)])
+def test_sos_auto_strategy(iir, C, n):
+    """Default mode: few channels x long streams are cut into chunks (fused scan, both row layouts);
+    results, split calls and final states match the sequential recurrence."""
+    rng = np.random.default_rng(C + n)
+    ff, fb = _sections(8)
+    x = rand_cf32(rng, (C, n))
+    f = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder, n_channels=C)
+    h = n // 3 + 5
+    got = np.concatenate([f.execute_block(x[:, :h]), f.execute_block(x[:, h:])], axis=1)
+    for c in sorted({0, C // 2, C - 1}):
+        ref, ost = O.sos_cascade_fast(ff, fb, x[c])
+        assert nerr(got[c], ref) <= TOL
+    st, _ = f.get_state()
+    assert nerr(st[C - 1], ost.ravel()) <= 1e-4
