@@ -356,10 +356,15 @@ def run_gpu_arm(args):
         t_fma = W["flop_per_unit"] / (peak_fma * 1e12)
         t_hbm = W["bytes_per_unit"] / (hbm_peak * 1e9)
         bound = "fma" if t_fma >= t_hbm else "hbm"
-        traffic = None
+        # DRAM bytes (read + write) of one launch of the dominant kernel at this workload's full size,
+        # from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture
+        # (tools/profile_round.sh -> tools/traffic_json.py); only valid for the default sizes at N = 1.
+        traffic, traffic_detail = None, None
         tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists():
-            traffic = json.loads(tf.read_text()).get(name)
+        if tf.exists() and world == 1 and args.log2_samples == 30:
+            traffic_detail = json.loads(tf.read_text()).get(name)
+            if traffic_detail:
+                traffic = traffic_detail.get("dram_bytes")
         roofline = {
             "bound": bound,
             "achieved": ach_tflops if bound == "fma" else ach_gbs,
@@ -367,6 +372,7 @@ def run_gpu_arm(args):
             "unit": "TFLOP/s" if bound == "fma" else "GB/s",
             "frac": (ach_tflops / peak_fma) if bound == "fma" else (ach_gbs / hbm_peak),
             "traffic": traffic,
+            "traffic_detail": traffic_detail,
             "kernel": {"fir": "fir_decim_kernel<R=16,M1>", "decim": "fir_decim_kernel<R=16>",
                        "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
                        "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)"}[name],

@@ -680,7 +680,7 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     do {                                                                                      \
         if (PS == 1) LAUNCH_DWARP(MV, 1, 1, 4);                                               \
         else if (PS == 2) LAUNCH_DWARP(MV, 2, 2, 4);                                          \
-        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 3);                                       \
+        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4);                                       \
     } while (0)
         if (f->M == 8) LAUNCH_DWARP_M(8);
         else if (f->M == 4) LAUNCH_DWARP_M(4);
