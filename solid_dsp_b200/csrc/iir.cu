@@ -104,15 +104,40 @@ __device__ __forceinline__ float2 biquad(float2 x, float2 &v1, float2 &v2, const
 }
 
 // the whole cascade on one sample.  FOLD: sections 0 .. NSEC-2 have b0 == 1 and the last section
-// carries the product of all b0 (see fold_sections on the host side).
+// carries the product of all b0 (see fold_sections on the host side).  st[2s] = v1, st[2s+1] = v2.
 template <int NSEC, bool FOLD>
-__device__ __forceinline__ float2 cascade(float2 y, float2 (&v1)[NSEC], float2 (&v2)[NSEC], const SosCoefs &k) {
+__device__ __forceinline__ float2 cascade(float2 y, float2 (&st)[2 * NSEC], const SosCoefs &k) {
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
-        if (FOLD && s < NSEC - 1) y = biquad<true>(y, v1[s], v2[s], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
-        else y = biquad<false>(y, v1[s], v2[s], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
+        if (FOLD && s < NSEC - 1)
+            y = biquad<true>(y, st[2 * s], st[2 * s + 1], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
+        else
+            y = biquad<false>(y, st[2 * s], st[2 * s + 1], k.b0[s], k.b1[s], k.b2[s], k.na1[s], k.na2[s]);
     }
     return y;
+}
+
+// Normal mode (iir/mod.rs:98-130,272-280): one direct form II of order W-1 with W state values
+// st[i] = v[n-1-i].  k.b0[i] = b_i / a0, k.na1[i] = -a_{i+1} / a0 (zero padded to W).
+template <int W>
+__device__ __forceinline__ float2 normal_step(float2 x, float2 (&st)[W], const SosCoefs &k) {
+    float2 v0 = x;
+#pragma unroll
+    for (int i = 0; i + 1 < W; ++i) v0 = __ffma2_rn(st[i], make_float2(k.na1[i], k.na1[i]), v0);
+    float2 y = __fmul2_rn(v0, make_float2(k.b0[0], k.b0[0]));
+#pragma unroll
+    for (int i = 0; i + 1 < W; ++i) y = __ffma2_rn(st[i], make_float2(k.b0[i + 1], k.b0[i + 1]), y);
+#pragma unroll
+    for (int i = W - 1; i > 0; --i) st[i] = st[i - 1];
+    st[0] = v0;
+    return y;
+}
+
+// one sample through the filter the kernel was instantiated for (NORD > 0: Normal mode of window NORD)
+template <int NSEC, bool FOLD, int NORD>
+__device__ __forceinline__ float2 filter_step(float2 x, float2 (&st)[NORD > 0 ? NORD : 2 * NSEC], const SosCoefs &k) {
+    if constexpr (NORD > 0) return normal_step<NORD>(x, st, k);
+    else return cascade<NSEC, FOLD>(x, st, k);
 }
 
 // WRAP: 0 plain, 1 decimating (keep every M-th output), 2 interpolating (L-1 zeros after each input)
@@ -120,8 +145,9 @@ __device__ __forceinline__ float2 cascade(float2 y, float2 (&v1)[NSEC], float2 (
 // Full tiles (every row of the warp has 16 more samples) take the fast path: cp.async prefetch of
 // the next tile, unpredicated fully unrolled cascade, 16-byte coalesced stores.  The ragged tail
 // (and every tile of the interpolating wrapper) takes the guarded path.
-template <int NSEC, int WRAP, bool FOLD, int TILE, int NW, int MINB>
+template <int NSEC, int WRAP, bool FOLD, int TILE, int NW, int MINB, int NORD = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a) {
+    constexpr int NST = NORD > 0 ? NORD : 2 * NSEC;  // complex state values per row
     extern __shared__ float4 smem[];
     constexpr int kTile = TILE;          // samples per channel per tile (TILE * 8 bytes)
     constexpr int LPR = TILE / 2;        // loader lanes per row (16 bytes each)
@@ -209,19 +235,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     const long long warm_tiles = warm / kTile;  // <= full_tiles: every valid row is longer than `warm`
 
     // state
-    float2 v1[NSEC], v2[NSEC];
+    float2 st[NST];
 #pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        v1[s] = make_float2(0.f, 0.f);
-        v2[s] = make_float2(0.f, 0.f);
-    }
+    for (int i = 0; i < NST; ++i) st[i] = make_float2(0.f, 0.f);
     if (a.state_in && lane < nvalid && st_in >= 0) {
-        const float4 *sp = reinterpret_cast<const float4 *>(a.state_in + st_in * (2 * NSEC));
+        const float2 *sp = a.state_in + st_in * NST;
+        if constexpr (NST % 2 == 0) {
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-            const float4 t = sp[s];
-            v1[s] = make_float2(t.x, t.y);
-            v2[s] = make_float2(t.z, t.w);
+            for (int i = 0; i < NST / 2; ++i) {
+                const float4 t = reinterpret_cast<const float4 *>(sp)[i];
+                st[2 * i] = make_float2(t.x, t.y);
+                st[2 * i + 1] = make_float2(t.z, t.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NST; ++i) st[i] = sp[i];
         }
     }
 
@@ -286,11 +314,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
             for (int j = 0; j < LPR; ++j) {
                 const float4 xin = myrow[j];
                 float2 y0 = make_float2(xin.x, xin.y), y1 = make_float2(xin.z, xin.w);
-                y0 = cascade<NSEC, FOLD>(y0, v1, v2, a.k);
+                y0 = filter_step<NSEC, FOLD, NORD>(y0, st, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y0; ++dec_ptr; }
                 }
-                y1 = cascade<NSEC, FOLD>(y1, v1, v2, a.k);
+                y1 = filter_step<NSEC, FOLD, NORD>(y1, st, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y1; ++dec_ptr; }
                 }
@@ -363,7 +391,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
                 } else {
                     y = *cell;
                 }
-                y = cascade<NSEC, FOLD>(y, v1, v2, a.k);
+                y = filter_step<NSEC, FOLD, NORD>(y, st, a.k);
                 if constexpr (WRAP == 1) {
                     if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out) *dec_ptr = y; ++dec_ptr; }
                 } else {
@@ -389,9 +417,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     }
 
     if (a.state_out && lane < nvalid && st_out >= 0) {
-        float4 *sp = reinterpret_cast<float4 *>(a.state_out + st_out * (2 * NSEC));
+        float2 *sp = a.state_out + st_out * NST;
+        if constexpr (NST % 2 == 0) {
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) sp[s] = make_float4(v1[s].x, v1[s].y, v2[s].x, v2[s].y);
+            for (int i = 0; i < NST / 2; ++i)
+                reinterpret_cast<float4 *>(sp)[i] = make_float4(st[2 * i].x, st[2 * i].y, st[2 * i + 1].x, st[2 * i + 1].y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NST; ++i) sp[i] = st[i];
+        }
     }
 }
 
@@ -660,6 +694,34 @@ int launch_sos_n(const IirArgs &a, int wrap, cudaStream_t s) {
     return launch_sos_t<NSEC, 0, FOLD>(a, s);
 }
 
+// Normal mode, plain wrapper, window W <= 8: the tile kernel with the direct-form step
+template <int W>
+int launch_normal_t(const IirArgs &a, cudaStream_t s) {
+    constexpr int TILE = kScanTile, NW = 4, MINB = 3;
+    const unsigned blocks = (unsigned)((a.n_warps + NW - 1) / NW);
+    const size_t smem = (size_t)NW * 2 * 32 * (TILE / 2 + 1) * sizeof(float4);
+    auto kern = iir_sos_kernel<1, 0, false, TILE, NW, MINB, W>;
+    SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, NW * 32, smem, s>>>(a);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    return SGPU_OK;
+}
+
+int launch_normal(int W, const IirArgs &a, cudaStream_t s) {
+    switch (W) {
+        case 1: return launch_normal_t<1>(a, s);
+        case 2: return launch_normal_t<2>(a, s);
+        case 3: return launch_normal_t<3>(a, s);
+        case 4: return launch_normal_t<4>(a, s);
+        case 5: return launch_normal_t<5>(a, s);
+        case 6: return launch_normal_t<6>(a, s);
+        case 7: return launch_normal_t<7>(a, s);
+        case 8: return launch_normal_t<8>(a, s);
+    }
+    return fail(SGPU_ERR_UNSUPPORTED, "Normal-mode window above 8 in the tile kernel");
+}
+
 int launch_sos(const sgpu_iir *f, const IirArgs &a, int wrap, cudaStream_t s) {
 #define SGPU_SOS_CASE(N) \
     case N: return f->fold ? launch_sos_n<N, true>(a, wrap, s) : launch_sos_n<N, false>(a, wrap, s);
@@ -739,6 +801,21 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
             cudaStream_t s) {
     const bool vec = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (istr % 2 == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (ostr % 2 == 0);
+    if (f->type == SGPU_IIR_NORMAL && f->wrap == SGPU_IIR_PLAIN && f->W <= 8 && !getenv("SGPU_IIR_NORMAL_SLOW")) {
+        // tile kernel (coalesced 256-byte row segments, states in registers); coefficients ride in the
+        // SosCoefs block: b0[i] = b_i/a0, na1[i] = -a_{i+1}/a0
+        IirArgs a{};
+        a.in = d_in; a.out = d_out;
+        a.in_stride = istr; a.out_stride = ostr; a.n_in = n_in;
+        a.C = (int)f->C; a.factor = 1; a.idx0 = 0;
+        a.vec = vec ? 1 : 0;
+        for (int i = 0; i < kMaxSec; ++i) { a.k.b0[i] = 0.f; a.k.na1[i] = 0.f; }
+        for (int i = 0; i < f->nb; ++i) a.k.b0[i] = (float)f->num_norm[i];
+        for (int i = 0; i < f->na - 1; ++i) a.k.na1[i] = -(float)f->den_norm[i];
+        a.layout = 0; a.P = 1; a.Lc = n_in; a.n_warps = (long long)ceil_div(f->C, 32);
+        a.state_in = f->d_state; a.state_out = f->d_state; a.write_out = 1;
+        return launch_normal(f->W, a, s);
+    }
     if (f->type == SGPU_IIR_NORMAL) {
         NormalArgs a{};
         a.in = d_in; a.out = d_out; a.state = f->d_state;

@@ -312,3 +312,29 @@ def test_sos_auto_strategy(iir, C, n):
         assert nerr(got[c], ref) <= TOL
     st, _ = f.get_state()
     assert nerr(st[C - 1], ost.ravel()) <= 1e-4
+
+
+@pytest.mark.parametrize("W", [1, 2, 3, 5, 8, 9, 12])
+def test_iir_normal_mode_orders(iir, W):
+    """Normal mode over a range of windows: W <= 8 runs in the tile kernel (states in registers,
+    coalesced rows), larger windows in the one-thread-per-channel kernel.  70 channels so that three
+    warps (one of them partial) are busy; split calls; state in the reference's order (newest first)."""
+    rng = np.random.default_rng(W)
+    nb, na = W, max(1, W - 1)
+    b = f32_taps(rng.uniform(-0.5, 0.5, nb))
+    # stable denominator: small feedback taps
+    a = f32_taps(np.concatenate([[1.0], rng.uniform(-0.9, 0.9, na - 1) / max(1, na - 1)]))
+    x = rand_cf32(rng, (70, 3001))
+    f = iir.IIRFilter(b, a, iir.IIRFilterType.Normal, n_channels=70)
+    got = np.concatenate([f.execute_block(x[:, :1000]), f.execute_block(x[:, 1000:1033]),
+                          f.execute_block(x[:, 1033:])], axis=1)
+    for c in (0, 31, 32, 69):
+        assert nerr(got[c], O.IIRFilter(b, a, O.NORMAL).execute_block(x[c])) <= TOL
+    g = iir.IIRFilter(b, a, iir.IIRFilterType.Normal, n_channels=70)
+    g.execute_block(x[:, :1000])
+    h = g.clone()
+    st, _ = g.get_state()
+    k = iir.IIRFilter(b, a, iir.IIRFilterType.Normal, n_channels=70)
+    k.set_state(st)
+    y1, y2, y3 = (q.execute_block(x[:, 1000:]) for q in (g, h, k))
+    assert np.array_equal(y1, y2) and np.array_equal(y1, y3) and np.array_equal(y1, got[:, 1000:])
