@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     const int nvalid = nrows;
     const long long max_len = len0, min_len = len0;
     const long long ntiles = (max_len + kTile - 1) / kTile;
-    const long long full_tiles = WRAP == 2 ? 0 : min_len / kTile;
+    long long full_tiles = WRAP == 2 ? 0 : min_len / kTile;  // WRAP 2: set by the interpolating fast path
     const long long warm_tiles = warm / kTile;  // <= full_tiles: every valid row is longer than `warm`
 
     // state
@@ -258,19 +258,103 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     auto role_r = [&](int i) { return lrow + RPI * i; };
     auto role_c = [&](int) { return lj; };
     int dec_cnt = a.idx0;                          // decimator phase (WRAP 1)
-    float2 *dec_ptr = a.out + out_base + (long long)lane * rstr_out;  // next decimated output (WRAP 1)
+    int kout = 0;                                  // outputs kept so far in the current tile (WRAP 1)
+    long long dec_pos = 0;                         // outputs stored so far per row (WRAP 1)
+
+    // loader / storer role: the lane's i-th 16-byte chunk of a tile is chunk role_c(i) of row
+    // role_r(i).  `whole` (warp-uniform): all 32 rows valid and 16-byte accesses allowed -> no
+    // per-row predicates or clamps.
+    const bool whole = a.vec && nvalid == 32;
+    float2 *st_ptr = a.out + out_base;
+    const long long st_step = RPI * rstr_out, st_role = (long long)lrow * rstr_out + 2 * lj;
+    const int role_off = lrow * kRowF4 + lj;
+    auto store_tile = [&](const float4 *cur) {  // one tile of outputs, 16-byte coalesced
+        if (whole) {
+            float2 *dst = st_ptr + st_role;
+            const float4 *src = cur + role_off;
+#pragma unroll
+            for (int i = 0; i < LPR; ++i) {
+                *reinterpret_cast<float4 *>(dst) = src[i * RPI * kRowF4];
+                dst += st_step;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < LPR; ++i) {
+                const int r = role_r(i), c = role_c(i);
+                const float4 v = cur[r * kRowF4 + c];
+                float2 *dst = st_ptr + (long long)r * rstr_out + 2 * c;
+                if (r < nvalid) {
+                    if (a.vec) {
+                        *reinterpret_cast<float4 *>(dst) = v;
+                    } else {
+                        dst[0] = make_float2(v.x, v.y);
+                        dst[1] = make_float2(v.z, v.w);
+                    }
+                }
+            }
+        }
+    };
+
+    // ------------------------------------------------------------------ interpolating wrapper, fast path
+    // L a power of two <= the tile: a tile of 32 outputs per row consumes 32/L inputs per row, which
+    // are staged (8-byte cp.async, double buffered in the second tile buffer) while the outputs are
+    // produced in the first one: input, then L-1 zeros (iir/interp.rs:184-190).
+    long long ip_done = 0;  // inputs per row consumed by this path
+    if constexpr (WRAP == 2) {
+        const int L = a.factor;
+        const bool pow2 = (L & (L - 1)) == 0 && L >= 2 && L <= kTile;
+        const long long tiles2 = pow2 ? len0 / kTile : 0;
+        if (tiles2 > 0) {
+            static_assert(kTile == 32, "interpolating fast path assumes 32-sample tiles");
+            const int sh = __ffs(L) - 1, ish = 5 - sh, IN_T = kTile >> sh;
+            constexpr int IPITCH = kTile / 2 + 1;  // float2 units: 136-byte rows, conflict-free lane reads
+            constexpr int ISTAGE = 32 * IPITCH;    // two stages = one tile buffer
+            float2 *ibuf = reinterpret_cast<float2 *>(buf + kTileF4);
+            const float2 *ld = a.in + in_base;
+            auto prefetch_in = [&](float2 *dst) {
+                for (int i = 0; i < IN_T; ++i) {
+                    const int e = i * 32 + lane, r = e >> ish, c = e & (IN_T - 1);
+                    const int rl = r < nvalid ? r : nvalid - 1;
+                    cp_async8(dst + r * IPITCH + c, ld + (long long)rl * rstr_in + c);
+                }
+                cp_async_commit();
+                ld += IN_T;
+            };
+            prefetch_in(ibuf);
+            for (long long t = 0; t < tiles2; ++t) {
+                const float2 *irow = ibuf + (t & 1) * ISTAGE + lane * IPITCH;
+                if (t + 1 < tiles2) {
+                    prefetch_in(ibuf + ((t + 1) & 1) * ISTAGE);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                float4 *orow = buf + lane * kRowF4;
+#pragma unroll
+                for (int j = 0; j < LPR; ++j) {
+                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                    if (((2 * j) & (L - 1)) == 0) y0 = irow[(2 * j) >> sh];
+                    y0 = filter_step<NSEC, FOLD, NORD>(y0, st, a.k);
+                    if (((2 * j + 1) & (L - 1)) == 0) y1 = irow[(2 * j + 1) >> sh];
+                    y1 = filter_step<NSEC, FOLD, NORD>(y1, st, a.k);
+                    orow[j] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+                __syncwarp();
+                if (a.write_out) store_tile(buf);
+                st_ptr += kTile;
+                __syncwarp();
+            }
+            ip_done = tiles2 * IN_T;
+            full_tiles = tiles2;
+        }
+    }
 
     // ------------------------------------------------------------------ fast path: full tiles
-    if (full_tiles > 0) {
-        // loader / storer role: the lane's i-th 16-byte chunk of a tile is chunk role_c(i) of row
-        // role_r(i).  `whole` (warp-uniform): all 32 rows valid and 16-byte accesses allowed -> no
-        // per-row predicates or clamps.
-        const bool whole = a.vec && nvalid == 32;
+    if (WRAP != 2 && full_tiles > 0) {
         const float2 *ld_ptr = a.in + in_base;
-        float2 *st_ptr = a.out + out_base;
-        const long long ld_step = RPI * rstr_in, st_step = RPI * rstr_out;
-        const long long ld_role = (long long)lrow * rstr_in + 2 * lj, st_role = (long long)lrow * rstr_out + 2 * lj;
-        const int role_off = lrow * kRowF4 + lj;
+        const long long ld_step = RPI * rstr_in;
+        const long long ld_role = (long long)lrow * rstr_in + 2 * lj;
         auto prefetch = [&](float4 *dst) {
             if (whole) {
                 const float2 *src = ld_ptr + ld_role;
@@ -315,43 +399,35 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
                 const float4 xin = myrow[j];
                 float2 y0 = make_float2(xin.x, xin.y), y1 = make_float2(xin.z, xin.w);
                 y0 = filter_step<NSEC, FOLD, NORD>(y0, st, a.k);
-                if constexpr (WRAP == 1) {
-                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y0; ++dec_ptr; }
+                if constexpr (WRAP == 1) {  // kept outputs are compacted at the head of the row (warp-uniform)
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; reinterpret_cast<float2 *>(myrow)[kout++] = y0; }
                 }
                 y1 = filter_step<NSEC, FOLD, NORD>(y1, st, a.k);
                 if constexpr (WRAP == 1) {
-                    if (++dec_cnt == a.factor) { dec_cnt = 0; if (a.write_out && lane < nvalid) *dec_ptr = y1; ++dec_ptr; }
+                    if (++dec_cnt == a.factor) { dec_cnt = 0; reinterpret_cast<float2 *>(myrow)[kout++] = y1; }
                 }
                 if constexpr (WRAP == 0) myrow[j] = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
-            if constexpr (WRAP == 0) {
+            if constexpr (WRAP == 1) {
+                // the tile kept kout <= kTile/2 outputs per row (factor >= 2): half-warps store rows of 8-byte samples
                 __syncwarp();
-                if (a.write_out && t >= warm_tiles) {
-                    if (whole) {
-                        float2 *dst = st_ptr + st_role;
-                        const float4 *src = cur + role_off;
+                if (a.write_out) {
+                    const int hrow = lane >> 4, col = lane & 15;
+                    static_assert(kTile == 32, "decimating store assumes 32-sample tiles");
+                    const float2 *src = reinterpret_cast<const float2 *>(cur) + hrow * (2 * kRowF4) + col;
+                    float2 *dst = a.out + out_base + (long long)hrow * rstr_out + dec_pos + col;
 #pragma unroll
-                        for (int i = 0; i < LPR; ++i) {
-                            *reinterpret_cast<float4 *>(dst) = src[i * RPI * kRowF4];
-                            dst += st_step;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < LPR; ++i) {
-                            const int r = role_r(i), c = role_c(i);
-                            const float4 v = cur[r * kRowF4 + c];
-                            float2 *dst = st_ptr + (long long)r * rstr_out + 2 * c;
-                            if (r < nvalid) {
-                                if (a.vec) {
-                                    *reinterpret_cast<float4 *>(dst) = v;
-                                } else {
-                                    dst[0] = make_float2(v.x, v.y);
-                                    dst[1] = make_float2(v.z, v.w);
-                                }
-                            }
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        if (col < kout && 2 * i + hrow < nvalid) *dst = src[i * (4 * kRowF4)];
+                        dst += 2 * rstr_out;
                     }
                 }
+                dec_pos += kout;
+                kout = 0;
+            }
+            if constexpr (WRAP == 0) {
+                __syncwarp();
+                if (a.write_out && t >= warm_tiles) store_tile(cur);
                 st_ptr += kTile;
             }
             __syncwarp();
@@ -359,11 +435,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     }
 
     // ------------------------------------------------------------------ guarded path: ragged tail
+    float2 *dec_ptr = a.out + out_base + (long long)lane * rstr_out + dec_pos;  // next decimated output (WRAP 1)
     if (full_tiles < ntiles) {
         float4 *cur = buf;
         const float2 *my_in = a.in + in_base + (long long)lane * rstr_in;
         int ip_cnt = 0;       // interpolator phase (WRAP 2)
-        long long ip_in = 0;  // next input index (WRAP 2)
+        long long ip_in = ip_done;  // next input index (WRAP 2)
         for (long long t = full_tiles; t < ntiles; ++t) {
             const long long s0 = t * kTile;
             if constexpr (WRAP != 2) {
@@ -674,9 +751,7 @@ constexpr int kWarpsPerSm = 12;  // resident warps per SM of the plain kernel (s
 
 template <int NSEC, int WRAP, bool FOLD>
 int launch_sos_t(const IirArgs &a, cudaStream_t s) {
-    constexpr int TILE = WRAP == 0 ? kScanTile : 16;
-    constexpr int NW = WRAP == 0 ? 4 : 8;
-    constexpr int MINB = WRAP == 0 ? 3 : (NSEC > 8 ? 2 : 3);
+    constexpr int TILE = kScanTile, NW = 4, MINB = 3;
     const unsigned blocks = (unsigned)((a.n_warps + NW - 1) / NW);
     const size_t smem = (size_t)NW * 2 * 32 * (TILE / 2 + 1) * sizeof(float4);
     auto kern = iir_sos_kernel<NSEC, WRAP, FOLD, TILE, NW, MINB>;
@@ -723,6 +798,7 @@ int launch_normal(int W, const IirArgs &a, cudaStream_t s) {
 }
 
 int launch_sos(const sgpu_iir *f, const IirArgs &a, int wrap, cudaStream_t s) {
+    if (wrap != 0 && a.factor == 1) wrap = 0;  // decimation / interpolation by 1 is the plain filter
 #define SGPU_SOS_CASE(N) \
     case N: return f->fold ? launch_sos_n<N, true>(a, wrap, s) : launch_sos_n<N, false>(a, wrap, s);
     switch (f->nsec_pad) {

@@ -117,6 +117,23 @@ def iirn(Cn=65536, n=16400, nsec=8):
                       "Gsamp_s": tot / best / 1e6, "GBps": tot * 16 / best / 1e6}))
 
 
+def iirwrap(Cn=65536, logn=12, factor=4, nsec=8):
+    """decimating / interpolating IIR wrappers (iir/decim.rs, iir/interp.rs)"""
+    from solid_dsp_b200.filter.iir import DecimatingIIRFilter, InterpolatingIIRFilter, IIRFilterType
+    from solid_dsp_b200.filter.iirdes import stable_lowpass_sections
+    n = 1 << logn
+    ff, fb = stable_lowpass_sections(nsec)
+    x = torch.randn((Cn, n), dtype=torch.complex64, device="cuda")
+    f = DecimatingIIRFilter(ff, fb, IIRFilterType.SecondOrder, factor, n_channels=Cn)
+    best, _ = ev_time(lambda: f.execute_block(x))
+    print(json.dumps({"kernel": "iir_decim", "C": Cn, "n": n, "M": factor, "best_ms": best, "Gsamp_in_s": Cn * n / best / 1e6}))
+    xi = x[:, : n // factor].contiguous()
+    g = InterpolatingIIRFilter(ff, fb, IIRFilterType.SecondOrder, factor, n_channels=Cn)
+    best, _ = ev_time(lambda: g.execute_block(xi))
+    print(json.dumps({"kernel": "iir_interp", "C": Cn, "n_in": n // factor, "L": factor, "best_ms": best,
+                      "Gsamp_out_s": Cn * n / best / 1e6}))
+
+
 def iirscan(logn=26, nsec=8):
     from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
     from solid_dsp_b200.filter.iirdes import stable_lowpass_sections
