@@ -268,12 +268,15 @@ def run_gpu_arm(args):
         if args.log2_samples != 30:
             n_per = 1 << args.log2_samples
         if name == "iir_scan":
-            c_loc = 1  # does not shard: replicas only
-            units_total = n_per * world
+            c_loc = 1  # one stream: time segments per rank, warm-up halo from the previous rank
+            units_total = n_per
         else:
             _, c_loc = sharding.shard_channels(chans, world, rank)
             units_total = chans * n_per * (4 if name == "interp" else 1)
-        x = rand_c((c_loc, n_per))
+        n_loc = n_per
+        if name == "iir_scan" and world > 1:
+            _, n_loc = sharding.shard_stream(n_per, 32, world, rank)
+        x = rand_c((c_loc, n_loc))
         if name == "decim":
             filt = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
         elif name == "interp":
@@ -281,9 +284,18 @@ def run_gpu_arm(args):
         else:
             filt = IIRFilter(taps[0], taps[1], IIRFilterType.SecondOrder, n_channels=c_loc)
         shape_desc = {"channels": chans, "samples_per_channel": n_per}
+        if name == "iir_scan" and world > 1:
+            warm = filt.decay_length()
+            assert warm > 0, "the benchmark cascade decays"
+            halo_prev = torch.zeros(warm, dtype=torch.complex64, device=dev)
+            shape_desc.update({"segments": world, "halo": warm})
 
-        def step():
-            return filt.execute_block(x)
+            def step():
+                sharding.exchange_halo(x[0], halo_prev, rank, world, dist)
+                return sharding.iir_segment(filt, x, halo_prev.unsqueeze(0), rank)
+        else:
+            def step():
+                return filt.execute_block(x)
 
     def barrier():
         if world > 1:
@@ -396,7 +408,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": W["desc"], "name": name, **shape_desc,
                        "l2": "inputs (>= 2 GiB per rank) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"stream segments x{world} with halo" if name == "fir" else f"channels x{world}"},
+                       "parallelism": f"stream segments x{world} with halo" if name in ("fir", "iir_scan") else f"channels x{world}"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity,
         }

@@ -363,6 +363,11 @@ class IIRFilter : public Filter<cf32, cf32> {  // iir/mod.rs:68-419
     IIRFilterType iir_type() const { return (IIRFilterType)sgpu_iir_type(h_); }                  // :239
     size_t channels() const { return sgpu_iir_channels(h_); }
     void set_mode(int mode) { detail::check(sgpu_iir_set_mode(h_, mode)); }
+    std::size_t decay_length() const {
+        std::size_t n = 0;
+        detail::check(sgpu_iir_decay_length(h_, &n));
+        return n;
+    }
 
     std::vector<cf32> execute(cf32 sample) override { return execute_block(std::vector<cf32>{sample}); }  // :270
     std::vector<cf32> execute_block(const std::vector<cf32> &samples) override {                          // :310

@@ -206,6 +206,13 @@ size_t sgpu_iir_state_len(const sgpu_iir *f); /* complex values per channel */
  * when the filter's memory decays within 2^16 samples, else the three-pass scan), 2 three-pass scan
  * (zero-state pass, f64 carry recurrence, output pass) regardless of the decay. */
 int sgpu_iir_set_mode(sgpu_iir *f, int mode);
+/* Memory of a second-order cascade in samples: the smallest multiple of 32 after which the influence
+ * of an older state is below 1e-10 (infinity norm of the zero-input transition matrix power), 0 when
+ * the filter does not decay within 2^16 samples or is in Normal mode.  A stream cut into segments
+ * (one per GPU) stays within 1e-10 of the unbroken recurrence when every segment but the first is
+ * preceded by that many samples of the previous segment: reset, execute_block(halo) with the output
+ * discarded, then execute_block(segment).  No counterpart in the reference (it is single-threaded). */
+int sgpu_iir_decay_length(sgpu_iir *f, size_t *n);
 
 /* ---- DotProduct ----------------------------------------------------------------------
  * sum_{i < min(len_c, len_x)} c[i] * x[i], c stored FORWARD or REVERSED

@@ -112,6 +112,7 @@ extern "C" {
     pub fn sgpu_iir_reset(f: *mut sgpu_iir) -> c_int;
     pub fn sgpu_iir_state_len(f: *const sgpu_iir) -> size_t;
     pub fn sgpu_iir_set_mode(f: *mut sgpu_iir, mode: c_int) -> c_int;
+    pub fn sgpu_iir_decay_length(f: *mut sgpu_iir, n: *mut usize) -> c_int;
 
     pub fn sgpu_dot_create(coefs: *const c_double, n: size_t, kind: c_int, dir: c_int,
                            out: *mut *mut sgpu_dot) -> c_int;

@@ -103,6 +103,7 @@ PROTOTYPES = {
     "sgpu_iir_reset": (C.c_int, [vp]),
     "sgpu_iir_state_len": (c_size, [vp]),
     "sgpu_iir_set_mode": (C.c_int, [vp, C.c_int]),
+    "sgpu_iir_decay_length": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "sgpu_dot_create": (C.c_int, [c_dp, c_size, C.c_int, C.c_int, vpp]),
     "sgpu_dot_destroy": (C.c_int, [vp]),
     "sgpu_dot_len": (c_size, [vp]),

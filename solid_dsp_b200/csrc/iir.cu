@@ -1170,6 +1170,15 @@ SGPU_EXPORT int sgpu_iir_set_mode(sgpu_iir *f, int mode) {
     return SGPU_OK;
 }
 
+SGPU_EXPORT int sgpu_iir_decay_length(sgpu_iir *f, size_t *n) {
+    if (!f || !n) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    *n = 0;
+    if (f->type != SGPU_IIR_SECOND_ORDER) return SGPU_OK;
+    const long long d = decay_length(f);
+    if (d > 0) *n = (size_t)d;
+    return SGPU_OK;
+}
+
 SGPU_EXPORT int sgpu_iir_numerator_coefs(const sgpu_iir *f, double *out, size_t *n) {
     if (!f || !n) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     const std::vector<double> &v = f->type == SGPU_IIR_SECOND_ORDER ? f->ff_raw : f->num_norm;

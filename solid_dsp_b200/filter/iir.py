@@ -111,6 +111,13 @@ class IIRFilter(Filter):
         """-1 auto, 0 one-channel-per-thread batch, 1 chunked scan (fused when the filter decays), 2 three-pass scan"""
         check(lib.sgpu_iir_set_mode(self._h, mode))
 
+    def decay_length(self) -> int:
+        """samples after which an older state no longer matters (1e-10); 0 = does not decay.
+        Segments of one stream on different GPUs warm up over that many preceding samples."""
+        n = _ffi.c_size()
+        check(lib.sgpu_iir_decay_length(self._h, C.byref(n)))
+        return n.value
+
     def execute_block(self, samples):  # iir/mod.rs:310
         ib = InBuf(samples, self._C)
         n_out = lib.sgpu_iir_out_len(self._h, ib.n)

@@ -5,6 +5,10 @@
   * one long FIR stream: contiguous time segments; rank r > 0 needs the T-1 samples that precede
     its segment (the "halo") -- one tiny point-to-point message per boundary per step.  For a
     decimator the segment starts are multiples of M so every rank starts at decimator phase 0.
+  * one long IIR stream (second-order cascade whose memory decays): contiguous time segments; rank
+    r > 0 warms its filter up over the `decay_length` samples that precede its segment (same halo
+    exchange, the warm-up output is discarded) -- no carry exchange, within 1e-10 of the unbroken
+    recurrence.  Filters that do not decay stay on one GPU.
 
 The arithmetic lives in the C ABI (sgpu_shard_channels / sgpu_shard_stream); the exchange uses
 torch.distributed point-to-point ops so the same code runs over NCCL (GPU) and gloo (CPU tests)."""
@@ -43,3 +47,12 @@ def exchange_halo(x_local, halo_out, rank: int, world: int, dist):
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     return halo_out
+
+
+def iir_segment(filt, x_local, halo, rank: int):
+    """Run this rank's segment of one long IIR stream: rank r > 0 first resets the filter and runs
+    it over the halo (the previous rank's last decay_length samples), discarding that output."""
+    if rank > 0:
+        filt.reset()
+        filt.execute_block(halo)
+    return filt.execute_block(x_local)

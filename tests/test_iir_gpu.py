@@ -338,3 +338,29 @@ def test_iir_normal_mode_orders(iir, W):
     k.set_state(st)
     y1, y2, y3 = (q.execute_block(x[:, 1000:]) for q in (g, h, k))
     assert np.array_equal(y1, y2) and np.array_equal(y1, y3) and np.array_equal(y1, got[:, 1000:])
+
+
+def test_decay_length_and_stream_segments(iir):
+    """sgpu_iir_decay_length + the segment recipe of solid_dsp_b200.sharding (multi-GPU long stream):
+    segments warmed up over the previous decay_length samples reproduce the unbroken recurrence."""
+    from solid_dsp_b200 import sharding
+    rng = np.random.default_rng(99)
+    ff, fb = _sections(8)
+    f = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder)
+    warm = f.decay_length()
+    assert warm % 32 == 0 and 256 <= warm <= 1024           # pole radii <= 0.95: a few hundred samples
+    r = 0.9999                                               # memory of ~2.3e5 samples: "does not decay"
+    g = iir.IIRFilter(f32_taps([1e-3, 2e-3, 1e-3]), f32_taps([1.0, -2 * r * np.cos(0.1), r * r]),
+                      iir.IIRFilterType.SecondOrder)
+    assert g.decay_length() == 0
+    assert iir.IIRFilter([0.5, 0.2], [1.0, -0.3], iir.IIRFilterType.Normal).decay_length() == 0
+    n = 90_000
+    x = rand_cf32(rng, n)
+    ref, _ = O.sos_cascade_fast(ff, fb, x)
+    world = 3
+    for rank in range(world):
+        first, count = sharding.shard_stream(n, 32, world, rank)
+        halo = x[first - warm:first] if rank else np.zeros(0, dtype=np.complex64)
+        seg = iir.IIRFilter(ff, fb, iir.IIRFilterType.SecondOrder)
+        y = sharding.iir_segment(seg, x[first:first + count], halo, rank)
+        assert nerr(y, ref[first:first + count]) <= TOL
