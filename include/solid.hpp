@@ -437,5 +437,59 @@ class InterpolatingIIRFilter : public IIRFilter {  // iir/interp.rs:5-273
 };
 }  // namespace interp
 }  // namespace iir
+
+// ------------------------------------------------------------------------------------------------
+namespace auto_correlator {
+
+// AutoCorrelator<C> -- filter/auto_correlator/mod.rs:24-216.  One object = `n_channels` independent
+// correlators (one reference object per channel), channel-major buffers.
+class AutoCorrelator {
+   public:
+    AutoCorrelator(size_t window_size, size_t delay, size_t n_channels = 1) {  // ::new :51
+        detail::check(sgpu_autocorr_create(window_size, delay, n_channels, &h_));
+    }
+    AutoCorrelator(const AutoCorrelator &o) { detail::check(sgpu_autocorr_clone(o.h_, &h_)); }
+    AutoCorrelator &operator=(const AutoCorrelator &) = delete;
+    ~AutoCorrelator() { sgpu_autocorr_destroy(h_); }
+
+    size_t window_size() const { return sgpu_autocorr_window_size(h_); }
+    size_t delay() const { return sgpu_autocorr_delay(h_); }
+    size_t channels() const { return sgpu_autocorr_channels(h_); }
+    void reset() { detail::check(sgpu_autocorr_reset(h_)); }  // :76
+    void push(cf32 sample) { write(std::vector<cf32>(channels(), sample)); }  // :99 (same sample on every channel)
+    void write(const std::vector<cf32> &samples) {  // :130
+        const size_t n = samples.size() / channels();
+        detail::check(sgpu_autocorr_write(h_, detail::fp(samples.data()), n, n, SGPU_HOST, nullptr));
+    }
+    std::vector<std::complex<double>> execute() {  // :165, one value per channel
+        std::vector<std::complex<double>> out(channels());
+        detail::check(sgpu_autocorr_execute(h_, reinterpret_cast<double *>(out.data())));
+        return out;
+    }
+    std::vector<cf32> execute_block(const std::vector<cf32> &samples) {  // :184
+        const size_t C = channels(), n = samples.size() / C;
+        std::vector<cf32> out(C * n);
+        size_t n_out = 0;
+        detail::check(sgpu_autocorr_execute_block(h_, detail::fp(samples.data()), n, n, detail::fp(out.data()),
+                                                  n ? n : 1, &n_out, SGPU_HOST, nullptr));
+        return out;
+    }
+    size_t execute_block_device(const cf32 *d_in, size_t n, size_t in_stride, cf32 *d_out, size_t out_stride,
+                                void *stream) {
+        size_t n_out = 0;
+        detail::check(sgpu_autocorr_execute_block(h_, detail::fp(d_in), n, in_stride, detail::fp(d_out), out_stride,
+                                                  &n_out, SGPU_DEVICE, stream));
+        return n_out;
+    }
+    std::vector<double> get_energy() {  // :214, one value per channel
+        std::vector<double> out(channels());
+        detail::check(sgpu_autocorr_get_energy(h_, out.data()));
+        return out;
+    }
+
+   private:
+    sgpu_autocorr *h_ = nullptr;
+};
+}  // namespace auto_correlator
 }  // namespace filter
 }  // namespace solid

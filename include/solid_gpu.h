@@ -78,6 +78,7 @@ typedef struct sgpu_fir sgpu_fir;       /* FIRFilter / DecimatingFIRFilter      
 typedef struct sgpu_interp sgpu_interp; /* InterpolatingFIRFilter (+ its PolyPhaseFilterBank) */
 typedef struct sgpu_iir sgpu_iir;       /* IIRFilter / Decimating- / InterpolatingIIRFilter   */
 typedef struct sgpu_dot sgpu_dot;       /* DotProduct                              */
+typedef struct sgpu_autocorr sgpu_autocorr; /* AutoCorrelator                      */
 
 /* ---- library ------------------------------------------------------------------------ */
 int sgpu_abi_version(void);
@@ -213,6 +214,34 @@ int sgpu_iir_set_mode(sgpu_iir *f, int mode);
  * preceded by that many samples of the previous segment: reset, execute_block(halo) with the output
  * discarded, then execute_block(segment).  No counterpart in the reference (it is single-threaded). */
 int sgpu_iir_decay_length(sgpu_iir *f, size_t *n);
+
+/* ---- AutoCorrelator ------------------------------------------------------------------
+ * filter/auto_correlator/mod.rs: new(window_size, delay) :51-62, push :99-111, write :130-141,
+ * execute :165-172, execute_block :184-191, get_energy :214-216, reset :76-85.
+ * With W = window_size, d = delay and the reference's Window(capacity, delay) semantics
+ * (window/mod.rs:17-34,44-51,63-71: the delayed window's tail is never written),
+ *     r[n] = sum_{i < W-d} x[n-i] * conj(x[n-d-i])      (0 for d >= W)
+ *     energy = sum_{i < W} |x[n-i]|^2
+ * One handle = n_channels independent correlators (one reference object each), channel-major
+ * buffers like every other handle.  execute_block: one output per input.  execute / get_energy
+ * report the current window: [n_channels] complex doubles / doubles in HOST memory.
+ * State = the last window_size samples per channel, oldest first. */
+int sgpu_autocorr_create(size_t window_size, size_t delay, size_t n_channels, sgpu_autocorr **out);
+int sgpu_autocorr_destroy(sgpu_autocorr *f);
+int sgpu_autocorr_clone(const sgpu_autocorr *f, sgpu_autocorr **out);
+size_t sgpu_autocorr_window_size(const sgpu_autocorr *f);
+size_t sgpu_autocorr_delay(const sgpu_autocorr *f);
+size_t sgpu_autocorr_channels(const sgpu_autocorr *f);
+int sgpu_autocorr_execute_block(sgpu_autocorr *f, const float *in, size_t n_in, size_t in_stride,
+                                float *out, size_t out_stride, size_t *n_out, sgpu_mem mem,
+                                void *stream);
+int sgpu_autocorr_write(sgpu_autocorr *f, const float *in, size_t n_in, size_t in_stride,
+                        sgpu_mem mem, void *stream);
+int sgpu_autocorr_execute(sgpu_autocorr *f, double *out);
+int sgpu_autocorr_get_energy(sgpu_autocorr *f, double *out);
+int sgpu_autocorr_reset(sgpu_autocorr *f);
+int sgpu_autocorr_get_state(sgpu_autocorr *f, float *state);
+int sgpu_autocorr_set_state(sgpu_autocorr *f, const float *state);
 
 /* ---- DotProduct ----------------------------------------------------------------------
  * sum_{i < min(len_c, len_x)} c[i] * x[i], c stored FORWARD or REVERSED

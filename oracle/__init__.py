@@ -102,6 +102,13 @@ def lib(native: bool = False):
     sig("so_iir_free", None, vp)
     sig("so_iir_execute_block", c_size, vp, c_dp, c_size, c_dp, c_size)
     sig("so_sos_cascade_fast", None, c_dp, c_dp, c_size, c_dp, c_dp, c_size, c_dp)
+    sig("so_autocorr_new", vp, c_size, c_size)
+    sig("so_autocorr_free", None, vp)
+    sig("so_autocorr_push", None, vp, C.c_double, C.c_double)
+    sig("so_autocorr_execute", None, vp, c_dp)
+    sig("so_autocorr_execute_block", c_size, vp, c_dp, c_size, c_dp)
+    sig("so_autocorr_get_energy", C.c_double, vp)
+    sig("so_autocorr_fast", None, c_size, c_size, c_dp, c_size, c_dp, c_size, c_dp)
     sig("so_sinc", C.c_double, C.c_double)
     sig("so_lngamma", C.c_double, C.c_double)
     sig("so_gamma", C.c_double, C.c_double)
@@ -420,7 +427,57 @@ class InterpolatingIIRFilter(IIRFilter):
         super().__init__(ff, fb, iirtype, 2, interpolation)
 
 
+class AutoCorrelator:
+    """filter/auto_correlator/mod.rs:24-216 (structural mirror, incl. the Window delay quirk)"""
+
+    def __init__(self, window_size, delay, native=False):
+        self._L = lib(native)
+        self._h = self._L.so_autocorr_new(window_size, delay)
+        if not self._h:
+            raise OracleError(-1)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.so_autocorr_free(self._h)
+            self._h = None
+
+    def push(self, sample):
+        z = complex(sample)
+        self._L.so_autocorr_push(self._h, z.real, z.imag)
+
+    def write(self, samples):
+        for z in np.asarray(samples).ravel():
+            self.push(z)
+
+    def execute(self):
+        out = np.zeros(2)
+        self._L.so_autocorr_execute(self._h, _p(out))
+        return complex(out[0], out[1])
+
+    def execute_block(self, samples):
+        x, xv = _cx(samples)
+        out = np.zeros(max(len(x), 1), dtype=np.complex128)
+        n = self._L.so_autocorr_execute_block(self._h, _p(xv), len(x), _p(out.view(np.float64)))
+        return out[:n].copy()
+
+    def get_energy(self):
+        return self._L.so_autocorr_get_energy(self._h)
+
+
 # ----------------------------------------------------------------------------- closed forms
+def autocorr_fast(window_size, delay, x, hist=None):
+    """out[n] = sum_{i < W-d} x[n-i] conj(x[n-d-i]); hist = samples preceding x[0], oldest first"""
+    x, xv = _cx(x)
+    out = np.zeros(max(len(x), 1), dtype=np.complex128)
+    hv, nh = None, 0
+    if hist is not None and len(hist):
+        h, hv = _cx(hist)
+        nh = len(h)
+    lib().so_autocorr_fast(window_size, delay, _p(hv) if hv is not None else None, nh, _p(xv), len(x),
+                           _p(out.view(np.float64)))
+    return out[:len(x)].copy()
+
+
 def fir_fast(coefs, x, scale=1.0, decimation=0, count0=0, hist=None):
     c, cc, cv = _coefs(coefs)
     x, xv = _cx(x)

@@ -609,6 +609,92 @@ SO_API void so_sos_cascade_fast(const double *ff, const double *fb, size_t nsec,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* AutoCorrelator<C> -- filter/auto_correlator/mod.rs:24-35,51-62,99-111,165-191,214-216  */
+/* Structural mirror.  Note what Window(window_size, delay) really does (window/mod.rs:17-34,   */
+/* 44-51,63-71): the buffer has window_size + delay elements, push() shifts only the first      */
+/* window_size - 1 and to_vec() copies window_size elements starting at +delay, so the delayed  */
+/* window holds conj(x[n-delay-i]) for i < window_size - delay and ZEROS after that:            */
+/*   execute() = sum_{i < window_size - delay} x[n-i] * conj(x[n-delay-i])   (0 if delay >= size) */
+typedef struct {
+    size_t window_size, delay;
+    so_window window, window_with_delay;
+    double *energy_buffer;
+    double energy_sum;
+    size_t energy_index;
+} so_autocorr;
+
+SO_API so_autocorr *so_autocorr_new(size_t window_size, size_t delay) {
+    if (window_size == 0) return NULL; /* Window::new asserts capacity > 0 */
+    so_autocorr *a = (so_autocorr *)calloc(1, sizeof(so_autocorr));
+    a->window_size = window_size;
+    a->delay = delay;
+    win_init(&a->window, window_size, 0);
+    win_init(&a->window_with_delay, window_size, delay);
+    a->energy_buffer = (double *)calloc(window_size, sizeof(double));
+    return a;
+}
+SO_API void so_autocorr_free(so_autocorr *a) {
+    if (!a) return;
+    win_free(&a->window);
+    win_free(&a->window_with_delay);
+    free(a->energy_buffer);
+    free(a);
+}
+/* push -- auto_correlator/mod.rs:99-111 */
+SO_API void so_autocorr_push(so_autocorr *a, double re, double im) {
+    cplx s = { re, im }, sc = { re, -im };
+    win_push(&a->window, s);
+    win_push(&a->window_with_delay, sc);
+    double e2 = c_mul(s, sc).re;
+    a->energy_sum -= a->energy_buffer[a->energy_index];
+    a->energy_sum += e2;
+    a->energy_buffer[a->energy_index] = e2;
+    a->energy_index = (a->energy_index + 1) % a->window_size;
+}
+/* execute -- auto_correlator/mod.rs:165-172: two to_vec copies, zip, map, sum (from zero) */
+SO_API void so_autocorr_execute(const so_autocorr *a, double *out2) {
+    cplx *x = win_to_vec(&a->window), *y = win_to_vec(&a->window_with_delay);
+    cplx sum = { 0.0, 0.0 };
+    for (size_t i = 0; i < a->window_size; i++) sum = c_add(sum, c_mul(x[i], y[i]));
+    free(x);
+    free(y);
+    out2[0] = sum.re;
+    out2[1] = sum.im;
+}
+/* execute_block -- auto_correlator/mod.rs:184-191 */
+SO_API size_t so_autocorr_execute_block(so_autocorr *a, const double *x, size_t n, double *out) {
+    for (size_t k = 0; k < n; k++) {
+        so_autocorr_push(a, x[2 * k], x[2 * k + 1]);
+        so_autocorr_execute(a, out + 2 * k);
+    }
+    return n;
+}
+SO_API double so_autocorr_get_energy(const so_autocorr *a) { return a->energy_sum; }
+
+/* closed form, same accumulation order (i ascending from the newest sample), zero history:    */
+/* out[n] = sum_{i < W-d} x[n-i] * conj(x[n-d-i]); the terms with i >= W-d multiply by the     */
+/* window's zero tail and are added as exact zeros, which cannot change an f64 sum.             */
+SO_API void so_autocorr_fast(size_t window_size, size_t delay, const double *hist, size_t nhist,
+                             const double *x, size_t n, double *out) {
+    /* hist: the nhist samples preceding x[0], oldest first (may be NULL) */
+    const size_t wd = delay < window_size ? window_size - delay : 0;
+    for (size_t k = 0; k < n; k++) {
+        cplx sum = { 0.0, 0.0 };
+        for (size_t i = 0; i < wd; i++) {
+            ptrdiff_t ia = (ptrdiff_t)k - (ptrdiff_t)i, ib = ia - (ptrdiff_t)delay;
+            cplx xa = { 0.0, 0.0 }, xb = { 0.0, 0.0 };
+            if (ia >= 0) { xa.re = x[2 * ia]; xa.im = x[2 * ia + 1]; }
+            else if ((ptrdiff_t)nhist + ia >= 0) { xa.re = hist[2 * (nhist + ia)]; xa.im = hist[2 * (nhist + ia) + 1]; }
+            if (ib >= 0) { xb.re = x[2 * ib]; xb.im = -x[2 * ib + 1]; }
+            else if ((ptrdiff_t)nhist + ib >= 0) { xb.re = hist[2 * (nhist + ib)]; xb.im = -hist[2 * (nhist + ib) + 1]; }
+            sum = c_add(sum, c_mul(xa, xb));
+        }
+        out[2 * k] = sum.re;
+        out[2 * k + 1] = sum.im;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Design helpers needed to produce identical taps on both sides.                        */
 /* math/mod.rs:17-27 */
 SO_API double so_sinc(double x) {

@@ -40,6 +40,7 @@ pub const SGPU_IIR_INTERPOLATING: c_int = 2;
 #[repr(C)] pub struct sgpu_interp { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_iir { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_dot { _private: [u8; 0] }
+#[repr(C)] pub struct sgpu_autocorr { _private: [u8; 0] }
 
 extern "C" {
     pub fn sgpu_abi_version() -> c_int;
@@ -113,6 +114,24 @@ extern "C" {
     pub fn sgpu_iir_state_len(f: *const sgpu_iir) -> size_t;
     pub fn sgpu_iir_set_mode(f: *mut sgpu_iir, mode: c_int) -> c_int;
     pub fn sgpu_iir_decay_length(f: *mut sgpu_iir, n: *mut usize) -> c_int;
+
+    pub fn sgpu_autocorr_create(window_size: size_t, delay: size_t, n_channels: size_t,
+                                out: *mut *mut sgpu_autocorr) -> c_int;
+    pub fn sgpu_autocorr_destroy(f: *mut sgpu_autocorr) -> c_int;
+    pub fn sgpu_autocorr_clone(f: *const sgpu_autocorr, out: *mut *mut sgpu_autocorr) -> c_int;
+    pub fn sgpu_autocorr_window_size(f: *const sgpu_autocorr) -> size_t;
+    pub fn sgpu_autocorr_delay(f: *const sgpu_autocorr) -> size_t;
+    pub fn sgpu_autocorr_channels(f: *const sgpu_autocorr) -> size_t;
+    pub fn sgpu_autocorr_execute_block(f: *mut sgpu_autocorr, input: *const c_float, n_in: size_t, in_stride: size_t,
+                                       out: *mut c_float, out_stride: size_t, n_out: *mut size_t, mem: c_int,
+                                       stream: *mut c_void) -> c_int;
+    pub fn sgpu_autocorr_write(f: *mut sgpu_autocorr, input: *const c_float, n_in: size_t, in_stride: size_t,
+                               mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn sgpu_autocorr_execute(f: *mut sgpu_autocorr, out: *mut c_double) -> c_int;
+    pub fn sgpu_autocorr_get_energy(f: *mut sgpu_autocorr, out: *mut c_double) -> c_int;
+    pub fn sgpu_autocorr_reset(f: *mut sgpu_autocorr) -> c_int;
+    pub fn sgpu_autocorr_get_state(f: *mut sgpu_autocorr, state: *mut c_float) -> c_int;
+    pub fn sgpu_autocorr_set_state(f: *mut sgpu_autocorr, state: *const c_float) -> c_int;
 
     pub fn sgpu_dot_create(coefs: *const c_double, n: size_t, kind: c_int, dir: c_int,
                            out: *mut *mut sgpu_dot) -> c_int;

@@ -337,4 +337,76 @@ pub mod filter {
             }
         }
     }
+    pub mod auto_correlator {
+        //! reference: src/filter/auto_correlator/mod.rs
+        use num::complex::Complex;
+        use solid_gpu_sys as sys;
+        use std::error::Error;
+        use std::fmt;
+        use std::ptr;
+
+        /// AutoCorrelator<C> -- auto_correlator/mod.rs:24-35 (the f32-sample instantiation)
+        pub struct AutoCorrelator { h: *mut sys::sgpu_autocorr }
+
+        impl AutoCorrelator {
+            /// AutoCorrelator::new -- auto_correlator/mod.rs:51
+            pub fn new(window_size: usize, delay: usize) -> Self {
+                let mut h = ptr::null_mut();
+                let st = unsafe { sys::sgpu_autocorr_create(window_size, delay, 1, &mut h) };
+                assert_eq!(st, sys::SGPU_OK, "sgpu_autocorr_create failed: {}", crate::last_error());
+                AutoCorrelator { h }
+            }
+            /// :76
+            pub fn reset(&mut self) { unsafe { sys::sgpu_autocorr_reset(self.h) }; }
+            /// :99
+            pub fn push(&mut self, sample: Complex<f32>) { let _ = self.write(&[sample]); }
+            /// :130
+            pub fn write(&mut self, samples: &[Complex<f32>]) -> Result<(), Box<dyn Error>> {
+                let st = unsafe { sys::sgpu_autocorr_write(self.h, samples.as_ptr() as *const f32, samples.len(), samples.len(),
+                                                           sys::SGPU_HOST, ptr::null_mut()) };
+                assert_eq!(st, sys::SGPU_OK, "sgpu_autocorr_write failed: {}", crate::last_error());
+                Ok(())
+            }
+            /// :165
+            pub fn execute(&self) -> Complex<f32> {
+                let mut out = [0.0f64; 2];
+                unsafe { sys::sgpu_autocorr_execute(self.h, out.as_mut_ptr()) };
+                Complex::new(out[0] as f32, out[1] as f32)
+            }
+            /// :184 -- one output per input
+            pub fn execute_block(&mut self, samples: &[Complex<f32>]) -> Vec<Complex<f32>> {
+                let mut out = vec![Complex::new(0.0f32, 0.0f32); samples.len()];
+                let mut n_out = 0usize;
+                let st = unsafe { sys::sgpu_autocorr_execute_block(self.h, samples.as_ptr() as *const f32, samples.len(), samples.len(),
+                                                                   out.as_mut_ptr() as *mut f32, out.len().max(1), &mut n_out,
+                                                                   sys::SGPU_HOST, ptr::null_mut()) };
+                assert_eq!(st, sys::SGPU_OK, "sgpu_autocorr_execute_block failed: {}", crate::last_error());
+                out
+            }
+            /// :214
+            pub fn get_energy(&self) -> f64 {
+                let mut e = 0.0f64;
+                unsafe { sys::sgpu_autocorr_get_energy(self.h, &mut e) };
+                e
+            }
+        }
+        impl Clone for AutoCorrelator {
+            fn clone(&self) -> Self {
+                let mut h = ptr::null_mut();
+                let st = unsafe { sys::sgpu_autocorr_clone(self.h, &mut h) };
+                assert_eq!(st, sys::SGPU_OK);
+                AutoCorrelator { h }
+            }
+        }
+        impl Drop for AutoCorrelator {
+            fn drop(&mut self) { unsafe { sys::sgpu_autocorr_destroy(self.h) }; }
+        }
+        impl fmt::Display for AutoCorrelator {
+            /// auto_correlator/mod.rs:219-228
+            fn fmt(&self, f: &mut fmt::Formatter) -> fmt::Result {
+                let (w, d) = unsafe { (sys::sgpu_autocorr_window_size(self.h), sys::sgpu_autocorr_delay(self.h)) };
+                write!(f, "AutoCorrelator<f32> [Size={}] [Delay={}] [Energy={}]", w, d, self.get_energy())
+            }
+        }
+    }
 }

@@ -104,6 +104,19 @@ PROTOTYPES = {
     "sgpu_iir_state_len": (c_size, [vp]),
     "sgpu_iir_set_mode": (C.c_int, [vp, C.c_int]),
     "sgpu_iir_decay_length": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "sgpu_autocorr_create": (C.c_int, [c_size, c_size, c_size, vpp]),
+    "sgpu_autocorr_destroy": (C.c_int, [vp]),
+    "sgpu_autocorr_clone": (C.c_int, [vp, vpp]),
+    "sgpu_autocorr_window_size": (c_size, [vp]),
+    "sgpu_autocorr_delay": (c_size, [vp]),
+    "sgpu_autocorr_channels": (c_size, [vp]),
+    "sgpu_autocorr_execute_block": (C.c_int, [vp, vp, c_size, c_size, vp, c_size, c_sizep, C.c_int, vp]),
+    "sgpu_autocorr_write": (C.c_int, [vp, vp, c_size, c_size, C.c_int, vp]),
+    "sgpu_autocorr_execute": (C.c_int, [vp, c_dp]),
+    "sgpu_autocorr_get_energy": (C.c_int, [vp, c_dp]),
+    "sgpu_autocorr_reset": (C.c_int, [vp]),
+    "sgpu_autocorr_get_state": (C.c_int, [vp, vp]),
+    "sgpu_autocorr_set_state": (C.c_int, [vp, vp]),
     "sgpu_dot_create": (C.c_int, [c_dp, c_size, C.c_int, C.c_int, vpp]),
     "sgpu_dot_destroy": (C.c_int, [vp]),
     "sgpu_dot_len": (c_size, [vp]),

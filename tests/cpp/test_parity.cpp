@@ -16,6 +16,8 @@ size_t so_firinterp_fast(const double *coefs, size_t T, int coef_complex, size_t
                          const double *x, size_t n, double *out);
 void so_sos_cascade_fast(const double *ff, const double *fb, size_t nsec, double *state, const double *x, size_t n,
                          double *out);
+void so_autocorr_fast(size_t window_size, size_t delay, const double *hist, size_t nhist, const double *x, size_t n,
+                      double *out);
 int so_firdes_kaiser(size_t len, double fc, double as, double mu, double *h);
 int so_pll_active_lag(double w, double zeta, double k, double *num, double *den);
 }
@@ -164,6 +166,25 @@ int main() {
             worst = std::max(worst, nerr(yc, ref, n));
         }
         EXPECT(worst <= TOL, "IIR 8 sections x 64 channels vs oracle");
+    }
+    // AutoCorrelator: reference doc-test (auto_correlator/mod.rs:199-211) and a random stream vs the oracle
+    {
+        using solid::filter::auto_correlator::AutoCorrelator;
+        std::vector<cf32> x(500);
+        for (int k = -250; k < 250; ++k) x[k + 250] = cf32((float)(std::cos((double)k) * 0.05), (float)(std::sin((double)k) * 0.05));
+        AutoCorrelator a(5, 10);
+        auto out = a.execute_block(x);
+        bool zeros = true;
+        for (auto v : out) zeros = zeros && v == cf32(0.f, 0.f);
+        EXPECT(zeros && std::round(a.get_energy()[0] * 10000.0) == 125.0, "AutoCorrelator doc-test: energy 125, delay >= window");
+        const size_t n = 5000;
+        auto xr = rand_cf32(gen, n);
+        AutoCorrelator b(48, 16);
+        auto y = b.execute_block(xr);
+        auto xd = widen(xr);
+        std::vector<double> ref(2 * n);
+        so_autocorr_fast(48, 16, nullptr, 0, xd.data(), n, ref.data());
+        EXPECT(nerr(y, ref, n) <= TOL, "AutoCorrelator(48, 16) vs oracle");
     }
     std::printf("%s (%d failure%s), kernels launched: %llu\n", failures ? "FAILED" : "PASSED", failures,
                 failures == 1 ? "" : "s", (unsigned long long)sgpu_launch_count());

@@ -232,3 +232,27 @@ def test_fast_equals_structural_random():
     a = f.execute_block(x[6:])
     b = O.fir_fast(h, x[6:], 1.0, 4, count0=2, hist=np.concatenate([np.zeros(63 - 6), x[:6]])[-63:])
     assert np.array_equal(a, b)
+
+
+def test_auto_correlator(ref):
+    """auto_correlator/mod.rs:199-211 -- the reference's only numeric assertion for this type -- and
+    the Window(capacity, delay) quirk that the restatement must carry: the delayed window's tail is
+    never written (window/mod.rs:17-71), so only W-d lags contribute and delay >= window gives 0."""
+    g = ref["auto_correlator_get_energy"]
+    x = np.array([complex(np.cos(float(k)) * 0.05, np.sin(float(k)) * 0.05) for k in range(-250, 250)])
+    a = O.AutoCorrelator(g["construct"]["window_size"], g["construct"]["delay"])
+    out = a.execute_block(x)
+    assert round(a.get_energy() * 10000.0) == g["expect_rounded"]
+    assert np.all(out == 0)                                   # delay (10) >= window (5)
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=200) + 1j * rng.normal(size=200)
+    for W, d in [(1, 0), (7, 0), (10, 5), (16, 15), (16, 16)]:
+        s = O.AutoCorrelator(W, d).execute_block(y)
+        assert np.array_equal(s, O.autocorr_fast(W, d, y))   # closed form == structural, bit for bit
+        n = 150                                                # hand check of one output
+        want = sum(y[n - i] * np.conj(y[n - d - i]) for i in range(max(W - d, 0)))
+        assert abs(s[n] - want) <= 1e-12 * max(1.0, abs(want))
+    # split calls == one call (the windows carry the state)
+    b = O.AutoCorrelator(10, 5)
+    two = np.concatenate([b.execute_block(y[:77]), b.execute_block(y[77:])])
+    assert np.array_equal(two, O.AutoCorrelator(10, 5).execute_block(y))

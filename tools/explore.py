@@ -134,6 +134,16 @@ def iirwrap(Cn=65536, logn=12, factor=4, nsec=8):
                       "Gsamp_out_s": Cn * n / best / 1e6}))
 
 
+def autocorr(W=64, d=16, Cn=1024, logn=20):
+    from solid_dsp_b200.filter.auto_correlator import AutoCorrelator
+    n = 1 << logn
+    x = torch.randn((Cn, n), dtype=torch.complex64, device="cuda")
+    f = AutoCorrelator(W, d, n_channels=Cn)
+    best, med = ev_time(lambda: f.execute_block(x))
+    print(json.dumps({"kernel": "autocorr", "W": W, "d": d, "C": Cn, "n": n, "best_ms": best,
+                      "Gsamp_s": Cn * n / best / 1e6, "GBps": Cn * n * 16 / best / 1e6}))
+
+
 def iirscan(logn=26, nsec=8):
     from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
     from solid_dsp_b200.filter.iirdes import stable_lowpass_sections
