@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the filtering hot path on B200, one JSON line per run.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir|decim|interp|iir_batch|iir_scan]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir|decim|interp|iir_batch|iir_scan|autocorr]
     python bench.py --impl reference ...        # the reference's CPU path (restated oracle) on host cores
     torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU)
 
@@ -49,7 +49,11 @@ WORKLOADS = {
                       flop_per_unit=144.0, bytes_per_unit=16.0, unit="sample"),
     "iir_scan": dict(desc="BASELINE configs[4b]: 8-section biquad cascade, one stream of 2^28 samples (chunked scan)",
                      flop_per_unit=144.0, bytes_per_unit=16.0, unit="sample"),
+    # widening, not a BASELINE config: 8 flop per lag product + 2 complex adds per output
+    "autocorr": dict(desc="SURVEY 8f: AutoCorrelator window 64, delay 16, 1024 channels x 2^20 samples",
+                     flop_per_unit=16.0, bytes_per_unit=16.0, unit="sample"),
 }
+AUTOCORR_SHAPE = (64, 16)
 
 
 def f32_taps(h):
@@ -64,6 +68,8 @@ def workload_taps(name):
         return f32_taps(firdes.firdes_kaiser(256, 0.5 / 8 * 0.9, 80.0, 0.0))
     if name == "interp":
         return f32_taps(firdes.firdes_kaiser(128, 0.5 / 4 * 0.9, 80.0, 0.0))
+    if name == "autocorr":
+        return AUTOCORR_SHAPE
     return iirdes.stable_lowpass_sections(8)
 
 
@@ -153,6 +159,15 @@ def cpu_reference_path(name: str, n_threads: int, budget_s: float, native: bool 
             O.run_units("interp", x, n_in, n_units, n_in, out, n_in * 4 + 1, n_threads, coefs=taps, interpolation=4,
                         native=native)
             return time.perf_counter() - t0, n_units * n_in * 4
+        if name == "autocorr":
+            # structural oracle objects, one per unit, on a thread pool (ctypes releases the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+            x = rng.uniform(-1, 1, (n_units, n_in)) + 1j * rng.uniform(-1, 1, (n_units, n_in))
+            objs = [O.AutoCorrelator(*taps, native=native) for _ in range(n_units)]
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max(n_threads, 1)) as ex:
+                list(ex.map(lambda i: objs[i].execute_block(x[i]), range(n_units)))
+            return time.perf_counter() - t0, n_units * n_in
         ff, fb = taps
         x = rng.uniform(-1, 1, n_units * n_in) + 1j * rng.uniform(-1, 1, n_units * n_in)
         out = np.zeros(n_units * n_in, dtype=np.complex128)
@@ -263,8 +278,8 @@ def run_gpu_arm(args):
             filt.write(halo_prev)
             return filt.execute_block(x)
     else:
-        chans = {"decim": 4096, "interp": 1024, "iir_batch": 65536, "iir_scan": 1}[name]
-        n_per = 1 << {"decim": 20, "interp": 20, "iir_batch": 14, "iir_scan": 28}[name]
+        chans = {"decim": 4096, "interp": 1024, "iir_batch": 65536, "iir_scan": 1, "autocorr": 1024}[name]
+        n_per = 1 << {"decim": 20, "interp": 20, "iir_batch": 14, "iir_scan": 28, "autocorr": 20}[name]
         if args.log2_samples != 30:
             n_per = 1 << args.log2_samples
         if name == "iir_scan":
@@ -281,6 +296,9 @@ def run_gpu_arm(args):
             filt = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
         elif name == "interp":
             filt = InterpolatingFIRFilter(taps, 4, n_channels=c_loc)
+        elif name == "autocorr":
+            from solid_dsp_b200.filter.auto_correlator import AutoCorrelator
+            filt = AutoCorrelator(*taps, n_channels=c_loc)
         else:
             filt = IIRFilter(taps[0], taps[1], IIRFilterType.SecondOrder, n_channels=c_loc)
         shape_desc = {"channels": chans, "samples_per_channel": n_per}
@@ -387,7 +405,8 @@ def run_gpu_arm(args):
             "traffic_detail": traffic_detail,
             "kernel": {"fir": "fir_decim_kernel<R=16,M1>", "decim": "fir_decim_kernel<R=16>",
                        "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
-                       "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)"}[name],
+                       "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)",
+                       "autocorr": "autocorr_kernel"}[name],
             "kernel_ms_per_launch": ms_kernel,
             "algorithmic": {"flop_per_unit": W["flop_per_unit"], "bytes_per_unit": W["bytes_per_unit"], "unit": W["unit"],
                             "units_per_launch": units_rank},
@@ -467,6 +486,18 @@ def spot_check(name, taps, filt, x, y, halo_prev):
                 e = nerr(got, ref)
                 windows.append([int(c), start, e])
                 worst = max(worst, e)
+    elif name == "autocorr":
+        # outputs further than window_size into the call depend on this call's inputs only
+        W, d = taps
+        n = x.shape[1]
+        for c in rng.integers(0, x.shape[0], 3):
+            for start in (0, n // 2, n - (1 << 13)):
+                xs = x[int(c), start:start + (1 << 13)].cpu().numpy()
+                ref = O.autocorr_fast(W, d, xs)[W:]
+                got = y[int(c), start + W:start + W + len(ref)].cpu().numpy()
+                e = nerr(got, ref)
+                windows.append([int(c), start, e])
+                worst = max(worst, e)
     else:
         # the timed handle is streaming (state persists over steps): check a fresh handle instead
         from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
@@ -509,6 +540,10 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
     elif name == "interp":
         f = InterpolatingFIRFilter(taps, 4, n_channels=c_loc)
         n_out = n_in * 4
+    elif name == "autocorr":
+        from solid_dsp_b200.filter.auto_correlator import AutoCorrelator
+        f = AutoCorrelator(*taps, n_channels=c_loc)
+        n_out = n_in
     else:
         f = IIRFilter(taps[0], taps[1], IIRFilterType.SecondOrder, n_channels=c_loc)
         n_out = n_in
@@ -516,7 +551,8 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
     hout = torch.empty((c_loc, n_out), dtype=torch.complex64, pin_memory=True)
     hin.copy_(x.reshape(c_loc, n_in))
     fn = {"fir": _ffi.lib.sgpu_fir_execute_block, "decim": _ffi.lib.sgpu_fir_execute_block,
-          "interp": _ffi.lib.sgpu_interp_execute_block}.get(name, _ffi.lib.sgpu_iir_execute_block)
+          "interp": _ffi.lib.sgpu_interp_execute_block,
+          "autocorr": _ffi.lib.sgpu_autocorr_execute_block}.get(name, _ffi.lib.sgpu_iir_execute_block)
     got = _ffi.c_size()
     stream = torch.cuda.current_stream(dev).cuda_stream
 

@@ -28,7 +28,7 @@ def build(native: bool = False, force: bool = False) -> Path:
     out = _HERE / "_build" / ("libsolid_oracle_native.so" if native else "libsolid_oracle.so")
     if out.exists() and not force and out.stat().st_mtime >= _SRC.stat().st_mtime and not native:
         return out
-    if native and out.exists() and not force:
+    if native and out.exists() and not force and out.stat().st_mtime >= _SRC.stat().st_mtime:
         stamp = out.with_suffix(".host")
         if stamp.exists() and stamp.read_text() == _host_id():
             return out

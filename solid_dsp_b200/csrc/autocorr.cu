@@ -15,8 +15,8 @@
 // p[j] = x[j] conj(x[j-d]) is formed ONCE, and a thread then slides the window sum over its R = 8
 // consecutive outputs: r[n+1] = r[n] + p[n+1] - p[n+1-Wd], restarted from a direct sum (through sums
 // of 8 for long windows) every 8 outputs so that rounding never accumulates over more than 7 updates.
-// p and the staged outputs live in a skewed layout (one pad slot per 8) so that lanes 8 samples apart
-// hit different banks.  Runs are aligned to the absolute stream position, which makes the results
+// p lives in a skewed layout (one pad slot per 8) so that lanes 8 samples apart hit different banks; the
+// samples arrive by 8-byte cp.async and a run's 8 outputs leave straight from registers.  Runs are aligned to the absolute stream position, which makes the results
 // independent of how the stream is cut into calls (bit for bit).
 #include <algorithm>
 
@@ -37,6 +37,7 @@ struct AcArgs {
     long long in_stride, out_stride, n_in;
     int W, d, Wd, HW;
     int shift;  // samples pushed before this call, mod 8
+    int vec_out;  // out base 16-byte aligned and out_stride even
 };
 
 __device__ __forceinline__ int skew(int j) { return j + (j >> 3); }
@@ -55,9 +56,8 @@ __global__ void __launch_bounds__(kNT) autocorr_kernel(const AcArgs a) {
     const int NX = kTileOut + H;              // staged samples: xs[k] = x[n_base - H + k]
     const int NP = kTileOut + a.Wd - 1;       // lag products:   p[k]  = product at n_base - (Wd-1) + k
     const int NB = NP / 8;                    // whole blocks of 8 lag products
-    float2 *xs = sm;  // later reused for the skewed output tile: at least kTileOut * 9/8 slots
-    const int XS = max(NX, kTileOut + kTileOut / 8 + 1);
-    float2 *ps = sm + ((XS + 1) & ~1);
+    float2 *xs = sm;
+    float2 *ps = sm + ((NX + 1) & ~1);
     float2 *bs = ps + ((NP + NP / 8 + 2) & ~1);
     // Tiles are aligned to the ABSOLUTE stream position (a.shift = samples pushed so far mod 8), so
     // the association order of every output's sum -- and with it the rounding -- does not depend on
@@ -66,7 +66,16 @@ __global__ void __launch_bounds__(kNT) autocorr_kernel(const AcArgs a) {
     const long long n_base = (long long)blockIdx.x * kTileOut - a.shift;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ hist = a.hist + (long long)ch * a.HW;
-    for (int k = tid; k < NX; k += kNT) xs[k] = ac_fetch(x, hist, n_base - H + k, a.n_in, a.HW);
+    if (n_base - H >= 0 && n_base + kTileOut <= a.n_in) {  // interior tile: straight 8-byte LDGSTS
+        const float2 *src = x + (n_base - H);
+        for (int k = tid; k < NX; k += kNT) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + k);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + k) : "memory");
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else {
+        for (int k = tid; k < NX; k += kNT) xs[k] = ac_fetch(x, hist, n_base - H + k, a.n_in, a.HW);
+    }
     __syncthreads();
     // p at stream position n uses x[n] and x[n-d]; position of p[k] is n_base - (Wd-1) + k, i.e.
     // xs index k + H - (Wd-1) = k + d   (H - Wd + 1 = d)  and, d earlier, xs index k
@@ -124,14 +133,22 @@ __global__ void __launch_bounds__(kNT) autocorr_kernel(const AcArgs a) {
 #pragma unroll
         for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
     }
-    // stage the outputs (xs is free) and store them coalesced
+    // the run's 8 outputs are 64 contiguous bytes: straight from registers (the L2 merges the sectors)
+    const long long n0 = n_base + k0;
+    float2 *__restrict__ out = a.out + (long long)ch * a.out_stride + n0;
+    if (n0 >= 0 && n0 + kR <= a.n_in) {
+        if (a.vec_out && (a.shift & 1) == 0) {
 #pragma unroll
-    for (int r = 0; r < kR; ++r) xs[skew(k0 + r)] = y[r];
-    __syncthreads();
-    float2 *__restrict__ out = a.out + (long long)ch * a.out_stride;
-    for (int k = tid; k < kTileOut; k += kNT) {
-        const long long n = n_base + k;
-        if (n >= 0 && n < a.n_in) out[n] = xs[skew(k)];
+            for (int r = 0; r < kR; r += 2)
+                *reinterpret_cast<float4 *>(out + r) = make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kR; ++r) out[r] = y[r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+            if (n0 + r >= 0 && n0 + r < a.n_in) out[r] = y[r];
     }
 }
 
@@ -198,7 +215,8 @@ int ac_launch(sgpu_autocorr *f, const float2 *d_in, long long n_in, long long is
     a.HW = (int)f->W + kHistExtra;
     if (a.Wd == 0) a.d = 0;  // delay >= window: all outputs are zero; keep the index math in range
     a.shift = (int)(f->pos & 7);
-    const size_t nx = std::max<size_t>(kTileOut + f->W - 1, kTileOut + kTileOut / 8 + 1), np = kTileOut + (size_t)a.Wd;
+    a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (ostr % 2 == 0);
+    const size_t nx = kTileOut + f->W - 1, np = kTileOut + (size_t)a.Wd;
     const size_t smem = (((nx + 1) & ~(size_t)1) + ((np + np / 8 + 4) & ~(size_t)1) + np / 8 + 2) * sizeof(float2);
     if (d_out) {
         SGPU_CUDA(cudaFuncSetAttribute(autocorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
