@@ -317,7 +317,7 @@ def test_interp_complex_taps(fir, L):
 
 
 # ------------------------------------------------------------------ warp-private tile kernels (fir_walk.cuh)
-@pytest.mark.parametrize("T", [33, 64, 512])
+@pytest.mark.parametrize("T", [33, 64, 512, 3000, 9000])
 def test_fir_many_warp_tiles(fir, T):
     """Streams that span several warps, blocks and TPW groups of fir_warp_kernel, ragged end, split
     calls whose boundaries fall inside tiles; two channels with a row stride."""
