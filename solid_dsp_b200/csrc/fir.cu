@@ -651,6 +651,39 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         }
     }
     if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps && env_int("SGPU_DEC_WARP", 1)) {
+        if (f->Qpad == 2 * kR && env_int("SGPU_DEC_WALK", 0)) {
+            // walking decimator (fir_walk.cuh): one phase per lane, K runs per lane
+            int st = SGPU_OK;
+            bool done = false;
+#define LAUNCH_DWALK(MV, KV, NWV, MB)                                                                      \
+    do {                                                                                                   \
+        constexpr int G_ = 32 / MV, ROWS_ = 2 + G_ * KV, RS_ = ROWS_ | 1;                                  \
+        constexpr size_t warp_f4 = (size_t)MV * ((kR / 2) * RS_ + 1) + 32 * (kR / 2 + 1);                  \
+        const size_t smem = NWV * warp_f4 * sizeof(float4) + (size_t)MV * (2 * kR + kTapSkew) * sizeof(float); \
+        if (smem <= (size_t)kMaxSmem) {                                                                    \
+            auto kern = fir_decim_walk_kernel<kR, MV, KV, NWV, MB, 8>;                                     \
+            st = set_smem(kern, smem);                                                                     \
+            if (st) return st;                                                                             \
+            const long long per_block = (long long)G_ * KV * kR * 8 * NWV;                                 \
+            dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);                    \
+            kern<<<grid, NWV * 32, smem, s>>>(a);                                                          \
+            done = true;                                                                                   \
+        }                                                                                                  \
+    } while (0)
+            if (f->M == 8) {
+                // measured on config 3's shape: K=3 362, K=5 347 G in-samp/s against 404 for
+                // fir_decim_warp_kernel -- fewer instructions per FFMA2 (0.2 vs 0.42) but only 6-10
+                // resident warps per SM, so the 8-byte de-interleave loads are exposed: opt-in only
+                if (env_int("SGPU_DEC_WALK_K", 3) == 5) LAUNCH_DWALK(8, 5, 4, 1);
+                else LAUNCH_DWALK(8, 3, 2, 5);
+            }
+#undef LAUNCH_DWALK
+            if (done) {
+                SGPU_LAUNCH_CHECK();
+                count_launch();
+                return SGPU_OK;
+            }
+        }
         // warp-private tiles (fir_walk.cuh)
         int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
         if (PS != 1 && PS != 2 && PS != 4) PS = 4;
