@@ -650,7 +650,8 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
             return SGPU_OK;
         }
     }
-    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps && env_int("SGPU_DEC_WARP", 1)) {
+    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32) && f->packed && !f->complex_taps &&
+        env_int("SGPU_DEC_WARP", 1)) {
         if (f->Qpad == 2 * kR && env_int("SGPU_DEC_WALK", 0)) {
             // walking decimator (fir_walk.cuh): one phase per lane, K runs per lane
             int st = SGPU_OK;
@@ -717,7 +718,15 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     } while (0)
         if (f->M == 8) LAUNCH_DWARP_M(8);
         else if (f->M == 4) LAUNCH_DWARP_M(4);
-        else LAUNCH_DWARP_M(2);
+        else if (f->M == 2) LAUNCH_DWARP_M(2);
+        else if (f->M == 16) {  // 16 / 32 phase planes per stage: fewer warps per block as the tile grows
+            LAUNCH_DWARP(16, 4, 4, 2);
+            if (!done) LAUNCH_DWARP(16, 4, 2, 2);
+            if (!done) LAUNCH_DWARP(16, 4, 1, 2);
+        } else {
+            LAUNCH_DWARP(32, 4, 2, 2);
+            if (!done) LAUNCH_DWARP(32, 4, 1, 2);
+        }
 #undef LAUNCH_DWARP_M
 #undef LAUNCH_DWARP
         if (done) {
@@ -1037,10 +1046,10 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
-    if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8) &&
+    if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8 || f->L == 16 || f->L == 32) &&
         env_int("SGPU_WALK", 1)) {
         // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase, warp-private tiles
-        const int K = env_int("SGPU_WALK_K", 5) == 7 ? 7 : 5;  // measured (L=4, 1024 ch): K=1 408, 3 412, 5 434, 7 421, 9 404 G out-samp/s
+        const int K = (f->L < 16 && env_int("SGPU_WALK_K", 5) == 7) ? 7 : 5;  // measured (L=4, 1024 ch): K=1 408, 3 412, 5 434, 7 421, 9 404 G out-samp/s
         const int G = 32 / (int)f->L;
         const int rows = 2 + G * K;
         a.RS = rows | 1;
@@ -1065,7 +1074,9 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     } while (0)
         if (f->L == 2) LAUNCH_IWALK_T(2);
         else if (f->L == 4) LAUNCH_IWALK_T(4);
-        else LAUNCH_IWALK_T(8);
+        else if (f->L == 8) LAUNCH_IWALK_T(8);
+        else if (f->L == 16) LAUNCH_IWALK(16, 5, 3);
+        else LAUNCH_IWALK(32, 5, 3);
 #undef LAUNCH_IWALK_T
 #undef LAUNCH_IWALK
         SGPU_LAUNCH_CHECK();

@@ -332,7 +332,7 @@ def test_fir_many_warp_tiles(fir, T):
         assert nerr(got[c], O.fir_fast(h, x[c], 0.75)) <= TOL
 
 
-@pytest.mark.parametrize("M,T", [(2, 40), (4, 128), (8, 256), (8, 700)])
+@pytest.mark.parametrize("M,T", [(2, 40), (4, 128), (8, 256), (8, 700), (16, 512), (16, 100), (32, 1024), (32, 4000)])
 def test_decim_many_warp_tiles(fir, M, T):
     rng = np.random.default_rng(M * 1000 + T)
     h = f32_taps(rng.uniform(-1, 1, T))
@@ -346,7 +346,7 @@ def test_decim_many_warp_tiles(fir, M, T):
         assert nerr(got[c], O.fir_fast(h, x[c], 1.25, M)) <= TOL
 
 
-@pytest.mark.parametrize("L,T", [(2, 64), (4, 128), (8, 256), (4, 100), (8, 17)])
+@pytest.mark.parametrize("L,T", [(2, 64), (4, 128), (8, 256), (4, 100), (8, 17), (16, 512), (16, 40), (32, 1000)])
 def test_interp_many_warp_tiles(fir, L, T):
     """Sub-filters of <= 32 taps take fir_interp_walk_kernel: several warps / blocks / tiles per warp,
     ragged end inside a run, split calls."""
