@@ -25,7 +25,7 @@ struct FirArgs {
     int T;                  // taps of the full filter
     int M;                  // decimation (decim kernel) or interpolation L (interp kernel)
     int c0;                 // decimator phase counter on entry (current_item)
-    int Qpad;               // taps per phase, padded to a multiple of 2R
+    int Qpad;               // taps per phase, padded to a multiple of R
     int RS;                 // row stride of a plane in float4, odd
     int vec_in, vec_out;    // 16-byte vector access allowed
     float scale_re, scale_im;
@@ -177,13 +177,13 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     for (int r = 0; r < NACC; ++r) acc[r] = make_float2(0.f, 0.f);
     const int ot = tid / PS, part = tid % PS;
     const int row0 = HR + ot;
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     const int Mp = (M + PS - 1) / PS;  // phases per lane of a split group (contiguous block)
     for (int sidx = 0; sidx < Mp; ++sidx) {
         const int p = part * Mp + sidx;
         if (p < M)
             fir_core<R, PACKED, CT>(acc, smem + (size_t)p * plane_f4, RS, row0,
-                                    taps_s + (size_t)p * (Qpad * TW + kTapSkew), npairs);
+                                    taps_s + (size_t)p * (Qpad * TW + kTapSkew), nchunks);
     }
     if constexpr (PS > 1) {  // butterfly over the PS lanes of a group: everyone ends with the full sums
 #pragma unroll
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
 
     const int ot = tid / PS, part = tid % PS;
     const int row0 = HR + ot;
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     float2 *my = stage + (size_t)ot * (R * L + 1);
     const int Lp = (L + PS - 1) / PS;
     for (int sidx = 0; sidx < Lp; ++sidx) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
         float2 acc[NACC];
 #pragma unroll
         for (int r = 0; r < NACC; ++r) acc[r] = make_float2(0.f, 0.f);
-        fir_core<R, PACKED, CT>(acc, smem, RS, row0, taps_s + (size_t)p * (Qpad * TW + kTapSkew), npairs);
+        fir_core<R, PACKED, CT>(acc, smem, RS, row0, taps_s + (size_t)p * (Qpad * TW + kTapSkew), nchunks);
 #pragma unroll
         for (int r = 0; r < R; ++r) {  // no scale: pfb.rs:85-90
             if constexpr (CT) my[r * L + p] = make_float2(acc[r].x - acc[R + r].y, acc[r].y + acc[R + r].x);
@@ -420,6 +420,9 @@ static int fir_upload_taps(sgpu_fir *f) {
     const int T = (int)f->T, M = (int)f->M, tw = f->complex_taps ? 2 : 1;
     f->Q = (T + M - 1) / M;
     f->Qpad = (int)round_up((size_t)f->Q, 2 * fir_R(f));
+    // sub-filters of <= 16 taps: single-chunk instantiations of the warp-private kernels (no zero padding to 32)
+    if (f->Q <= kR && !f->complex_taps && f->packed && (f->M == 1 || f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32))
+        f->Qpad = kR;
     // g[k] = h[T-1-k] (REVERSE, fir/mod.rs:86); phase p filter: g_p[q] = g[q*M + p]
     std::vector<float> ph((size_t)M * f->Q * tw, 0.f);
     for (int k = 0; k < T; ++k)
@@ -560,7 +563,7 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     a.scale_im = (float)f->scale_im;
     const int tw = 1;
     if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps &&
-        env_int("SGPU_PIPE_DEC", 0)) {
+        f->Qpad % (2 * kR) == 0 && env_int("SGPU_PIPE_DEC", 0)) {
         // persistent multi-stage decimator (fir_pipe.cuh).  Measured SLOWER than the one-tile-per-block
         // kernel below on B200 (257 vs 338 G input samples/s on config 3's shape: the ring spends shared
         // memory on in-flight stages instead of resident warps), so it is opt-in for experiments only.
@@ -627,11 +630,11 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         const int ns = env_int("SGPU_FIR_NS", 1);
         int st = SGPU_OK;
         bool done = false;
-#define LAUNCH_FWARP(NWV, MB, NSV)                                                            \
+#define LAUNCH_FWARP(NWV, MB, NSV, ONEV)                                                      \
     do {                                                                                      \
         const size_t smem = (size_t)NWV * NSV * stage_b + taps_b;                             \
         if (smem <= (size_t)kMaxSmem) {                                                       \
-            auto kern = fir_warp_kernel<kR, NWV, MB, TPW, NSV>;                               \
+            auto kern = fir_warp_kernel<kR, NWV, MB, TPW, NSV, ONEV>;                         \
             st = set_smem(kern, smem);                                                        \
             if (st) return st;                                                                \
             const long long per_block = 32LL * kR * TPW * NWV;                                \
@@ -640,9 +643,10 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
             done = true;                                                                      \
         }                                                                                     \
     } while (0)
-        if (ns == 2) LAUNCH_FWARP(4, 3, 2);
-        else LAUNCH_FWARP(4, 4, 1);
-        if (!done) LAUNCH_FWARP(1, 1, 1);  // very long filters: one warp per block
+        if (f->Qpad == kR) LAUNCH_FWARP(4, 4, 1, true);  // <= 16 taps: single tap chunk
+        else if (ns == 2) LAUNCH_FWARP(4, 3, 2, false);
+        else LAUNCH_FWARP(4, 4, 1, false);
+        if (!done && f->Qpad != kR) LAUNCH_FWARP(1, 1, 1, false);  // very long filters: one warp per block
 #undef LAUNCH_FWARP
         if (done) {
             SGPU_LAUNCH_CHECK();
@@ -689,6 +693,8 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
         if (PS != 1 && PS != 2 && PS != 4) PS = 4;
         if (PS > (int)f->M) PS = (int)f->M;
+        const bool one = f->Qpad == kR;  // sub-filters of <= 16 taps: single tap chunk
+        if (one) PS = f->M >= 4 ? 4 : 2;
         const int G = 32 / PS;
         const int rows = f->Qpad / kR + G;
         a.RS = rows | 1;
@@ -697,11 +703,11 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         constexpr int TPW = 8;
         int st = SGPU_OK;
         bool done = false;
-#define LAUNCH_DWARP(MV, PSV, NWV, MB)                                                        \
+#define LAUNCH_DWARP(MV, PSV, NWV, MB, ONEV)                                                  \
     do {                                                                                      \
         const size_t smem = (size_t)NWV * stage_b + taps_b;                                   \
         if (smem <= (size_t)kMaxSmem) {                                                       \
-            auto kern = fir_decim_warp_kernel<kR, MV, PSV, NWV, MB, TPW>;                     \
+            auto kern = fir_decim_warp_kernel<kR, MV, PSV, NWV, MB, TPW, ONEV>;               \
             st = set_smem(kern, smem);                                                        \
             if (st) return st;                                                                \
             const long long per_block = (long long)(32 / PSV) * kR * TPW * NWV;               \
@@ -712,20 +718,27 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
     } while (0)
 #define LAUNCH_DWARP_M(MV)                                                                    \
     do {                                                                                      \
-        if (PS == 1) LAUNCH_DWARP(MV, 1, 1, 4);                                               \
-        else if (PS == 2) LAUNCH_DWARP(MV, 2, 2, 4);                                          \
-        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4);                                       \
+        if (one) LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4, true);                             \
+        else if (PS == 1) LAUNCH_DWARP(MV, 1, 1, 4, false);                                   \
+        else if (PS == 2) LAUNCH_DWARP(MV, 2, 2, 4, false);                                   \
+        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4, false);                                \
     } while (0)
         if (f->M == 8) LAUNCH_DWARP_M(8);
         else if (f->M == 4) LAUNCH_DWARP_M(4);
         else if (f->M == 2) LAUNCH_DWARP_M(2);
         else if (f->M == 16) {  // 16 / 32 phase planes per stage: fewer warps per block as the tile grows
-            LAUNCH_DWARP(16, 4, 4, 2);
-            if (!done) LAUNCH_DWARP(16, 4, 2, 2);
-            if (!done) LAUNCH_DWARP(16, 4, 1, 2);
+            if (one) LAUNCH_DWARP(16, 4, 4, 2, true);
+            else {
+                LAUNCH_DWARP(16, 4, 4, 2, false);
+                if (!done) LAUNCH_DWARP(16, 4, 2, 2, false);
+                if (!done) LAUNCH_DWARP(16, 4, 1, 2, false);
+            }
         } else {
-            LAUNCH_DWARP(32, 4, 2, 2);
-            if (!done) LAUNCH_DWARP(32, 4, 1, 2);
+            if (one) LAUNCH_DWARP(32, 4, 2, 2, true);
+            else {
+                LAUNCH_DWARP(32, 4, 2, 2, false);
+                if (!done) LAUNCH_DWARP(32, 4, 1, 2, false);
+            }
         }
 #undef LAUNCH_DWARP_M
 #undef LAUNCH_DWARP
@@ -735,6 +748,8 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
             return SGPU_OK;
         }
     }
+    if (n_out > 0 && f->Qpad % (2 * fir_R(f)) != 0)
+        return fail(SGPU_ERR_UNSUPPORTED, "single-chunk tap image: the warp-private kernels are disabled (SGPU_*_WARP=0)");
     if (n_out > 0) {
         const bool m1 = f->M == 1;
         const int R = fir_R(f);
@@ -917,6 +932,8 @@ static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S (complex: 
             for (int c = 0; c < tw; ++c)
                 f->phase_taps[((size_t)p * S + j) * tw + c] = (float)taps_eff[(p + (size_t)(S - 1 - j) * L) * tw + c];
     f->Qpad = (int)round_up((size_t)S, 2 * (f->complex_taps ? 8 : kR));
+    if (S <= kR && !f->complex_taps && f->packed && (L == 2 || L == 4 || L == 8 || L == 16 || L == 32))
+        f->Qpad = kR;  // single-chunk walking kernel
     std::vector<float> img;
     build_tap_image(f->phase_taps, L, S, f->Qpad, tw, img);
     SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
@@ -1046,12 +1063,13 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
-    if (!f->complex_taps && f->packed && f->Qpad == 2 * kR && (f->L == 2 || f->L == 4 || f->L == 8 || f->L == 16 || f->L == 32) &&
-        env_int("SGPU_WALK", 1)) {
-        // walking kernel (fir_walk.cuh): sub-filters of <= 32 taps, one lane per phase, warp-private tiles
-        const int K = (f->L < 16 && env_int("SGPU_WALK_K", 5) == 7) ? 7 : 5;  // measured (L=4, 1024 ch): K=1 408, 3 412, 5 434, 7 421, 9 404 G out-samp/s
+    if (!f->complex_taps && f->packed && (f->Qpad == 2 * kR || f->Qpad == kR) &&
+        (f->L == 2 || f->L == 4 || f->L == 8 || f->L == 16 || f->L == 32) && env_int("SGPU_WALK", 1)) {
+        // walking kernel (fir_walk.cuh): sub-filters of <= 16 / <= 32 taps, one lane per phase, warp-private tiles
+        const int NC = f->Qpad / kR;
+        const int K = (f->L < 16 && NC == 2 && env_int("SGPU_WALK_K", 5) == 7) ? 7 : 5;  // measured (L=4, 1024 ch): K=1 408, 3 412, 5 434, 7 421, 9 404 G out-samp/s
         const int G = 32 / (int)f->L;
-        const int rows = 2 + G * K;
+        const int rows = NC + G * K;
         a.RS = rows | 1;
         const size_t smem = (size_t)(kNT / 32) * 2 * ((size_t)(kR / 2) * a.RS + 1) * sizeof(float4) +
                             f->L * (size_t)(f->Qpad + kTapSkew) * sizeof(float);
@@ -1060,29 +1078,32 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
         const long long per_block = tile * TPW * (kNT / 32);
         dim3 grid((unsigned)((n_in + per_block - 1) / per_block), (unsigned)f->C);
         int st;
-#define LAUNCH_IWALK(LV, KV, MB)                                          \
+#define LAUNCH_IWALK(LV, KV, MB, NCV)                                     \
     do {                                                                  \
-        auto kern = fir_interp_walk_kernel<kR, LV, KV, kNT, MB, TPW>;     \
+        auto kern = fir_interp_walk_kernel<kR, LV, KV, kNT, MB, TPW, NCV>; \
         st = set_smem(kern, smem);                                        \
         if (st) return st;                                                \
         kern<<<grid, kNT, smem, s>>>(a);                                  \
     } while (0)
 #define LAUNCH_IWALK_T(LV)                                                \
     do {                                                                  \
-        if (K == 7) LAUNCH_IWALK(LV, 7, 3);                               \
-        else LAUNCH_IWALK(LV, 5, 3);                                      \
+        if (NC == 1) LAUNCH_IWALK(LV, 5, 3, 1);                           \
+        else if (K == 7) LAUNCH_IWALK(LV, 7, 3, 2);                       \
+        else LAUNCH_IWALK(LV, 5, 3, 2);                                   \
     } while (0)
         if (f->L == 2) LAUNCH_IWALK_T(2);
         else if (f->L == 4) LAUNCH_IWALK_T(4);
         else if (f->L == 8) LAUNCH_IWALK_T(8);
-        else if (f->L == 16) LAUNCH_IWALK(16, 5, 3);
-        else LAUNCH_IWALK(32, 5, 3);
+        else if (f->L == 16) { if (NC == 1) LAUNCH_IWALK(16, 5, 3, 1); else LAUNCH_IWALK(16, 5, 3, 2); }
+        else { if (NC == 1) LAUNCH_IWALK(32, 5, 3, 1); else LAUNCH_IWALK(32, 5, 3, 2); }
 #undef LAUNCH_IWALK_T
 #undef LAUNCH_IWALK
         SGPU_LAUNCH_CHECK();
         count_launch();
         return SGPU_OK;
     }
+    if (f->Qpad % (2 * (f->complex_taps ? 8 : kR)) != 0)
+        return fail(SGPU_ERR_UNSUPPORTED, "single-chunk tap image: the walking kernel is disabled (SGPU_WALK=0)");
     if (!f->complex_taps && env_int("SGPU_PIPE", 1)) {
         // persistent multi-stage interpolator (fir_pipe.cuh)
         int PSp = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);

@@ -87,22 +87,30 @@ __device__ __forceinline__ void fir_chunk(float2 (&acc)[CT ? 2 * R : R], const f
     }
 }
 
-// acc[r] += sum_{k < 2*R*npairs} g[k] * seq[R*row0 + r - k]   (seq = the plane's sample sequence)
-template <int R, bool PACKED, bool CT = false>
+// acc[r] += sum_{k < R*nchunks} g[k] * seq[R*row0 + r - k]   (seq = the plane's sample sequence)
+// nchunks = taps per phase / R.  Chunks run in pairs (the two halves of the register window swap
+// roles), so nchunks is even -- except in the ONE instantiations, which are the single-chunk
+// kernels for sub-filters of <= R taps (no loop at all).
+template <int R, bool PACKED, bool CT = false, bool ONE = false>
 __device__ __forceinline__ void fir_core(float2 (&acc)[CT ? 2 * R : R], const float4 *__restrict__ plane,
                                          const int RS, const int row0,
-                                         const float *__restrict__ taps, const int npairs) {
+                                         const float *__restrict__ taps, const int nchunks) {
     constexpr int TW = CT ? 2 : 1;  // floats per tap in shared memory
     float2 W[2 * R];
     load_row<R, 0>(W, plane, RS, row0);
-    int row = row0;
-    for (int cp = 0; cp < npairs; ++cp) {
-        load_row<R, R>(W, plane, RS, row - 1);
+    if constexpr (ONE) {
+        load_row<R, R>(W, plane, RS, row0 - 1);
         fir_chunk<R, PACKED, 0, CT>(acc, W, taps);
-        load_row<R, 0>(W, plane, RS, row - 2);
-        fir_chunk<R, PACKED, R, CT>(acc, W, taps + R * TW);
-        row -= 2;
-        taps += 2 * R * TW;
+    } else {
+        int row = row0;
+        for (int cp = 0; cp < (nchunks >> 1); ++cp) {
+            load_row<R, R>(W, plane, RS, row - 1);
+            fir_chunk<R, PACKED, 0, CT>(acc, W, taps);
+            load_row<R, 0>(W, plane, RS, row - 2);
+            fir_chunk<R, PACKED, R, CT>(acc, W, taps + R * TW);
+            row -= 2;
+            taps += 2 * R * TW;
+        }
     }
 }
 

@@ -27,7 +27,7 @@ struct FirPipeArgs {
     int T;      // history convention: hist holds T-1 samples per channel
     int M;      // decimation M or interpolation L
     int c0;     // decimator phase on entry
-    int Qpad;   // taps per phase, multiple of 2R
+    int Qpad;   // taps per phase, multiple of R
     int RS;     // plane row stride in float4 (odd)
     int vec_out;
     float scale_re;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_pipe_kernel(const FirPipeA
     }
     const int ot = tid / PS, part = tid % PS;
     const int row0 = HR + ot;
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     constexpr int RP = R / PS;  // outputs this lane stores
     int stg = 0;
     for (; tile < a.total_tiles; tile += stride) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_pipe_kernel(const FirPipeA
 #pragma unroll
         for (int sidx = 0; sidx < MP; ++sidx) {
             const int p = part * MP + sidx;
-            fir_core<R, PACKED>(acc, st + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
+            fir_core<R, PACKED>(acc, st + (size_t)p * plane_f4, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), nchunks);
         }
         if constexpr (PS > 1) {
 #pragma unroll
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_pipe_kernel(const FirPipe
     }
     const int ot = tid / PS, part = tid % PS;
     const int row0 = HR + ot;
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     const int Lp = (L + PS - 1) / PS;
     int stg = 0;
     for (; tile < a.total_tiles; tile += stride) {
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_pipe_kernel(const FirPipe
             float2 acc[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-            fir_core<R, PACKED>(acc, st, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
+            fir_core<R, PACKED>(acc, st, RS, row0, taps_s + (size_t)p * (Qpad + kTapSkew), nchunks);
             float2 *yp = y + p;
             if ((long long)R * L <= room) {
 #pragma unroll

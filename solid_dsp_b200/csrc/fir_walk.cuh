@@ -18,14 +18,16 @@
 // one run of R outputs over a 2R-tap sub-filter.  PAR = 0: the run's newest row sits in W[0, R) and
 // the row before it in W[R, 2R); PAR = 1: the other way round.  `next_row` (two rows older than
 // the run's newest) replaces the newest row between the two tap chunks.
-template <int R, int PAR>
+template <int R, int PAR, int NC = 2>
 __device__ __forceinline__ void walk_run(float2 (&acc)[R], float2 (&W)[2 * R], const float4 *__restrict__ plane,
                                          const int RS, const int next_row, const float *__restrict__ taps) {
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
     fir_chunk<R, true, PAR ? R : 0, false>(acc, W, taps);
     load_row<R, PAR ? R : 0>(W, plane, RS, next_row);
-    fir_chunk<R, true, PAR ? 0 : R, false>(acc, W, taps + R);
+    // NC = 1 (sub-filters of <= R taps): the run ends here and the row just loaded is the next run's
+    // older row; NC = 2: second tap chunk over (newest-1, newest-2)
+    if constexpr (NC == 2) fir_chunk<R, true, PAR ? 0 : R, false>(acc, W, taps + R);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -36,11 +38,12 @@ __device__ __forceinline__ void walk_run(float2 (&acc)[R], float2 (&W)[2 * R], c
 // in, so the warps of an SM drift apart and the FMA pipe always finds one in its arithmetic phase.
 // A warp tile = 32/L groups x K runs x R input positions; group g owns positions [g*K*R, (g+1)*K*R)
 // and its lane p produces phase p of their outputs.
-template <int R, int L, int K, int NT, int MINB, int TPW>
+template <int R, int L, int K, int NT, int MINB, int TPW, int NC = 2>
 __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     static_assert(K % 2 == 1, "K must be odd (bank conflicts, parity of the last run)");
-    constexpr int G = 32 / L, HR = 2, ROWS = HR + G * K, QP = 2 * R, TILE = G * K * R, NW = NT / 32;
+    static_assert(NC == 1 || NC == 2, "sub-filters of NC * R taps");
+    constexpr int G = 32 / L, HR = NC, ROWS = HR + G * K, QP = NC * R, TILE = G * K * R, NW = NT / 32;
     constexpr int RS = ROWS | 1, STAGE_F4 = (R / 2) * RS + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *taps_s = reinterpret_cast<float *>(smem + NW * 2 * STAGE_F4);
@@ -108,13 +111,14 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs
         };
 #pragma unroll 1
         for (int it = 0; it < (K - 1) / 2; ++it) {
-            walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);
+            walk_run<R, 0, NC>(acc, W, plane, RS, row - 2, tp);
             store();
-            walk_run<R, 1>(acc, W, plane, RS, row - 3, tp);
+            walk_run<R, 1, NC>(acc, W, plane, RS, row - 3, tp);
             store();
             row -= 2;
         }
-        walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);  // rows 0/1 of the plane are the halo: row - 2 >= 0
+        // the halo rows keep row - 2 >= 0 for NC = 2; for NC = 1 the last row load is not needed: clamp
+        walk_run<R, 0, NC>(acc, W, plane, RS, max(row - 2, 0), tp);
         store();
     }
 }
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs
 // free by then): a lane writes its R sums as R/2 float4, then reads and adds the PS partials of
 // the pieces it stores -- every PS-th 16-byte piece of the run, so each store instruction writes
 // whole 32-byte sectors.  8 STS + 8 LDS + 12 FADD2 instead of the 128 SHFL/FADD of a butterfly.
-template <int R, int M, int PS, int NW, int MINB, int TPW>
+template <int R, int M, int PS, int NW, int MINB, int TPW, bool ONE = false>
 __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     constexpr int G = 32 / PS, MP = M / PS, RM = R * M, LPRW = RM / 32;  // LPRW: loader steps per row of all planes
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
         }
     };
     const int g = lane / PS, part = lane % PS;
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     constexpr int TILE = G * R;  // outputs per warp tile
     constexpr int RED = R / 2 + 1;  // float4 pitch of a lane's partial sums
     constexpr long long STEP = (long long)NW * TILE;  // warps take the block's tiles round-robin (halo = L2 hit)
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
 #pragma unroll
         for (int sidx = 0; sidx < MP; ++sidx) {
             const int p = part * MP + sidx;
-            fir_core<R, true>(acc, stage + (size_t)p * plane_f4, RS, HR + g, taps_s + (size_t)p * (Qpad + kTapSkew), npairs);
+            fir_core<R, true, false, ONE>(acc, stage + (size_t)p * plane_f4, RS, HR + g, taps_s + (size_t)p * (Qpad + kTapSkew),
+                                          nchunks);
         }
         float4 out[NPC];
         if constexpr (PS > 1) {
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
 // A warp tile is 32 runs of R outputs (one per lane) plus the Qpad-sample halo in front of them; NS
 // private stages filled by 16-byte cp.async, __syncwarp only.  The R outputs of a lane are turned
 // into coalesced 16-byte stores through the stage the warp has just finished reading.
-template <int R, int NW, int MINB, int TPW, int NS>
+template <int R, int NW, int MINB, int TPW, int NS, bool ONE = false>
 __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
             }
         }
     };
-    const int npairs = Qpad / (2 * R);
+    const int nchunks = Qpad / R;
     constexpr int TILE = 32 * R;
     constexpr int RED = R / 2 + 1;
     constexpr long long STEP = (long long)NW * TILE;  // warps take the block's tiles round-robin (halo = L2 hit)
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-        fir_core<R, true>(acc, st, RS, HR + lane, taps_s, npairs);
+        fir_core<R, true, false, ONE>(acc, st, RS, HR + lane, taps_s, nchunks);
         // transpose: lane's R outputs -> rows of the stage -> 16-byte pieces, 4 runs (512 bytes) per instruction
         __syncwarp();
         const float s = a.scale_re;
