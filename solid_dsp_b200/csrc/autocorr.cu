@@ -218,17 +218,26 @@ int ac_launch(sgpu_autocorr *f, const float2 *d_in, long long n_in, long long is
     a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (ostr % 2 == 0);
     const size_t nx = kTileOut + f->W - 1, np = kTileOut + (size_t)a.Wd;
     const size_t smem = (((nx + 1) & ~(size_t)1) + ((np + np / 8 + 4) & ~(size_t)1) + np / 8 + 2) * sizeof(float2);
-    if (d_out) {
-        SGPU_CUDA(cudaFuncSetAttribute(autocorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)ceil_div((size_t)n_in + a.shift, kTileOut), (unsigned)f->C);
-        autocorr_kernel<<<grid, kNT, smem, s>>>(a);
+    constexpr size_t kMaxGridY = 65535;  // channels ride in grid.y: larger handles go in channel blocks
+    const float2 *hist_all = f->d_hist[f->cur];
+    if (d_out) SGPU_CUDA(cudaFuncSetAttribute(autocorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (size_t c0 = 0; c0 < f->C; c0 += kMaxGridY) {
+        const unsigned nc = (unsigned)std::min<size_t>(kMaxGridY, f->C - c0);
+        if (d_out) {
+            a.in = d_in + (long long)c0 * istr;
+            a.out = d_out + (long long)c0 * ostr;
+            a.hist = hist_all + c0 * (size_t)a.HW;
+            dim3 grid((unsigned)ceil_div((size_t)n_in + a.shift, kTileOut), nc);
+            autocorr_kernel<<<grid, kNT, smem, s>>>(a);
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+        }
+        dim3 hg((unsigned)ceil_div(f->W + kHistExtra, 128), nc);
+        ac_hist_update_kernel<<<hg, 128, 0, s>>>(d_in + (long long)c0 * istr, istr, n_in, hist_all + c0 * (size_t)a.HW,
+                                                 f->d_hist[f->cur ^ 1] + c0 * (size_t)a.HW, a.HW);
         SGPU_LAUNCH_CHECK();
         count_launch();
     }
-    dim3 hg((unsigned)ceil_div(f->W + kHistExtra, 128), (unsigned)f->C);
-    ac_hist_update_kernel<<<hg, 128, 0, s>>>(d_in, istr, n_in, f->d_hist[f->cur], f->d_hist[f->cur ^ 1], a.HW);
-    SGPU_LAUNCH_CHECK();
-    count_launch();
     f->cur ^= 1;
     f->pos += (uint64_t)n_in;
     return SGPU_OK;
@@ -250,7 +259,7 @@ SGPU_EXPORT int sgpu_autocorr_create(size_t window_size, size_t delay, size_t n_
     *out = nullptr;
     if (window_size == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "window_size == 0 (Window::new asserts capacity > 0)");
     if (window_size > (size_t)kMaxWindow) return fail(SGPU_ERR_UNSUPPORTED, "window_size above %d", kMaxWindow);
-    if (n_channels == 0 || n_channels > 65535) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels must be 1..65535");
+    if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels == 0");
     int dev = 0, sms = 0;
     int st = require_device(&dev, &sms);
     if (st) return st;

@@ -14,6 +14,7 @@ namespace sgpu {
 namespace {
 
 constexpr int kMaxSmem = 227 * 1024;
+constexpr size_t kMaxGridY = 65535;
 
 struct FirArgs {
     const float2 *in;
@@ -406,6 +407,7 @@ struct sgpu_fir {
     double scale_re = 1.0, scale_im = 0.0;
     std::vector<float> taps_f32;  // caller order h[0..T), rounded to f32 (x2 when complex)
     uint64_t current_item = 0;    // fir/decim.rs:8
+    size_t ch_off = 0;            // first channel of the block being launched (grids carry <= 65535 channels in y)
     int Q = 0, Qpad = 0;          // taps per phase
     float *d_taps = nullptr;      // tap image
     float2 *d_hist[2] = {nullptr, nullptr};
@@ -533,21 +535,42 @@ int set_smem(K kernel, size_t bytes) {
 int enqueue_hist_update(const float2 *d_in, long long in_stride, long long n_in, float2 *hist[2], int &cur,
                         size_t C, size_t H, cudaStream_t s) {
     if (H == 0 || n_in == 0) return SGPU_OK;
-    dim3 grid((unsigned)ceil_div(H, 128), (unsigned)C);
-    hist_update_kernel<<<grid, 128, 0, s>>>(d_in, in_stride, n_in, hist[cur], hist[cur ^ 1], (int)H);
-    SGPU_LAUNCH_CHECK();
-    count_launch();
+    for (size_t c0 = 0; c0 < C; c0 += kMaxGridY) {
+        dim3 grid((unsigned)ceil_div(H, 128), (unsigned)std::min<size_t>(kMaxGridY, C - c0));
+        hist_update_kernel<<<grid, 128, 0, s>>>(d_in + (long long)c0 * in_stride, in_stride, n_in, hist[cur] + c0 * H,
+                                                hist[cur ^ 1] + c0 * H, (int)H);
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+    }
     cur ^= 1;
     return SGPU_OK;
 }
 
+int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
+                     long long out_stride, long long n_out, cudaStream_t s);
+
+// Channels ride in grid.y (<= 65535): larger handles are launched in channel blocks.
 int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
                long long out_stride, long long n_out, cudaStream_t s) {
-    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
+    const size_t Ctot = f->C;
+    int st = SGPU_OK;
+    for (size_t c0 = 0; c0 < Ctot && st == SGPU_OK; c0 += kMaxGridY) {
+        f->C = std::min<size_t>(kMaxGridY, Ctot - c0);
+        f->ch_off = c0;
+        st = fir_launch_block(f, d_in + (long long)c0 * in_stride, n_in, in_stride, d_out + (long long)c0 * out_stride,
+                              out_stride, n_out, s);
+    }
+    f->C = Ctot;
+    f->ch_off = 0;
+    return st;
+}
+
+int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
+                     long long out_stride, long long n_out, cudaStream_t s) {
     FirArgs a{};
     a.in = d_in;
     a.out = d_out;
-    a.hist = f->d_hist[f->cur];
+    a.hist = f->d_hist[f->cur] + f->ch_off * (f->T - 1);
     a.taps = f->d_taps;
     a.in_stride = in_stride;
     a.out_stride = out_stride;
@@ -582,7 +605,7 @@ int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_str
         const long long tiles_total = ((n_out + (long long)OT * kR - 1) / ((long long)OT * kR)) * (long long)f->C;
         if (smem_for(NS) <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
             FirPipeArgs pa{};
-            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur]; pa.taps = f->d_taps;
+            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur] + f->ch_off * (f->T - 1); pa.taps = f->d_taps;
             pa.in_stride = in_stride; pa.out_stride = out_stride; pa.n_in = n_in; pa.n_out = n_out;
             pa.tiles_per_ch = (int)((n_out + (long long)OT * kR - 1) / ((long long)OT * kR));
             pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
@@ -916,6 +939,7 @@ struct sgpu_interp {
     bool packed = true, complex_taps = false;
     double scale_re = 1.0, scale_im = 0.0;  // stored, never applied (pfb.rs:85-90)
     std::vector<float> phase_taps;           // [L][S][tw]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first)
+    size_t ch_off = 0;                       // first channel of the block being launched
     int Qpad = 0;
     float *d_taps = nullptr;
     float2 *d_hist[2] = {nullptr, nullptr};  // S samples per channel: the PFB window (oldest first)
@@ -1042,14 +1066,31 @@ SGPU_EXPORT int sgpu_interp_coefficients(const sgpu_interp *f, double *out) {
 }
 
 namespace {
+int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long long istr, float2 *d_out, long long ostr,
+                        long long n_out, cudaStream_t s);
+
 int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long istr, float2 *d_out, long long ostr,
                   long long n_out, cudaStream_t s) {
+    const size_t Ctot = f->C;
+    int st = SGPU_OK;
+    for (size_t c0 = 0; c0 < Ctot && st == SGPU_OK; c0 += kMaxGridY) {  // channels ride in grid.y (<= 65535)
+        f->C = std::min<size_t>(kMaxGridY, Ctot - c0);
+        f->ch_off = c0;
+        st = interp_launch_block(f, d_in + (long long)c0 * istr, n_in, istr, d_out + (long long)c0 * ostr, ostr, n_out, s);
+    }
+    f->C = Ctot;
+    f->ch_off = 0;
+    return st;
+}
+
+int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long long istr, float2 *d_out, long long ostr,
+                        long long n_out, cudaStream_t s) {
     FirArgs a{};
     a.in = d_in;
     a.out = d_out;
     // the kernel's history convention is "T-1 samples before x[0]" with T = S+1 here: the PFB
     // window keeps S samples, of which the interpolator only ever reads the newest S-1 as past.
-    a.hist = f->d_hist[f->cur];
+    a.hist = f->d_hist[f->cur] + f->ch_off * f->S;
     a.taps = f->d_taps;
     a.in_stride = istr;
     a.out_stride = ostr;
@@ -1117,7 +1158,7 @@ int interp_launch(sgpu_interp *f, const float2 *d_in, long long n_in, long long 
         const long long tiles_total = ((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR)) * (long long)f->C;
         if (smemp <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
             FirPipeArgs pa{};
-            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur]; pa.taps = f->d_taps;
+            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur] + f->ch_off * f->S; pa.taps = f->d_taps;
             pa.in_stride = istr; pa.out_stride = ostr; pa.n_in = n_in; pa.n_out = n_out;
             pa.tiles_per_ch = (int)((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR));
             pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
@@ -1198,7 +1239,6 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
     if (!in || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
     if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
     if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
-    if (f->C > 65535) return fail(SGPU_ERR_UNSUPPORTED, "more than 65535 channels per handle");
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
     auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,

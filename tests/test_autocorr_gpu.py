@@ -90,3 +90,15 @@ def test_device_pointers_and_errors(ac):
         assert nerr(got[c].cpu().numpy(), O.autocorr_fast(20, 4, x[c])) <= TOL
     with pytest.raises(_ffi.SolidGpuError):
         ac.AutoCorrelator(0, 0)                              # Window::new asserts capacity > 0
+
+
+def test_more_than_65535_channels(ac):
+    rng = np.random.default_rng(70000)
+    C, n = 66000, 200
+    x = rand_cf32(rng, (C, n))
+    f = ac.AutoCorrelator(12, 4, n_channels=C)
+    y = np.concatenate([f.execute_block(x[:, :77]), f.execute_block(x[:, 77:])], axis=1)
+    for c in (0, 65534, 65535, 65536, C - 1):
+        assert nerr(y[c], O.autocorr_fast(12, 4, x[c])) <= TOL
+    e = f.get_energy()
+    assert abs(e[C - 1] - np.sum(np.abs(x[C - 1, -12:].astype(np.complex128)) ** 2)) <= 1e-5 * e[C - 1]

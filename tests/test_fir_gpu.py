@@ -366,3 +366,21 @@ def test_interp_many_warp_tiles(fir, L, T):
     y = fir.InterpolatingFIRFilter(h, L).execute_block(imp)
     ref = O.firinterp_fast(h, L, imp)
     assert np.array_equal(np.nonzero(y)[0], np.nonzero(ref)[0]) and nerr(y, ref) <= 1e-7
+
+
+def test_more_than_65535_channels(fir):
+    """Channels ride in grid.y (<= 65535): larger handles are launched in channel blocks.  The first,
+    the 65535th / 65536th and the last channel against the oracle, FIR + decimator + interpolator."""
+    rng = np.random.default_rng(65536)
+    C, n = 70000, 300
+    x = rand_cf32(rng, (C, n))
+    h = f32_taps(rng.uniform(-1, 1, 40))
+    picks = (0, 65534, 65535, 65536, C - 1)
+    f = fir.FIRFilter(h, 1.0, n_channels=C)
+    y = np.concatenate([f.execute_block(x[:, :100]), f.execute_block(x[:, 100:])], axis=1)
+    d = fir.DecimatingFIRFilter(h, 1.0, 4, n_channels=C).execute_block(x)
+    i = fir.InterpolatingFIRFilter(h, 2, n_channels=C).execute_block(x)
+    for c in picks:
+        assert nerr(y[c], O.fir_fast(h, x[c])) <= TOL
+        assert nerr(d[c], O.fir_fast(h, x[c], 1.0, 4)) <= TOL
+        assert nerr(i[c], O.firinterp_fast(h, 2, x[c])) <= TOL
