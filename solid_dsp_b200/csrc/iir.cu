@@ -16,6 +16,7 @@
 //           the carry kernel solves s_{p+1} = A^Lc s_p + z_p (A^Lc built on the host in f64,
 //           recurrence evaluated in f64 on the device, hierarchically); pass C re-runs every
 //           chunk from its true start state and writes the outputs.
+#include <algorithm>
 #include <cmath>
 
 #include "sgpu_common.cuh"
@@ -933,11 +934,19 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
         // front of it.  Chunks are at least 2 * decay long (re-read <= 50 % of the input) unless the
         // scan is forced (mode 1: at least `decay`).
         const long long warm = (long long)round_up((size_t)decay, kScanTile);
-        const long long lc_min = f->mode == 1 ? warm : 2 * warm;
-        long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)chunks_wanted), kScanTile);
-        if (Lc < lc_min) Lc = lc_min;
-        const long long NPt = (long long)ceil_div((size_t)n_in, (size_t)Lc);
-        if (NPt < 2) return plain();
+        const long long lc_ideal = (long long)round_up(ceil_div((size_t)n_in, (size_t)chunks_wanted), kScanTile);
+        long long Lc = std::max(lc_ideal, f->mode == 1 ? warm : 2 * warm);
+        long long NPt = (long long)ceil_div((size_t)n_in, (size_t)Lc);
+        if (f->mode == -1 && NPt * (long long)f->C * 5 < lanes * 2 && Lc + warm > 4096) {
+            // a long filter memory leaves too few chunks to fill 40 % of the lanes AND every lane has a
+            // long sequential run in front of it (~0.1 us per sample when the chip is that empty): hand
+            // over to the three-pass scan, whose chunks are as short as they like.  Measured, 8 sections
+            // at pole radius 0.999 (memory 62912 samples), 2^28 samples: fused 21, three-pass 148 Gsamp/s.
+            // Short streams stay fused: their few chunks are short (2^22 samples: 0.06 vs 0.27 ms).
+            NPt = 0;
+        }
+        if (NPt == 1) return plain();
+        if (NPt >= 2) {
         a.Lc = Lc; a.warm = warm; a.NPt = (int)NPt; a.last_len = n_in - (NPt - 1) * Lc;
         long long warps;
         if (f->C >= 32) {
@@ -959,8 +968,10 @@ int iir_run(sgpu_iir *f, const float2 *d_in, long long n_in, long long istr, flo
         if (st) return st;
         SGPU_CUDA(cudaMemcpyAsync(f->d_state, f->d_z, f->C * (size_t)D * sizeof(float2), cudaMemcpyDeviceToDevice, s));
         return SGPU_OK;
+        }
     }
-    // ---- three-pass scan for filters whose memory does not decay within 2^16 samples.
+    // ---- three-pass scan: filters whose memory does not decay within 2^16 samples, or is too long
+    // for the fused scan to fill the chip.
     long long Lc = (long long)round_up(ceil_div((size_t)n_in, (size_t)chunks_wanted), kScanTile);
     if (Lc < 256) Lc = 256;
     const long long NP = n_in / Lc;          // full chunks
