@@ -9,7 +9,7 @@ import sys
 def main():
     prefix, out = sys.argv[1], sys.argv[2]
     res = {}
-    for w in ("fir", "decim", "interp", "iir_batch", "iir_scan"):
+    for w in ("fir", "decim", "interp", "iir_batch", "iir_scan", "autocorr"):
         rows = [r for r in csv.reader(open(f"{prefix}{w}.csv")) if len(r) > 10]
         hdr = {h: i for i, h in enumerate(rows[0])}
         per = {}
