@@ -8,6 +8,7 @@
 //   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
 #include "fir_core.cuh"
 #include "fir_pipe.cuh"
+#include "fir_tc.cuh"
 #include "sgpu_common.cuh"
 
 namespace sgpu {
@@ -414,6 +415,8 @@ struct sgpu_fir {
     int cur = 0;
     Staging stage;
     HostPipe pipe;
+    FirTcState *tc = nullptr;     // tensor-core path for long real-tap filters (fir_tc.cu), built on first use
+    bool tc_tried = false;
 };
 
 static int fir_R(const sgpu_fir *f) { return f->complex_taps ? 8 : kR; }
@@ -489,6 +492,7 @@ SGPU_EXPORT int sgpu_fir_destroy(sgpu_fir *f) {
     if (f->d_taps) cudaFree(f->d_taps);
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
+    fir_tc_destroy(f->tc);
     f->stage.release();
     f->pipe.release();
     delete f;
@@ -640,6 +644,26 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
 #undef LAUNCH_DPIPE
             SGPU_LAUNCH_CHECK();
             count_launch();
+            return SGPU_OK;
+        }
+    }
+    if (n_out > 0 && f->M == 1 && !f->complex_taps && f->scale_im == 0.0 && (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", 192) &&
+        n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 20) && env_int("SGPU_FIR_TC", 0)) {
+        // long real-tap filters: banded-Toeplitz product on the tcgen05 tensor cores, 3 x TF32 (fir_tc.cu)
+        const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
+        const size_t span_in = (size_t)((f->C - 1) * in_stride + n_in) * 8, span_out = (size_t)((f->C - 1) * out_stride + n_out) * 8;
+        const bool overlap = ib < ob + span_out && ob < ib + span_in;
+        if (!f->tc_tried) {
+            f->tc_tried = true;
+            int st = fir_tc_create(&f->tc, f->taps_f32.data(), (int)f->T);
+            if (st) return st;
+        }
+        if (f->tc && !overlap) {
+            for (size_t c = 0; c < f->C; ++c) {
+                int st = fir_tc_run(f->tc, d_in + (long long)c * in_stride, n_in, a.hist + c * (f->T - 1),
+                                    d_out + (long long)c * out_stride, (float)f->scale_re, f->sm_count, s);
+                if (st) return st;
+            }
             return SGPU_OK;
         }
     }
