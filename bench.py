@@ -386,6 +386,27 @@ def run_gpu_arm(args):
         t_fma = W["flop_per_unit"] / (peak_fma * 1e12)
         t_hbm = W["bytes_per_unit"] / (hbm_peak * 1e9)
         bound = "fma" if t_fma >= t_hbm else "hbm"
+        # Long real-tap FIR: the library runs it on the tcgen05 tensor cores (csrc/fir_tc.cu, 3 x TF32 over a
+        # banded-Toeplitz GEMM), so the binding roofline is the tensor pipe: TF32 dense = half the measured bf16 rate.
+        tensor = None
+        if name == "fir" and getattr(filt, "last_path", "ffma") == "tensor":
+            bf16_peak, bf16_src = 1590.0, "fallback (B200_PROFILING.md)"
+            if peaks_file.exists():
+                pk = json.loads(peaks_file.read_text())
+                bf16_peak = float(pk.get("bf16_tflops_sustained") or pk["bf16_tflops"])
+                bf16_src = ("measured (MEASURED_PEAKS.json, bf16_tflops_sustained: the kernel runs for several ms "
+                            "back to back under the power cap)")
+            T_ = len(taps)
+            koff = (T_ - 1 + 31) // 32 * 32
+            executed = 3.0 * (koff + 128) / T_  # 3 TF32 MMAs per K step over a band of Koff + 128 columns per 128 outputs
+            tf32_peak = bf16_peak / 2.0
+            tensor = {"achieved_tflops": ach_tflops, "peak_tflops": tf32_peak, "frac": ach_tflops / tf32_peak,
+                      "peak_source": "TF32 dense = bf16 / 2; bf16: " + bf16_src,
+                      "executed_tflops": ach_tflops * executed, "executed_frac": ach_tflops * executed / tf32_peak,
+                      "executed_over_algorithmic": executed,
+                      "note": "algorithmic flops = 4 per real x complex tap; the tensor pipe executes 3 (hi*hi, lo*hi, "
+                              "hi*lo) x (Koff+128)/T (band zeros) times that"}
+            bound = "tensor"
         # DRAM bytes (read + write) of one launch of the dominant kernel at this workload's full size,
         # from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture
         # (tools/profile_round.sh -> tools/traffic_json.py); only valid for the default sizes at N = 1.
@@ -397,13 +418,14 @@ def run_gpu_arm(args):
                 traffic = traffic_detail.get("dram_bytes")
         roofline = {
             "bound": bound,
-            "achieved": ach_tflops if bound == "fma" else ach_gbs,
-            "peak": peak_fma if bound == "fma" else hbm_peak,
-            "unit": "TFLOP/s" if bound == "fma" else "GB/s",
-            "frac": (ach_tflops / peak_fma) if bound == "fma" else (ach_gbs / hbm_peak),
+            "achieved": ach_gbs if bound == "hbm" else ach_tflops,
+            "peak": {"fma": peak_fma, "hbm": hbm_peak, "tensor": tensor and tensor["peak_tflops"]}[bound],
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+            "frac": {"fma": ach_tflops / peak_fma, "hbm": ach_gbs / hbm_peak,
+                     "tensor": tensor and tensor["frac"]}[bound],
             "traffic": traffic,
             "traffic_detail": traffic_detail,
-            "kernel": {"fir": "fir_decim_kernel<R=16,M1>", "decim": "fir_decim_kernel<R=16>",
+            "kernel": {"fir": "fir_tc_fused_kernel (tcgen05, 3xTF32)" if tensor else "fir_warp_kernel<R=16>", "decim": "fir_decim_kernel<R=16>",
                        "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
                        "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)",
                        "autocorr": "autocorr_kernel"}[name],
@@ -414,6 +436,8 @@ def run_gpu_arm(args):
                     "peak_source": "measured live: libsgpu_peakbench FFMA chains (fp32, non-tensor)", "detail": peak_detail},
             "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
         }
+        if tensor:
+            roofline["tensor"] = tensor
         cpu = None
         if world == 1 and not args.no_cpu:
             rate1, what1, _ = cpu_reference_path(name, 1, args.cpu_seconds)
@@ -424,7 +448,8 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f32 (3xTF32 split on the tensor cores, f32 accumulation)" if tensor else "f32", "data": "synthetic",
             "config": {"workload": W["desc"], "name": name, **shape_desc,
                        "l2": "inputs (>= 2 GiB per rank) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"stream segments x{world} with halo" if name in ("fir", "iir_scan") else f"channels x{world}"},

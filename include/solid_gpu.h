@@ -125,6 +125,9 @@ int sgpu_fir_get_scale(const sgpu_fir *f, double *re, double *im); /* fir/mod.rs
 size_t sgpu_fir_len(const sgpu_fir *f);                           /* fir/mod.rs:142 */
 size_t sgpu_fir_decimation(const sgpu_fir *f);                    /* decim.rs:96; 1 for a FIR */
 size_t sgpu_fir_channels(const sgpu_fir *f);
+/* Which arithmetic path the last execute_block took: 0 = FP32 FFMA2 kernels, 1 = tcgen05 tensor cores (long
+ * real-tap FIR as a banded-Toeplitz product, csrc/fir_tc.cu).  Reporting only (bench.py roofline). */
+int sgpu_fir_last_path(const sgpu_fir *f);
 /* FIRFilter::coefficients (fir/mod.rs:176-178): the STORED (reversed) order, as doubles of
  * the f32 values used on the device.  out: n_taps (REAL) or 2*n_taps (COMPLEX) doubles. */
 int sgpu_fir_coefficients(const sgpu_fir *f, double *out);

@@ -66,6 +66,7 @@ extern "C" {
     pub fn sgpu_fir_len(f: *const sgpu_fir) -> size_t;
     pub fn sgpu_fir_decimation(f: *const sgpu_fir) -> size_t;
     pub fn sgpu_fir_channels(f: *const sgpu_fir) -> size_t;
+    pub fn sgpu_fir_last_path(f: *const sgpu_fir) -> c_int;
     pub fn sgpu_fir_coefficients(f: *const sgpu_fir, out: *mut c_double) -> c_int;
     pub fn sgpu_fir_get_state(f: *mut sgpu_fir, history: *mut c_float, current_item: *mut u64) -> c_int;
     pub fn sgpu_fir_set_state(f: *mut sgpu_fir, history: *const c_float, current_item: u64) -> c_int;

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "sgpu_fir_len": (c_size, [vp]),
     "sgpu_fir_decimation": (c_size, [vp]),
     "sgpu_fir_channels": (c_size, [vp]),
+    "sgpu_fir_last_path": (C.c_int, [vp]),
     "sgpu_fir_coefficients": (C.c_int, [vp, c_dp]),
     "sgpu_fir_get_state": (C.c_int, [vp, vp, c_u64p]),
     "sgpu_fir_set_state": (C.c_int, [vp, vp, C.c_uint64]),

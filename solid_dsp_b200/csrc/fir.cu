@@ -417,6 +417,7 @@ struct sgpu_fir {
     HostPipe pipe;
     FirTcState *tc = nullptr;     // tensor-core path for long real-tap filters (fir_tc.cu), built on first use
     bool tc_tried = false;
+    int last_path = 0;            // 0 = FFMA2 kernels, 1 = tensor cores
 };
 
 static int fir_R(const sgpu_fir *f) { return f->complex_taps ? 8 : kR; }
@@ -506,6 +507,7 @@ SGPU_EXPORT size_t sgpu_fir_out_len(const sgpu_fir *f, size_t n_in) {
 SGPU_EXPORT size_t sgpu_fir_len(const sgpu_fir *f) { return f ? f->T : 0; }
 SGPU_EXPORT size_t sgpu_fir_decimation(const sgpu_fir *f) { return f ? f->M : 0; }
 SGPU_EXPORT size_t sgpu_fir_channels(const sgpu_fir *f) { return f ? f->C : 0; }
+SGPU_EXPORT int sgpu_fir_last_path(const sgpu_fir *f) { return f ? f->last_path : 0; }
 
 SGPU_EXPORT int sgpu_fir_set_scale(sgpu_fir *f, double re, double im) {
     if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
@@ -647,8 +649,9 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             return SGPU_OK;
         }
     }
+    f->last_path = 0;
     if (n_out > 0 && f->M == 1 && !f->complex_taps && f->scale_im == 0.0 && (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", 192) &&
-        n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 20) && env_int("SGPU_FIR_TC", 0)) {
+        n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 21) && env_int("SGPU_FIR_TC", 1)) {
         // long real-tap filters: banded-Toeplitz product on the tcgen05 tensor cores, 3 x TF32 (fir_tc.cu)
         const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
         const size_t span_in = (size_t)((f->C - 1) * in_stride + n_in) * 8, span_out = (size_t)((f->C - 1) * out_stride + n_out) * 8;
@@ -664,6 +667,7 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
                                     d_out + (long long)c * out_stride, (float)f->scale_re, f->sm_count, s);
                 if (st) return st;
             }
+            f->last_path = 1;
             return SGPU_OK;
         }
     }

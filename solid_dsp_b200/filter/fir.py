@@ -127,6 +127,11 @@ class FIRFilter(_FirHandle):
     def execute_block(self, samples):  # fir/mod.rs:235
         return self._run(lib.sgpu_fir_execute_block, samples, lambda n: lib.sgpu_fir_out_len(self._h, n))
 
+    @property
+    def last_path(self) -> str:
+        """'tensor' when the last execute_block ran on the tcgen05 kernel (long real-tap filters), else 'ffma'."""
+        return "tensor" if lib.sgpu_fir_last_path(self._h) == 1 else "ffma"
+
     def write(self, samples):  # Window::write on the filter's history (window/mod.rs:73)
         ib = InBuf(samples, self._C)
         check(lib.sgpu_fir_write(self._h, ib.ptr, ib.n, ib.stride, ib.mem, ib.stream))

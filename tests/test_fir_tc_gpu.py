@@ -1,0 +1,151 @@
+"""GPU parity for the tensor-core FIR (csrc/fir_tc.cu): long real-tap filters on tcgen05 as a banded-Toeplitz
+product with a 3 x TF32 split.  Same bar as the FFMA2 kernels: max normalised error <= 1e-5 against the f64
+oracle on identical f32-rounded inputs, exact output counts, exact alignment, streaming across calls."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests._util import TOL, f32_taps, nerr
+
+pytestmark = pytest.mark.gpu
+
+N_MIN = 1 << 21  # the dispatcher sends shorter calls to the FFMA2 kernel
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+@pytest.fixture(scope="module")
+def FIR():
+    from solid_dsp_b200.filter.fir import FIRFilter
+    return FIRFilter
+
+
+def _rand(torch, n, seed, lo=-1.0, hi=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.empty(n, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).uniform_(lo, hi, generator=g)
+    return x
+
+
+def _check_windows(h, x, y, starts, width=2048, hist=None):
+    T = len(h)
+    worst = 0.0
+    for start in starts:
+        lo = max(0, start - (T - 1))
+        seg = x[lo:start + width].cpu().numpy()
+        if hist is not None and start - (T - 1) < 0:
+            need = (T - 1) - start
+            seg = np.concatenate([hist[len(hist) - need:], seg])
+            ref = O.fir_fast(h, seg)[need + start - lo:]
+        else:
+            ref = O.fir_fast(h, seg)[start - lo:]
+        got = y[start:start + width].cpu().numpy()
+        worst = max(worst, nerr(got, ref[:len(got)]))
+    return worst
+
+
+@pytest.mark.parametrize("T", [192, 200, 512, 777, 2048])
+def test_parity_random(torch, FIR, T):
+    h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
+    # ragged: last tile partial, not a multiple of 128; 310 tiles = up to 3 tiles per CTA (ring + barrier phases)
+    n = (16384 * 310 if T in (200, 512) else N_MIN) + 12345
+    x = _rand(torch, n, 100 + T)
+    f = FIR(h, 0.5)
+    y = f.execute_block(x)
+    assert f.last_path == "tensor"
+    assert y.shape == (n,)
+    h_scaled = h  # scale applied by the oracle below
+    starts = (0, T - 1, 16384 - 7, 16384 * 100 - 100, n // 2 + 3, n - 2048)
+    worst = 0.0
+    for s in starts:
+        lo = max(0, s - (T - 1))
+        ref = O.fir_fast(h_scaled, x[lo:s + 2048].cpu().numpy(), scale=0.5)[s - lo:]
+        worst = max(worst, nerr(y[s:s + 2048].cpu().numpy(), ref))
+    assert worst <= TOL, worst
+    # the FFMA2 kernel on the same input: two independent implementations agree over the whole stream
+    import os
+    os.environ["SGPU_FIR_TC"] = "0"
+    try:
+        f2 = FIR(h, 0.5)
+        y2 = f2.execute_block(x)
+        assert f2.last_path == "ffma"
+    finally:
+        del os.environ["SGPU_FIR_TC"]
+    assert (y - y2).abs().max().item() <= TOL * y2.abs().max().item()
+
+
+def test_dc_and_positive_taps_bias(torch, FIR):
+    """Worst case for the tensor core's truncating accumulator: all products of one sign (tools/tc_accum_probe.py)."""
+    for T in (512, 4096):
+        h = f32_taps(np.hanning(T + 2)[1:-1] / T)
+        n = N_MIN
+        x = torch.full((n,), 0.7 - 0.3j, dtype=torch.complex64, device="cuda")
+        f = FIR(h, 1.0)
+        y = f.execute_block(x)
+        assert f.last_path == "tensor"
+        assert _check_windows(h, x, y, (0, n // 2, n - 2048)) <= TOL / 4
+
+
+def test_streaming_split_calls(torch, FIR):
+    """concat(execute_block(a), execute_block(b)) == execute_block(a ++ b): the history tail feeds the split planes."""
+    T = 512
+    h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
+    n1, n2, n3 = N_MIN + 5, 1000, N_MIN + 16384 * 3 + 1
+    x = _rand(torch, n1 + n2 + n3, 7)
+    f = FIR(h, 1.0)
+    y1 = f.execute_block(x[:n1])
+    assert f.last_path == "tensor"
+    y2 = f.execute_block(x[n1:n1 + n2])  # short call: FFMA2 kernel, same history buffers
+    assert f.last_path == "ffma"
+    y3 = f.execute_block(x[n1 + n2:])  # odd sample offset: 8-byte aligned input, scalar split path
+    assert f.last_path == "tensor"
+    y = torch.cat([y1, y2, y3])
+    starts = (0, n1 - 300, n1 + n2 - 100, n1 + n2 + 100, n1 + n2 + n3 - 2048)
+    assert _check_windows(h, x, y, starts) <= TOL
+    # state after the calls equals the last T-1 inputs
+    hist, _ = f.get_state()
+    assert np.array_equal(np.asarray(hist).reshape(-1), x[-(T - 1):].cpu().numpy())
+
+
+def test_impulse_alignment_and_zeros(torch, FIR):
+    T = 512
+    h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
+    n = 16384 * 160 + 999
+    x = torch.zeros(n, dtype=torch.complex64, device="cuda")
+    pos = [0, 1151, 2176, 16383, 16384 * 149 + 5, n - 600]  # more than T apart; block and tile boundaries
+    for p in pos:
+        x[p] = 1.0 - 2.0j
+    f = FIR(h, 1.0)
+    y = f.execute_block(x)
+    assert f.last_path == "tensor"
+    hr = h[::-1]
+    for p in pos:
+        got = y[p:p + T].cpu().numpy()
+        ref = hr * (1.0 - 2.0j)
+        assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
+        # a one-sample shift would be unmistakable
+        assert np.max(np.abs(got[1:] - ref[:-1])) > 1e-3 * np.max(np.abs(ref))
+    # exact zeros everywhere else: zero products sum to zero in the tensor core too
+    mask = torch.ones(n, dtype=torch.bool, device="cuda")
+    for p in pos:
+        mask[p:p + T] = False
+    assert int(torch.count_nonzero(y[mask]).item()) == 0
+
+
+def test_two_channels_and_linearity(torch, FIR):
+    T = 256
+    h = f32_taps(O.firdes_kaiser(T, 0.2, 70.0, 0.0))
+    n = N_MIN
+    u, v = _rand(torch, n, 11), _rand(torch, n, 12)
+    f = FIR(h, 1.0, n_channels=2)
+    y = f.execute_block(torch.stack([u, v]))
+    assert f.last_path == "tensor" and y.shape == (2, n)
+    assert _check_windows(h, u, y[0], (0, n - 2048)) <= TOL
+    assert _check_windows(h, v, y[1], (0, n - 2048)) <= TOL
+    w = FIR(h, 1.0).execute_block(0.75 * u - 1.5 * v)
+    lin = 0.75 * y[0] - 1.5 * y[1]
+    assert (w - lin).abs().max().item() <= 4 * TOL * lin.abs().max().item()

@@ -50,7 +50,10 @@ def test_config2_fir_full_stream(torch_cuda):
     y = FIRFilter(h, 1.0).execute_block(x)
     hr = h[::-1].astype(np.complex64)
     for p in pos:
-        assert np.array_equal(_window(y, p, p + 512), hr)
+        got = _window(y, p, p + 512)
+        # tensor-core path: taps enter as TF32 hi + lo, exact to 2^-22; a one-sample shift is off by > 1e-3
+        assert np.max(np.abs(got - hr)) <= 1e-6 * np.max(np.abs(hr))
+        assert np.max(np.abs(got[1:] - hr[:-1])) > 1e-3 * np.max(np.abs(hr))
     assert int(torch.count_nonzero(y).item()) == 3 * int(np.count_nonzero(hr))
     # linearity on the full stream: F(a*u + b*v) = a*F(u) + b*F(v), checked on reductions of the whole output
     del y

@@ -12,8 +12,12 @@ from solid_dsp_b200.filter.fir import FIRFilter  # noqa: E402
 from tests._util import f32_taps, nerr  # noqa: E402
 
 
+MODES = {"ffma": ("0", "4"), "tc-v1": ("2", "4"), "tc-fused-c4": ("1", "4"), "tc-fused-c2": ("1", "2"),
+         "tc-fused-c8": ("1", "8"), "tc-fused-c1": ("1", "1")}
+
+
 def run(h, x, tc, reps=3):
-    os.environ["SGPU_FIR_TC"] = "1" if tc else "0"
+    os.environ["SGPU_FIR_TC"], os.environ["SGPU_FIR_TC_CHAIN"] = MODES[tc]
     f = FIRFilter(h, 1.0)
     y = f.execute_block(x)  # warm-up (allocates scratch), from zero history
     torch.cuda.synchronize()
@@ -32,14 +36,14 @@ def run(h, x, tc, reps=3):
 def main():
     logs = [int(a) for a in sys.argv[1:]] or [22, 26]
     g = torch.Generator(device="cuda").manual_seed(2)
-    for T in (512, 256, 1024, 200):
+    for T in (512, 256, 2048):
         h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
         for lg in logs:
             n = 1 << lg
             x = torch.empty(n, dtype=torch.complex64, device="cuda")
             torch.view_as_real(x).uniform_(-1, 1, generator=g)
             res = {}
-            for tc in (0, 1):
+            for tc in MODES:
                 try:
                     y, ms = run(h, x, tc)
                 except Exception as e:  # noqa: BLE001
@@ -53,9 +57,10 @@ def main():
                 res[tc] = y
                 print(f"T={T} n=2^{lg} tc={tc}: {ms:.3f} ms  {n / ms / 1e6:.1f} Gsamp/s  nerr(windows)={max(errs):.3e}",
                       flush=True)
-            if 0 in res and 1 in res:
-                d = (res[0] - res[1]).abs().max().item() / res[0].abs().max().item()
-                print(f"T={T} n=2^{lg} max|tc - ffma| / max|ffma| over the whole stream = {d:.3e}", flush=True)
+            for k in res:
+                if k != "ffma" and "ffma" in res:
+                    d = (res["ffma"] - res[k]).abs().max().item() / res["ffma"].abs().max().item()
+                    print(f"T={T} n=2^{lg} max|{k} - ffma| / max|ffma| over the whole stream = {d:.3e}", flush=True)
             del x, res
 
 
