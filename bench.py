@@ -386,8 +386,8 @@ def run_gpu_arm(args):
         t_fma = W["flop_per_unit"] / (peak_fma * 1e12)
         t_hbm = W["bytes_per_unit"] / (hbm_peak * 1e9)
         bound = "fma" if t_fma >= t_hbm else "hbm"
-        # Long real-tap FIR: the library runs it on the tcgen05 tensor cores (csrc/fir_tc.cu, 3 x TF32 over a
-        # banded-Toeplitz GEMM), so the binding roofline is the tensor pipe: TF32 dense = half the measured bf16 rate.
+        # Long real-tap FIR: the library runs it on the tcgen05 tensor cores (csrc/fir_tc.cu, BF16x3 over a
+        # banded-Toeplitz GEMM), so the binding roofline is the tensor pipe (measured bf16 dense rate).
         tensor = None
         if name == "fir" and getattr(filt, "last_path", "ffma") == "tensor":
             bf16_peak, bf16_src = 1590.0, "fallback (B200_PROFILING.md)"
@@ -398,14 +398,18 @@ def run_gpu_arm(args):
                             "back to back under the power cap)")
             T_ = len(taps)
             koff = (T_ - 1 + 31) // 32 * 32
-            executed = 3.0 * (koff + 128) / T_  # 3 TF32 MMAs per K step over a band of Koff + 128 columns per 128 outputs
-            tf32_peak = bf16_peak / 2.0
-            tensor = {"achieved_tflops": ach_tflops, "peak_tflops": tf32_peak, "frac": ach_tflops / tf32_peak,
-                      "peak_source": "TF32 dense = bf16 / 2; bf16: " + bf16_src,
-                      "executed_tflops": ach_tflops * executed, "executed_frac": ach_tflops * executed / tf32_peak,
-                      "executed_over_algorithmic": executed,
-                      "note": "algorithmic flops = 4 per real x complex tap; the tensor pipe executes 3 (hi*hi, lo*hi, "
-                              "hi*lo) x (Koff+128)/T (band zeros) times that"}
+            band = (koff + 128) / T_            # band of Koff + 128 columns per 128 outputs, zeros included
+            # one f32-accurate real product = 6 bf16 products (b1b1, b1b2, b2b1, b2b2, b1b3, b3b1), so the pipe's
+            # f32-equivalent peak is the measured bf16 rate / 6; `executed` counts every bf16 flop the pipe really does
+            executed = 6.0 * band
+            f32_eq_peak = bf16_peak / 6.0
+            tensor = {"achieved_tflops": ach_tflops, "peak_tflops": f32_eq_peak, "frac": ach_tflops / f32_eq_peak,
+                      "peak_source": "f32-equivalent tensor peak = bf16 dense / 6 (BF16x3 split: 6 bf16 MMAs per f32 product); bf16: " + bf16_src,
+                      "bf16_peak_tflops": bf16_peak,
+                      "executed_bf16_tflops": ach_tflops * executed, "executed_frac_of_bf16_peak": ach_tflops * executed / bf16_peak,
+                      "executed_over_algorithmic": executed, "band_overhead": band,
+                      "note": "algorithmic flops = 4 per real x complex tap; the tensor pipe executes 6 bf16 MMAs per K step "
+                              "over a band of (Koff+128)/T columns (Toeplitz zeros), i.e. 6 x band times the algorithmic flops"}
             bound = "tensor"
         # DRAM bytes (read + write) of one launch of the dominant kernel at this workload's full size,
         # from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture
@@ -425,7 +429,7 @@ def run_gpu_arm(args):
                      "tensor": tensor and tensor["frac"]}[bound],
             "traffic": traffic,
             "traffic_detail": traffic_detail,
-            "kernel": {"fir": "fir_tc_fused_kernel (tcgen05, 3xTF32)" if tensor else "fir_warp_kernel<R=16>", "decim": "fir_decim_kernel<R=16>",
+            "kernel": {"fir": "fir_tc_fused_kernel<BF16x3> (tcgen05.mma kind::f16, TMA, TMEM)" if tensor else "fir_warp_kernel<R=16>", "decim": "fir_decim_kernel<R=16>",
                        "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
                        "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)",
                        "autocorr": "autocorr_kernel"}[name],
@@ -449,7 +453,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "f32 (3xTF32 split on the tensor cores, f32 accumulation)" if tensor else "f32", "data": "synthetic",
+            "dtype": "f32 (BF16x3 split on the tensor cores: 6 bf16 MMAs per product, f32 accumulation)" if tensor else "f32", "data": "synthetic",
             "config": {"workload": W["desc"], "name": name, **shape_desc,
                        "l2": "inputs (>= 2 GiB per rank) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"stream segments x{world} with halo" if name in ("fir", "iir_scan") else f"channels x{world}"},

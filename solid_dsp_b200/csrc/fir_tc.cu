@@ -145,7 +145,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return d;
 }
 // kind::tf32, A and B K-major, D f32, M = 128, N = 256
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -285,9 +285,9 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                     for (int kk = 0; kk < kKC / kUK; ++kk) {
                         const uint64_t off = (uint64_t)(kk * kUK * 4 >> 4);
-                        umma_tf32(d, a_hi + off, b_hi + off, kIdesc, (q | kk) != 0 ? 1u : 0u);
-                        umma_tf32(d, a_lo + off, b_hi + off, kIdesc, 1u);
-                        umma_tf32(d, a_hi + off, b_lo + off, kIdesc, 1u);
+                        umma_tf32(d, a_hi + off, b_hi + off, kIdescTf32, (q | kk) != 0 ? 1u : 0u);
+                        umma_tf32(d, a_lo + off, b_hi + off, kIdescTf32, 1u);
+                        umma_tf32(d, a_hi + off, b_lo + off, kIdescTf32, 1u);
                     }
                     umma_commit(empty_bar(stage));  // smem stage free once these MMAs have read it
                     if (++stage == kStages) {
@@ -354,80 +354,202 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 constexpr int kEpiWarps = 8;
 constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
 
+// Operand format of the fused kernel.
+//   TF32x3: hi/lo TF32 planes (4 B), 3 MMAs per K step of 8, SWIZZLE_128B rows of 32 floats, 96 KB per K chunk of 32.
+//   BF16x3: b1/b2/b3 bf16 planes (2 B), 6 MMAs per K step of 16 (b1*b1, b1*b2, b2*b1, b2*b2, b1*b3, b3*b1: every
+//           product down to 2^-24 relative), SWIZZLE_64B rows of 32 bf16, 72 KB per K chunk of 32: the same tensor
+//           time per K (bf16 runs at twice the TF32 rate), 25 % less L2 -> shared-memory traffic, three stages.
+template <bool BF>
+struct Fmt {
+    static constexpr int kParts = BF ? 3 : 2;                       // planes per operand
+    static constexpr int kElem = BF ? 2 : 4;                        // bytes per element
+    static constexpr int kRowBytes = kKC * kElem;                   // 64 / 128: the swizzle span
+    static constexpr int kAPart = kBM * kRowBytes;                  // one A plane of a stage
+    static constexpr int kBPart = kBN * kRowBytes;                  // one B plane (re rows then im rows) of a stage
+    static constexpr int kA = kParts * kAPart;
+    static constexpr int kStage = kParts * (kAPart + kBPart);       // 73728 / 98304
+    static constexpr int kNStages = BF ? 3 : 2;
+    static constexpr int kKSteps = BF ? 2 : 4;                      // UMMAs along K per chunk (32-byte steps)
+    static constexpr size_t kSmem = (size_t)kNStages * kStage + 1024 + 256;
+    static constexpr uint32_t kIdesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24))
+                                          : kIdescTf32;
+};
+
+// K-major SWIZZLE_64B descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 struct TcFusedArgs {
     const float2 *in;
     long long n_in;
     const float2 *hist;  // last T-1 inputs of the previous call, oldest first
     int H;               // T-1
     float2 *out;
-    float *scratch;      // [gridDim.x * 2][4][tile_plane]
-    int tile_plane;      // floats per plane of one tile buffer = Koff + 16384
+    void *scratch;       // [gridDim.x * 2][2 * parts][tile_plane] elements
+    int tile_plane;      // elements per plane of one tile buffer = Koff + 16384 rounded up to 128
     int Koff;
     int ntiles, nchunks, gchunks, ngroups;
-    int slice;           // plane positions converted per chain flush (multiple of 4)
+    int slice;           // plane positions converted per chain flush (multiple of 8)
     int vec_ok;
     float scale;
 };
 
+__device__ __forceinline__ float2 tc_fetch(const TcFusedArgs &a, long long i) {
+    if (i >= 0) return i < a.n_in ? a.in[i] : make_float2(0.f, 0.f);
+    const long long h = (long long)a.H + i;  // window/mod.rs:63-71: the history tail, oldest first
+    return h >= 0 ? a.hist[h] : make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ uint32_t bf16_pair(float lo, float hi) {  // two bf16 (round to nearest even) in one word
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// L2 residency hints: the split ring (60-80 MB, rewritten every other tile) should stay in the 126 MB L2 while the
+// sample streams pass through once (ncu without hints: 19.5 GB of DRAM writes for 8.6 GB of output at 2^30 samples)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint_v4(void *ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_hint_v2(void *ptr, float a, float b, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(ptr), "f"(a), "f"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+
 // plane positions [q0, q1) of tile `tile`: position q holds stream sample tile*16384 - Koff + q
-__device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, float *__restrict__ dst, int q0, int q1,
-                                               int et) {
+template <bool BF>
+__device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
+                                               int et, uint64_t pol_ring, uint64_t pol_stream) {
     const long long pbase = (long long)tile * kTileSamples - a.Koff;
-    for (int q = q0 + 4 * et; q < q1; q += 4 * 32 * kEpiWarps) {
-        const long long p = pbase + q;
-        float2 v[4];
-        if (a.vec_ok && p >= 0 && p + 3 < a.n_in) {
-            const float4 x0 = __ldg(reinterpret_cast<const float4 *>(a.in + p));
-            const float4 x1 = __ldg(reinterpret_cast<const float4 *>(a.in + p + 2));
-            v[0] = make_float2(x0.x, x0.y);
-            v[1] = make_float2(x0.z, x0.w);
-            v[2] = make_float2(x1.x, x1.y);
-            v[3] = make_float2(x1.z, x1.w);
-        } else {
+    if constexpr (!BF) {
+        float *__restrict__ dst = reinterpret_cast<float *>(dstv);
+        for (int q = q0 + 4 * et; q < q1; q += 4 * 32 * kEpiWarps) {
+            const long long p = pbase + q;
+            float2 v[4];
+            if (a.vec_ok && p >= 0 && p + 3 < a.n_in) {
+                const float4 x0 = ld_hint_v4(a.in + p, pol_stream);
+                const float4 x1 = ld_hint_v4(a.in + p + 2, pol_stream);
+                v[0] = make_float2(x0.x, x0.y);
+                v[1] = make_float2(x0.z, x0.w);
+                v[2] = make_float2(x1.x, x1.y);
+                v[3] = make_float2(x1.z, x1.w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = tc_fetch(a, p + e);
+            }
+            float rh[4], ih[4], rl[4], il[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const long long i = p + e;
-                if (i >= 0) v[e] = i < a.n_in ? a.in[i] : make_float2(0.f, 0.f);
-                else {
-                    const long long h = (long long)a.H + i;
-                    v[e] = h >= 0 ? a.hist[h] : make_float2(0.f, 0.f);
+                rh[e] = rn_tf32(v[e].x);
+                ih[e] = rn_tf32(v[e].y);
+                rl[e] = rn_tf32(v[e].x - rh[e]);
+                il[e] = rn_tf32(v[e].y - ih[e]);
+            }
+#define SGPU_U(x) __float_as_uint(x)
+            st_hint_v4(dst + q, SGPU_U(rh[0]), SGPU_U(rh[1]), SGPU_U(rh[2]), SGPU_U(rh[3]), pol_ring);
+            st_hint_v4(dst + a.tile_plane + q, SGPU_U(ih[0]), SGPU_U(ih[1]), SGPU_U(ih[2]), SGPU_U(ih[3]), pol_ring);
+            st_hint_v4(dst + 2 * a.tile_plane + q, SGPU_U(rl[0]), SGPU_U(rl[1]), SGPU_U(rl[2]), SGPU_U(rl[3]), pol_ring);
+            st_hint_v4(dst + 3 * a.tile_plane + q, SGPU_U(il[0]), SGPU_U(il[1]), SGPU_U(il[2]), SGPU_U(il[3]), pol_ring);
+#undef SGPU_U
+        }
+    } else {
+        uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
+        for (int q = q0 + 8 * et; q < q1; q += 8 * 32 * kEpiWarps) {
+            const long long p = pbase + q;
+            float re[8], im[8];
+            if (a.vec_ok && p >= 0 && p + 7 < a.n_in) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 x = ld_hint_v4(a.in + p + 2 * e, pol_stream);
+                    re[2 * e] = x.x;
+                    im[2 * e] = x.y;
+                    re[2 * e + 1] = x.z;
+                    im[2 * e + 1] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float2 v = tc_fetch(a, p + e);
+                    re[e] = v.x;
+                    im[e] = v.y;
                 }
             }
-        }
-        float rh[4], ih[4], rl[4], il[4];
+            // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            rh[e] = rn_tf32(v[e].x);
-            ih[e] = rn_tf32(v[e].y);
-            rl[e] = rn_tf32(v[e].x - rh[e]);
-            il[e] = rn_tf32(v[e].y - ih[e]);
+            for (int part = 0; part < 3; ++part) {
+                uint32_t wr[4], wi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    wr[e] = bf16_pair(re[2 * e], re[2 * e + 1]);
+                    wi[e] = bf16_pair(im[2 * e], im[2 * e + 1]);
+                    re[2 * e] -= __uint_as_float(wr[e] << 16);
+                    re[2 * e + 1] -= __uint_as_float(wr[e] & 0xFFFF0000u);
+                    im[2 * e] -= __uint_as_float(wi[e] << 16);
+                    im[2 * e + 1] -= __uint_as_float(wi[e] & 0xFFFF0000u);
+                }
+                st_hint_v4(dst + (size_t)(2 * part) * a.tile_plane + q, wr[0], wr[1], wr[2], wr[3], pol_ring);
+                st_hint_v4(dst + (size_t)(2 * part + 1) * a.tile_plane + q, wi[0], wi[1], wi[2], wi[3], pol_ring);
+            }
         }
-        *reinterpret_cast<float4 *>(dst + q) = make_float4(rh[0], rh[1], rh[2], rh[3]);
-        *reinterpret_cast<float4 *>(dst + a.tile_plane + q) = make_float4(ih[0], ih[1], ih[2], ih[3]);
-        *reinterpret_cast<float4 *>(dst + 2 * a.tile_plane + q) = make_float4(rl[0], rl[1], rl[2], rl[3]);
-        *reinterpret_cast<float4 *>(dst + 3 * a.tile_plane + q) = make_float4(il[0], il[1], il[2], il[3]);
     }
 }
 
+template <bool BF>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcFusedArgs a) {
+    using F = Fmt<BF>;
+    constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + kStages * kStageBytes;
+    const uint32_t bars = base + NS * F::kStage;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-    auto tfull_bar = [&](int i) { return bars + 8u * (2 * kStages + i); };
-    auto tempty_bar = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
-    auto ready_bar = [&](int i) { return bars + 8u * (2 * kStages + 4 + i); };
-    const uint32_t tmem_slot = bars + 8u * (2 * kStages + 6);
-    auto stage_a = [&](int s) { return base + (uint32_t)s * kStageBytes; };
-    auto stage_b = [&](int s) { return base + (uint32_t)s * kStageBytes + kABytes; };
+    auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
+    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };
+    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
+    auto ready_bar = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
+    const uint32_t tmem_slot = bars + 8u * (2 * NS + 6);
+    auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
+    auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -460,10 +582,11 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int buf = 2 * (int)blockIdx.x + (it & 1);
                 for (int q = 0; q < a.nchunks; ++q) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), kStageBytes);
-                    tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
+                    mbar_expect_tx(full_bar(stage), F::kStage);
+                    if constexpr (BF) tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
+                    else tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
                     tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & 3) * kKC, q >> 2, 0, buf);
-                    if (++stage == kStages) {
+                    if (++stage == NS) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -484,19 +607,38 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int q = q0; q < q1; ++q) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint64_t a_hi = umma_desc(stage_a(stage));
-                        const uint64_t a_lo = umma_desc(stage_a(stage) + kBM * kKC * 4);
-                        const uint64_t b_hi = umma_desc(stage_b(stage));
-                        const uint64_t b_lo = umma_desc(stage_b(stage) + kBN * kKC * 4);
+                        if constexpr (BF) {
+                            uint64_t da[3], db[3];
 #pragma unroll
-                        for (int kk = 0; kk < kKC / kUK; ++kk) {
-                            const uint64_t off = (uint64_t)(kk * kUK * 4 >> 4);
-                            umma_tf32(d, a_hi + off, b_hi + off, kIdesc, (q != q0 || kk != 0) ? 1u : 0u);
-                            umma_tf32(d, a_lo + off, b_hi + off, kIdesc, 1u);
-                            umma_tf32(d, a_hi + off, b_lo + off, kIdesc, 1u);
+                            for (int i = 0; i < 3; ++i) {
+                                da[i] = umma_desc_sw64(stage_a(stage) + i * F::kAPart);
+                                db[i] = umma_desc_sw64(stage_b(stage) + i * F::kBPart);
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < F::kKSteps; ++kk) {
+                                const uint64_t off = (uint64_t)(kk * 32 >> 4);
+                                umma_bf16(d, da[0] + off, db[0] + off, F::kIdesc, (q != q0 || kk != 0) ? 1u : 0u);
+                                umma_bf16(d, da[0] + off, db[1] + off, F::kIdesc, 1u);
+                                umma_bf16(d, da[1] + off, db[0] + off, F::kIdesc, 1u);
+                                umma_bf16(d, da[1] + off, db[1] + off, F::kIdesc, 1u);
+                                umma_bf16(d, da[0] + off, db[2] + off, F::kIdesc, 1u);
+                                umma_bf16(d, da[2] + off, db[0] + off, F::kIdesc, 1u);
+                            }
+                        } else {
+                            const uint64_t a_hi = umma_desc(stage_a(stage));
+                            const uint64_t a_lo = umma_desc(stage_a(stage) + F::kAPart);
+                            const uint64_t b_hi = umma_desc(stage_b(stage));
+                            const uint64_t b_lo = umma_desc(stage_b(stage) + F::kBPart);
+#pragma unroll
+                            for (int kk = 0; kk < F::kKSteps; ++kk) {
+                                const uint64_t off = (uint64_t)(kk * 32 >> 4);
+                                umma_tf32(d, a_hi + off, b_hi + off, F::kIdesc, (q != q0 || kk != 0) ? 1u : 0u);
+                                umma_tf32(d, a_lo + off, b_hi + off, F::kIdesc, 1u);
+                                umma_tf32(d, a_hi + off, b_lo + off, F::kIdesc, 1u);
+                            }
                         }
                         umma_commit(empty_bar(stage));
-                        if (++stage == kStages) {
+                        if (++stage == NS) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -511,10 +653,12 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int half = ew >> 2;       // blocks [64 half, 64 half + 64) of the tile
         const int et = ew * 32 + lane;  // 0..255
         const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
-        float *ring = a.scratch + (size_t)(2 * blockIdx.x) * 4 * a.tile_plane;
+        const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
+        uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(2 * blockIdx.x) * buf_bytes;
+        const uint64_t pol_ring = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
         // first tile of this CTA: split it now
         if ((int)blockIdx.x < a.ntiles) {
-            tc_split_range(a, blockIdx.x, ring, 0, a.tile_plane, et);
+            tc_split_range<BF>(a, blockIdx.x, ring, 0, a.tile_plane, et, pol_ring, pol_stream);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(ready_bar(0));
@@ -523,7 +667,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int it = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
             const int next = tile + gridDim.x;
-            float *nbuf = ring + (size_t)((it + 1) & 1) * 4 * a.tile_plane;
+            uint8_t *nbuf = ring + (size_t)((it + 1) & 1) * buf_bytes;
             float accr[64], acci[64];
 #pragma unroll
             for (int i = 0; i < 64; ++i) accr[i] = acci[i] = 0.f;
@@ -549,7 +693,9 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
                 // between two flushes: one slice of the next tile's planes (its buffer was last read by tile
                 // it-1, whose loads all completed before this tile's first chain could finish)
-                if (next < a.ntiles) tc_split_range(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et);
+                if (next < a.ntiles)
+                    tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
+                                       pol_stream);
             }
             if (next < a.ntiles) {
                 fence_proxy_async();
@@ -560,7 +706,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
                 const long long n = n0 + (long long)i * kBM;
-                if (n < a.n_in) a.out[n] = make_float2(accr[i] * a.scale, acci[i] * a.scale);  // fir/mod.rs:211
+                if (n < a.n_in) st_hint_v2(a.out + n, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
             }
         }
     }
@@ -590,6 +736,19 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+uint16_t host_bf16_rne(float x) {  // cvt.rn.bf16.f32 (round to nearest even), finite inputs
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float host_bf16_to_f32(uint16_t b) {
+    const uint32_t u = (uint32_t)b << 16;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
 float host_rn_tf32(float x) {
     uint32_t u;
     memcpy(&u, &x, 4);
@@ -608,11 +767,13 @@ struct FirTcState {
     long long plane_cap = 0;     // floats per plane allocated
     CUtensorMap tmA;
     bool smem_set = false;
-    // fused kernel: per-CTA ring of two split tile buffers
-    float *d_ring = nullptr;
-    int ring_ctas = 0, tile_plane = 0;
+    // fused kernel: per-CTA ring of two split tile buffers (format: 0 = TF32x3, 1 = BF16x3)
+    void *d_ring = nullptr;
+    int ring_ctas = 0, tile_plane = 0, ring_fmt = -1;
     CUtensorMap tmRing;
-    bool fused_smem_set = false;
+    bool fused_smem_set[2] = {false, false};
+    uint16_t *d_A16 = nullptr;   // [3][128][K] bf16: b1, b2, b3 of the band
+    CUtensorMap tmA16;
 };
 
 int fir_tc_create(FirTcState **out, const float *taps, int T) {
@@ -654,6 +815,36 @@ int fir_tc_create(FirTcState **out, const float *taps, int T) {
         fir_tc_destroy(st);
         return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
+    {   // bf16 x 3 band for the BF16x3 format of the fused kernel
+        std::vector<uint16_t> A16((size_t)3 * kBM * st->K, 0);
+        for (int m = 0; m < kBM; ++m)
+            for (int k = 0; k < st->K; ++k) {
+                const int i = m + st->Koff - k;
+                if (i < 0 || i >= T) continue;
+                float g = taps[T - 1 - i];
+                for (int part = 0; part < 3; ++part) {
+                    const uint16_t b = host_bf16_rne(g);
+                    A16[((size_t)part * kBM + m) * st->K + k] = b;
+                    g -= host_bf16_to_f32(b);
+                }
+            }
+        if (cudaMalloc(&st->d_A16, A16.size() * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMemcpy(st->d_A16, A16.data(), A16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            fir_tc_destroy(st);
+            return fail(SGPU_ERR_CUDA, "upload of the bf16 banded tap matrix failed");
+        }
+        const cuuint64_t gdim3[3] = {(cuuint64_t)st->K, (cuuint64_t)kBM, 3};
+        const cuuint64_t gstr3[2] = {(cuuint64_t)st->K * 2, (cuuint64_t)st->K * 2 * kBM};
+        const cuuint32_t box3[3] = {kKC, kBM, 3};
+        const cuuint32_t estr3[3] = {1, 1, 1};
+        const CUresult r3 = enc(&st->tmA16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, st->d_A16, gdim3, gstr3, box3, estr3,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r3 != CUDA_SUCCESS) {
+            fir_tc_destroy(st);
+            return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A bf16) failed: %d", (int)r3);
+        }
+    }
     *out = st;
     return SGPU_OK;
 }
@@ -663,6 +854,7 @@ void fir_tc_destroy(FirTcState *st) {
     if (st->d_A) cudaFree(st->d_A);
     if (st->d_planes) cudaFree(st->d_planes);
     if (st->d_ring) cudaFree(st->d_ring);
+    if (st->d_A16) cudaFree(st->d_A16);
     delete st;
 }
 
@@ -673,28 +865,47 @@ int env_i(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+template <bool BF>
+int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, cudaStream_t s) {
+    using F = Fmt<BF>;
+    if (!st->fused_smem_set[BF]) {
+        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem));
+        st->fused_smem_set[BF] = true;
+    }
+    fir_tc_fused_kernel<BF><<<grid, kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA, st->tmRing, a);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
+    return SGPU_OK;
+}
+
 int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const float2 *hist, float2 *out, float scale,
                      int sm_count, cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
-    if (!st->fused_smem_set) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        st->fused_smem_set = true;
-    }
+    const char *fe = getenv("SGPU_FIR_TC_FMT");
+    const int fmt = (fe && fe[0] == 't') ? 0 : 1;  // default BF16x3; SGPU_FIR_TC_FMT=tf32 selects TF32x3
+    const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kTileSamples), kBM);
-    if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane) {
-        if (st->d_ring) cudaFree(st->d_ring);
+    if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt) {
+        if (st->d_ring) {
+            SGPU_CUDA(cudaStreamSynchronize(s));
+            cudaFree(st->d_ring);
+        }
         st->d_ring = nullptr;
-        const size_t bytes = (size_t)sm_count * 2 * 4 * tile_plane * sizeof(float);
+        const size_t bytes = (size_t)sm_count * 2 * 2 * parts * tile_plane * elem;
         if (cudaMalloc(&st->d_ring, bytes) != cudaSuccess)
             return fail(SGPU_ERR_CUDA, "cudaMalloc(split ring, %zu bytes) failed", bytes);
         st->ring_ctas = sm_count;
         st->tile_plane = tile_plane;
-        const cuuint64_t gdim[4] = {(cuuint64_t)kBM, (cuuint64_t)(tile_plane / kBM), 4, (cuuint64_t)(2 * sm_count)};
-        const cuuint64_t gstr[3] = {(cuuint64_t)kBM * 4, (cuuint64_t)tile_plane * 4, (cuuint64_t)tile_plane * 16};
-        const cuuint32_t box[4] = {kKC, kNB, 4, 1};
+        st->ring_fmt = fmt;
+        const cuuint64_t gdim[4] = {(cuuint64_t)kBM, (cuuint64_t)(tile_plane / kBM), (cuuint64_t)(2 * parts),
+                                    (cuuint64_t)(2 * sm_count)};
+        const cuuint64_t gstr[3] = {(cuuint64_t)kBM * elem, (cuuint64_t)tile_plane * elem,
+                                    (cuuint64_t)tile_plane * elem * 2 * parts};
+        const cuuint32_t box[4] = {kKC, kNB, (cuuint32_t)(2 * parts), 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = enc(&st->tmRing, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->d_ring, gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        const CUresult r = enc(&st->tmRing, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                               st->d_ring, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               fmt ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed: %d", (int)r);
     }
@@ -711,14 +922,11 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const flo
     a.nchunks = st->nchunks;
     a.gchunks = std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
     a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
-    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.ngroups), 4);
+    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.ngroups), 8);
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     a.scale = scale;
     const int grid = std::min(a.ntiles, sm_count);
-    fir_tc_fused_kernel<<<grid, kFusedThreads, kSmemBytes, s>>>(st->tmA, st->tmRing, a);
-    SGPU_LAUNCH_CHECK();
-    count_launch();
-    return SGPU_OK;
+    return fmt ? fir_tc_launch_fused<true>(st, a, grid, s) : fir_tc_launch_fused<false>(st, a, grid, s);
 }
 
 }  // namespace

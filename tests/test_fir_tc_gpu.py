@@ -18,10 +18,14 @@ def torch():
     return t
 
 
-@pytest.fixture(scope="module")
-def FIR():
+@pytest.fixture(scope="module", params=["bf16", "tf32"])
+def FIR(request):
+    """Both operand formats of the fused kernel: BF16x3 (default) and TF32x3 (SGPU_FIR_TC_FMT=tf32)."""
+    import os
     from solid_dsp_b200.filter.fir import FIRFilter
-    return FIRFilter
+    os.environ["SGPU_FIR_TC_FMT"] = request.param
+    yield FIRFilter
+    del os.environ["SGPU_FIR_TC_FMT"]
 
 
 def _rand(torch, n, seed, lo=-1.0, hi=1.0):

@@ -12,12 +12,12 @@ from solid_dsp_b200.filter.fir import FIRFilter  # noqa: E402
 from tests._util import f32_taps, nerr  # noqa: E402
 
 
-MODES = {"ffma": ("0", "4"), "tc-v1": ("2", "4"), "tc-fused-c4": ("1", "4"), "tc-fused-c2": ("1", "2"),
-         "tc-fused-c8": ("1", "8"), "tc-fused-c1": ("1", "1")}
+MODES = {"ffma": ("0", "2", "tf32"), "tc-tf32-c2": ("1", "2", "tf32"), "tc-bf16-c2": ("1", "2", "bf16"),
+         "tc-bf16-c4": ("1", "4", "bf16"), "tc-bf16-c1": ("1", "1", "bf16")}
 
 
 def run(h, x, tc, reps=3):
-    os.environ["SGPU_FIR_TC"], os.environ["SGPU_FIR_TC_CHAIN"] = MODES[tc]
+    os.environ["SGPU_FIR_TC"], os.environ["SGPU_FIR_TC_CHAIN"], os.environ["SGPU_FIR_TC_FMT"] = MODES[tc]
     f = FIRFilter(h, 1.0)
     y = f.execute_block(x)  # warm-up (allocates scratch), from zero history
     torch.cuda.synchronize()
