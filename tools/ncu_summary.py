@@ -21,6 +21,11 @@ KEYS = [
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe active %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+    ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "tcgen05 (UTCMMA) pipe active %"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "tensor-core smem operand wavefronts % of peak"),
+    ("l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "TMA load bytes (L2 -> smem)"),
+    ("l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second", "TMA load rate"),
+    ("smsp__cycles_elapsed.avg.per_second", "SM clock during the capture"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__cycles_elapsed.avg", "SM cycles"),
