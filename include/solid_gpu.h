@@ -166,6 +166,7 @@ int sgpu_interp_get_scale(const sgpu_interp *f, double *re, double *im);/* inter
 size_t sgpu_interp_interpolation(const sgpu_interp *f);                  /* interp.rs:82 / pfb.rs:62 */
 size_t sgpu_interp_sub_len(const sgpu_interp *f);
 size_t sgpu_interp_channels(const sgpu_interp *f);
+int sgpu_interp_last_path(const sgpu_interp *f); /* 0 = FP32 kernels, 1 = tcgen05 tensor cores (see sgpu_fir_last_path) */
 /* InterpolatingFIRFilter::coefficents (interp.rs:77-79): per-phase stored order flattened,
  * L*S values. */
 int sgpu_interp_coefficients(const sgpu_interp *f, double *out);

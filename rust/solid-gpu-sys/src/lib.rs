@@ -91,6 +91,7 @@ extern "C" {
     pub fn sgpu_interp_interpolation(f: *const sgpu_interp) -> size_t;
     pub fn sgpu_interp_sub_len(f: *const sgpu_interp) -> size_t;
     pub fn sgpu_interp_channels(f: *const sgpu_interp) -> size_t;
+    pub fn sgpu_interp_last_path(f: *const sgpu_interp) -> c_int;
     pub fn sgpu_interp_coefficients(f: *const sgpu_interp, out: *mut c_double) -> c_int;
     pub fn sgpu_interp_get_state(f: *mut sgpu_interp, history: *mut c_float) -> c_int;
     pub fn sgpu_interp_set_state(f: *mut sgpu_interp, history: *const c_float) -> c_int;

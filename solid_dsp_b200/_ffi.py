@@ -85,6 +85,7 @@ PROTOTYPES = {
     "sgpu_interp_interpolation": (c_size, [vp]),
     "sgpu_interp_sub_len": (c_size, [vp]),
     "sgpu_interp_channels": (c_size, [vp]),
+    "sgpu_interp_last_path": (C.c_int, [vp]),
     "sgpu_interp_coefficients": (C.c_int, [vp, c_dp]),
     "sgpu_interp_get_state": (C.c_int, [vp, vp]),
     "sgpu_interp_set_state": (C.c_int, [vp, vp]),

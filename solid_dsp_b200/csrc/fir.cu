@@ -662,11 +662,9 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             if (st) return st;
         }
         if (f->tc && !overlap) {
-            for (size_t c = 0; c < f->C; ++c) {
-                int st = fir_tc_run(f->tc, d_in + (long long)c * in_stride, n_in, a.hist + c * (f->T - 1),
-                                    d_out + (long long)c * out_stride, (float)f->scale_re, f->sm_count, s);
-                if (st) return st;
-            }
+            int st = fir_tc_run(f->tc, d_in, n_in, in_stride, a.hist, (int)f->T - 1, d_out, out_stride, f->C,
+                                (float)f->scale_re, f->sm_count, s);
+            if (st) return st;
             f->last_path = 1;
             return SGPU_OK;
         }
@@ -974,6 +972,9 @@ struct sgpu_interp {
     int cur = 0;
     Staging stage;
     HostPipe pipe;
+    FirTcState *tc = nullptr;  // tensor-core path (fir_tc.cu): real taps, L in {2, 4}, sub-filters >= 24 taps
+    bool tc_tried = false;
+    int last_path = 0;
 };
 
 static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S (complex: x2) values */) {
@@ -1064,12 +1065,14 @@ SGPU_EXPORT int sgpu_interp_destroy(sgpu_interp *f) {
     if (f->d_taps) cudaFree(f->d_taps);
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
+    fir_tc_destroy(f->tc);
     f->stage.release();
     f->pipe.release();
     delete f;
     return SGPU_OK;
 }
 
+SGPU_EXPORT int sgpu_interp_last_path(const sgpu_interp *f) { return f ? f->last_path : 0; }
 SGPU_EXPORT size_t sgpu_interp_interpolation(const sgpu_interp *f) { return f ? f->L : 0; }
 SGPU_EXPORT size_t sgpu_interp_sub_len(const sgpu_interp *f) { return f ? f->S : 0; }
 SGPU_EXPORT size_t sgpu_interp_channels(const sgpu_interp *f) { return f ? f->C : 0; }
@@ -1132,6 +1135,27 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     a.vec_out = 0;
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
+    f->last_path = 0;
+    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", 24) &&
+        n_in >= 128 * (128 / (long long)f->L) &&
+        n_out * (long long)f->C >= (long long)env_int("SGPU_INTERP_TC_MIN_OUT", 1 << 23) && env_int("SGPU_FIR_TC", 1)) {
+        // polyphase interpolator as a banded product on the tcgen05 tensor cores (fir_tc.cu): 128 outputs per block
+        // row = 128 / L inputs; HBM-bound instead of FMA-bound for sub-filters of 32 taps and more
+        const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
+        const size_t span_in = (size_t)((f->C - 1) * istr + n_in) * 8, span_out = (size_t)((f->C - 1) * ostr + n_out) * 8;
+        const bool overlap = ib < ob + span_out && ob < ib + span_in;
+        if (!f->tc_tried) {
+            f->tc_tried = true;
+            int st = fir_tc_create_pfb(&f->tc, f->phase_taps.data(), (int)f->L, (int)f->S);
+            if (st) return st;
+        }
+        if (f->tc && !overlap) {
+            int st = fir_tc_run(f->tc, d_in, n_in, istr, a.hist, (int)f->S, d_out, ostr, f->C, 1.f, f->sm_count, s);
+            if (st) return st;
+            f->last_path = 1;
+            return SGPU_OK;
+        }
+    }
     if (!f->complex_taps && f->packed && (f->Qpad == 2 * kR || f->Qpad == kR) &&
         (f->L == 2 || f->L == 4 || f->L == 8 || f->L == 16 || f->L == 32) && env_int("SGPU_WALK", 1)) {
         // walking kernel (fir_walk.cuh): sub-filters of <= 16 / <= 32 taps, one lane per phase, warp-private tiles

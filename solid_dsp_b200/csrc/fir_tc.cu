@@ -397,24 +397,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 
 struct TcFusedArgs {
-    const float2 *in;
-    long long n_in;
-    const float2 *hist;  // last T-1 inputs of the previous call, oldest first
-    int H;               // T-1
-    float2 *out;
-    void *scratch;       // [gridDim.x * 2][2 * parts][tile_plane] elements
-    int tile_plane;      // elements per plane of one tile buffer = Koff + 16384 rounded up to 128
+    const float2 *in;     // [C][in_stride]
+    long long n_in;       // inputs per channel
+    long long in_stride, out_stride;
+    long long n_out;      // outputs per channel = n_in * 128 / R
+    const float2 *hist;   // [C][H]: the last H inputs of the previous call per channel, oldest first
+    int H;                // T-1 for the FIR, S (the PFB window) for the interpolator
+    float2 *out;          // [C][out_stride]
+    void *scratch;        // [gridDim.x * 2][2 * parts][tile_plane] elements
+    int tile_plane;       // elements per plane of one tile buffer = Koff + 128 R rounded up to R
     int Koff;
+    int R, rsh;           // input samples per block row (128 / L); rsh = log2(R / 32)
+    int tiles_per_ch;     // tiles per channel (a tile = 128 blocks = 16384 outputs = 128 R inputs)
     int ntiles, nchunks, gchunks, ngroups;
-    int slice;           // plane positions converted per chain flush (multiple of 8)
+    int slice;            // plane positions converted per chain flush (multiple of 8)
     int vec_ok;
     float scale;
 };
 
-__device__ __forceinline__ float2 tc_fetch(const TcFusedArgs &a, long long i) {
-    if (i >= 0) return i < a.n_in ? a.in[i] : make_float2(0.f, 0.f);
+__device__ __forceinline__ float2 tc_fetch(const TcFusedArgs &a, const float2 *__restrict__ x,
+                                           const float2 *__restrict__ hist, long long i) {
+    if (i >= 0) return i < a.n_in ? x[i] : make_float2(0.f, 0.f);
     const long long h = (long long)a.H + i;  // window/mod.rs:63-71: the history tail, oldest first
-    return h >= 0 ? a.hist[h] : make_float2(0.f, 0.f);
+    return h >= 0 ? hist[h] : make_float2(0.f, 0.f);
 }
 
 __device__ __forceinline__ uint32_t bf16_pair(float lo, float hi) {  // two bf16 (round to nearest even) in one word
@@ -450,26 +455,30 @@ __device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
     return v;
 }
 
-// plane positions [q0, q1) of tile `tile`: position q holds stream sample tile*16384 - Koff + q
+// plane positions [q0, q1) of tile `tile` (channel tile / tiles_per_ch, tile tt inside it): position q holds input
+// sample tt * 128 R - Koff + q of that channel
 template <bool BF>
 __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
                                                int et, uint64_t pol_ring, uint64_t pol_stream) {
-    const long long pbase = (long long)tile * kTileSamples - a.Koff;
+    const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ hist = a.hist + (long long)ch * a.H;
+    const long long pbase = (long long)tt * (kNB * a.R) - a.Koff;
     if constexpr (!BF) {
         float *__restrict__ dst = reinterpret_cast<float *>(dstv);
         for (int q = q0 + 4 * et; q < q1; q += 4 * 32 * kEpiWarps) {
             const long long p = pbase + q;
             float2 v[4];
             if (a.vec_ok && p >= 0 && p + 3 < a.n_in) {
-                const float4 x0 = ld_hint_v4(a.in + p, pol_stream);
-                const float4 x1 = ld_hint_v4(a.in + p + 2, pol_stream);
+                const float4 x0 = ld_hint_v4(x + p, pol_stream);
+                const float4 x1 = ld_hint_v4(x + p + 2, pol_stream);
                 v[0] = make_float2(x0.x, x0.y);
                 v[1] = make_float2(x0.z, x0.w);
                 v[2] = make_float2(x1.x, x1.y);
                 v[3] = make_float2(x1.z, x1.w);
             } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = tc_fetch(a, p + e);
+                for (int e = 0; e < 4; ++e) v[e] = tc_fetch(a, x, hist, p + e);
             }
             float rh[4], ih[4], rl[4], il[4];
 #pragma unroll
@@ -494,16 +503,16 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
             if (a.vec_ok && p >= 0 && p + 7 < a.n_in) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float4 x = ld_hint_v4(a.in + p + 2 * e, pol_stream);
-                    re[2 * e] = x.x;
-                    im[2 * e] = x.y;
-                    re[2 * e + 1] = x.z;
-                    im[2 * e + 1] = x.w;
+                    const float4 xv = ld_hint_v4(x + p + 2 * e, pol_stream);
+                    re[2 * e] = xv.x;
+                    im[2 * e] = xv.y;
+                    re[2 * e + 1] = xv.z;
+                    im[2 * e + 1] = xv.w;
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float2 v = tc_fetch(a, p + e);
+                    const float2 v = tc_fetch(a, x, hist, p + e);
                     re[e] = v.x;
                     im[e] = v.y;
                 }
@@ -585,7 +594,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_expect_tx(full_bar(stage), F::kStage);
                     if constexpr (BF) tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
                     else tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
-                    tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & 3) * kKC, q >> 2, 0, buf);
+                    tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & ((1 << a.rsh) - 1)) * kKC, q >> a.rsh, 0, buf);
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1u;
@@ -702,11 +711,13 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ready_bar((it + 1) & 1));
             }
-            const long long n0 = (long long)tile * kTileSamples + (long long)(half * 64) * kBM + m;
+            const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+            float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
+            const long long n0 = (long long)tt * kTileSamples + (long long)(half * 64) * kBM + m;
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
                 const long long n = n0 + (long long)i * kBM;
-                if (n < a.n_in) st_hint_v2(a.out + n, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
+                if (n < a.n_out) st_hint_v2(y + n, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
             }
         }
     }
@@ -761,7 +772,7 @@ float host_rn_tf32(float x) {
 }  // namespace
 
 struct FirTcState {
-    int T = 0, Koff = 0, K = 0, nchunks = 0;
+    int T = 0 /* taps per phase (S) */, L = 1, R = kBM /* input samples per block of 128 outputs */, Koff = 0, K = 0, nchunks = 0;
     float *d_A = nullptr;        // [256][K]: rows 0..127 = hi, 128..255 = lo
     float *d_planes = nullptr;   // [4][plane_cap]
     long long plane_cap = 0;     // floats per plane allocated
@@ -776,22 +787,34 @@ struct FirTcState {
     CUtensorMap tmA16;
 };
 
-int fir_tc_create(FirTcState **out, const float *taps, int T) {
+// Banded matrix of a polyphase filter bank: output o = L n + p of the stream is sum_j tp[p][j] x[n - j]
+// (pfb.rs:85-90; L = 1, tp[0][j] = h[T-1-j] is the plain FIR).  A block of 128 outputs covers R = 128 / L inputs:
+//     A[m][k] = tp[m mod L][m / L + Koff - k],   B[b][k] = x[R b - Koff + k],   K = Koff + R.
+int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S) {
     *out = nullptr;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SGPU_OK;
+    if (L < 1 || kBM % L != 0 || kBM / L < kKC) return SGPU_OK;  // L = 1, 2, 4: row stride a multiple of the K chunk
     FirTcState *st = new (std::nothrow) FirTcState();
     if (!st) return fail(SGPU_ERR_ALLOC, "out of host memory");
-    st->T = T;
-    st->Koff = (int)round_up((size_t)(T - 1), kKC);
-    st->K = st->Koff + kBM;
+    const int T = S;
+    st->T = S;
+    st->L = L;
+    st->R = kBM / L;
+    st->Koff = (int)round_up((size_t)(S > 1 ? S - 1 : 1), kKC);
+    st->K = st->Koff + st->R;
     st->nchunks = st->K / kKC;
+    auto tap = [&](int m, int k, float &g) -> bool {
+        const int jj = m / L + st->Koff - k;
+        if (jj < 0 || jj >= T) return false;
+        g = tp[(size_t)(m % L) * S + jj];
+        return true;
+    };
     std::vector<float> A((size_t)2 * kBM * st->K, 0.f);
     for (int m = 0; m < kBM; ++m)
         for (int k = 0; k < st->K; ++k) {
-            const int i = m + st->Koff - k;  // tap index of g
-            if (i < 0 || i >= T) continue;
-            const float g = taps[T - 1 - i];
+            float g;
+            if (!tap(m, k, g)) continue;
             const float hi = host_rn_tf32(g);
             A[(size_t)m * st->K + k] = hi;
             A[(size_t)(kBM + m) * st->K + k] = host_rn_tf32(g - hi);
@@ -819,9 +842,8 @@ int fir_tc_create(FirTcState **out, const float *taps, int T) {
         std::vector<uint16_t> A16((size_t)3 * kBM * st->K, 0);
         for (int m = 0; m < kBM; ++m)
             for (int k = 0; k < st->K; ++k) {
-                const int i = m + st->Koff - k;
-                if (i < 0 || i >= T) continue;
-                float g = taps[T - 1 - i];
+                float g;
+                if (!tap(m, k, g)) continue;
                 for (int part = 0; part < 3; ++part) {
                     const uint16_t b = host_bf16_rne(g);
                     A16[((size_t)part * kBM + m) * st->K + k] = b;
@@ -847,6 +869,12 @@ int fir_tc_create(FirTcState **out, const float *taps, int T) {
     }
     *out = st;
     return SGPU_OK;
+}
+
+int fir_tc_create(FirTcState **out, const float *taps, int T) {
+    std::vector<float> tp((size_t)T);
+    for (int jj = 0; jj < T; ++jj) tp[jj] = taps[T - 1 - jj];  // g[j] = h[T-1-j] (fir/mod.rs:86)
+    return fir_tc_create_pfb(out, tp.data(), 1, T);
 }
 
 void fir_tc_destroy(FirTcState *st) {
@@ -878,13 +906,14 @@ int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, cudaStre
     return SGPU_OK;
 }
 
-int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const float2 *hist, float2 *out, float scale,
-                     int sm_count, cudaStream_t s) {
+int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
+                     float2 *out, long long out_stride, size_t C, float scale, int sm_count, cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
     const char *fe = getenv("SGPU_FIR_TC_FMT");
     const int fmt = (fe && fe[0] == 't') ? 0 : 1;  // default BF16x3; SGPU_FIR_TC_FMT=tf32 selects TF32x3
     const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
-    const int tile_plane = (int)round_up((size_t)(st->Koff + kTileSamples), kBM);
+    const int R = st->R;
+    const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
@@ -897,9 +926,9 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const flo
         st->ring_ctas = sm_count;
         st->tile_plane = tile_plane;
         st->ring_fmt = fmt;
-        const cuuint64_t gdim[4] = {(cuuint64_t)kBM, (cuuint64_t)(tile_plane / kBM), (cuuint64_t)(2 * parts),
+        const cuuint64_t gdim[4] = {(cuuint64_t)R, (cuuint64_t)(tile_plane / R), (cuuint64_t)(2 * parts),
                                     (cuuint64_t)(2 * sm_count)};
-        const cuuint64_t gstr[3] = {(cuuint64_t)kBM * elem, (cuuint64_t)tile_plane * elem,
+        const cuuint64_t gstr[3] = {(cuuint64_t)R * elem, (cuuint64_t)tile_plane * elem,
                                     (cuuint64_t)tile_plane * elem * 2 * parts};
         const cuuint32_t box[4] = {kKC, kNB, (cuuint32_t)(2 * parts), 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -909,21 +938,30 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const flo
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed: %d", (int)r);
     }
+    const long long tile_in = (long long)kNB * R;
+    const long long tiles_per_ch = (long long)ceil_div((size_t)n_in, (size_t)tile_in);
+    if (tiles_per_ch * (long long)C >= (1ll << 31)) return fail(SGPU_ERR_UNSUPPORTED, "too many tiles for one launch");
     TcFusedArgs a{};
     a.in = in;
     a.n_in = n_in;
+    a.in_stride = in_stride;
+    a.out_stride = out_stride;
+    a.n_out = n_in * st->L;
     a.hist = hist;
-    a.H = st->T - 1;
+    a.H = H;
     a.out = out;
     a.scratch = st->d_ring;
     a.tile_plane = tile_plane;
     a.Koff = st->Koff;
-    a.ntiles = (int)ceil_div((size_t)n_in, kTileSamples);
+    a.R = R;
+    a.rsh = R == 128 ? 2 : (R == 64 ? 1 : 0);
+    a.tiles_per_ch = (int)tiles_per_ch;
+    a.ntiles = (int)(tiles_per_ch * (long long)C);
     a.nchunks = st->nchunks;
     a.gchunks = std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
     a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
     a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.ngroups), 8);
-    a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
     a.scale = scale;
     const int grid = std::min(a.ntiles, sm_count);
     return fmt ? fir_tc_launch_fused<true>(st, a, grid, s) : fir_tc_launch_fused<false>(st, a, grid, s);
@@ -931,10 +969,11 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, const flo
 
 }  // namespace
 
-int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, const float2 *hist, float2 *out, float scale,
-               int sm_count, cudaStream_t s) {
+int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
+               float2 *out, long long out_stride, size_t C, float scale, int sm_count, cudaStream_t s) {
     if (n_in <= 0) return SGPU_OK;
-    if (env_i("SGPU_FIR_TC", 1) != 2) return fir_tc_run_fused(st, in, n_in, hist, out, scale, sm_count, s);
+    if (env_i("SGPU_FIR_TC", 1) != 2 || C != 1 || st->L != 1)
+        return fir_tc_run_fused(st, in, n_in, in_stride, hist, H, out, out_stride, C, scale, sm_count, s);
     // SGPU_FIR_TC=2: first generation (split pre-pass launch + one accumulation chain per tile), kept for comparison
     EncodeTiledFn enc = encode_fn();
     if (!st->smem_set) {

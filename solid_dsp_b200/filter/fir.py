@@ -288,5 +288,10 @@ class InterpolatingFIRFilter(_InterpHandle):
         L = self.interpolation()
         return self._run(lib.sgpu_interp_execute_block, samples, lambda n: n * L)
 
+    @property
+    def last_path(self) -> str:
+        """'tensor' when the last execute_block ran on the tcgen05 kernel (real taps, L = 2 / 4, long sub-filters)."""
+        return "tensor" if lib.sgpu_interp_last_path(self._h) == 1 else "ffma"
+
     def __str__(self):
         return f"InterpolatingFIR<f32> [Interpolation={self.interpolation()}] [SubLen={self.sub_len()}]"

@@ -153,3 +153,63 @@ def test_two_channels_and_linearity(torch, FIR):
     w = FIR(h, 1.0).execute_block(0.75 * u - 1.5 * v)
     lin = 0.75 * y[0] - 1.5 * y[1]
     assert (w - lin).abs().max().item() <= 4 * TOL * lin.abs().max().item()
+
+
+# ------------------------------------------------------------------ polyphase interpolator on the same kernel
+@pytest.mark.parametrize("L,T", [(4, 128), (2, 128), (4, 100), (4, 1024), (2, 777)])
+def test_interpolator_parity(torch, L, T):
+    """InterpolatingFIRFilter (interp.rs:102-111, pfb.rs:85-90): block rows of 128 / L inputs, exact output count,
+    padded sub-filters (T not a multiple of L), several channels in one launch, ragged tails."""
+    from solid_dsp_b200.filter.fir import InterpolatingFIRFilter
+    h = f32_taps(O.firdes_kaiser(T, 0.5 / L * 0.9, 80.0, 0.0))
+    C = 3
+    n = (1 << 20) + 4321 if T < 1024 else (1 << 19) + 77
+    x = torch.stack([_rand(torch, n, 40 + c) for c in range(C)])
+    f = InterpolatingFIRFilter(h, L, n_channels=C)
+    y = f.execute_block(x)
+    assert f.last_path == "tensor"
+    assert y.shape == (C, n * L)
+    S = f.sub_len()
+    for c in range(C):
+        for start in (0, 5000, n // 2 + 11, n - 3000):
+            lo = max(0, start - S)
+            ref = O.firinterp_fast(h, L, x[c, lo:start + 3000].cpu().numpy())[(start - lo) * L:]
+            got = y[c, start * L:(start + 3000) * L].cpu().numpy()
+            assert nerr(got, ref) <= TOL
+    # same input through the FP32 walking / tile kernels
+    import os
+    os.environ["SGPU_FIR_TC"] = "0"
+    try:
+        f2 = InterpolatingFIRFilter(h, L, n_channels=C)
+        y2 = f2.execute_block(x)
+        assert f2.last_path == "ffma"
+    finally:
+        del os.environ["SGPU_FIR_TC"]
+    assert (y - y2).abs().max().item() <= TOL * y2.abs().max().item()
+
+
+def test_interpolator_streaming_and_impulse(torch):
+    from solid_dsp_b200.filter.fir import InterpolatingFIRFilter
+    L, T = 4, 128
+    h = f32_taps(O.firdes_kaiser(T, 0.5 / L * 0.9, 80.0, 0.0))
+    n1, n2 = (1 << 21) + 3, (1 << 21) + 4096 * 5 + 1
+    x = _rand(torch, n1 + n2, 77)
+    f = InterpolatingFIRFilter(h, L)
+    y = torch.cat([f.execute_block(x[:n1]), f.execute_block(x[n1:])])
+    assert f.last_path == "tensor"
+    S = f.sub_len()
+    for start in (n1 - 100, n1, n1 + 7, n1 + n2 - 2000):
+        lo = start - S
+        ref = O.firinterp_fast(h, L, x[lo:start + 2000].cpu().numpy())[(start - lo) * L:]
+        assert nerr(y[start * L:(start + 2000) * L].cpu().numpy(), ref) <= TOL
+    # impulse at input n0: exact phase alignment against the oracle (a one-sample shift would be unmistakable)
+    f = InterpolatingFIRFilter(h, L)
+    z = torch.zeros(n1, dtype=torch.complex64, device="cuda")
+    n0 = 4096 * 37 + 5
+    z[n0] = 2.0
+    yz = f.execute_block(z)
+    ref = O.firinterp_fast(h, L, z[n0 - S:n0 + S + 8].cpu().numpy())[S * L:]
+    got = yz[n0 * L:(n0 + S + 8) * L].cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
+    assert np.max(np.abs(got[1:] - ref[:-1])) > 1e-3 * np.max(np.abs(ref))
+    assert int(torch.count_nonzero(yz).item()) == int(np.count_nonzero(ref))
