@@ -351,7 +351,8 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 //    flushes (a tile needs Koff + 16384 samples, 132 rows of 128), into a per-CTA ring of two tile buffers in
 //    global memory (148 x 2 x 270 KB = 80 MB: stays in the 126 MB L2).  TMA reads it back as before; HBM sees
 //    8 bytes in and 8 bytes out per sample.
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                          // 4 per TMEM lane quarter
+constexpr int kColsW = kNB / (kEpiWarps / 4);          // blocks (accumulator columns per re / im half) per epilogue warp
 constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
 
 // Operand format of the fused kernel.
@@ -457,7 +458,7 @@ __device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
 
 // plane positions [q0, q1) of tile `tile` (channel tile / tiles_per_ch, tile tt inside it): position q holds input
 // sample tt * 128 R - Koff + q of that channel
-template <bool BF>
+template <bool BF, int U = 1>
 __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
                                                int et, uint64_t pol_ring, uint64_t pol_stream) {
     const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
@@ -497,7 +498,49 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
         }
     } else {
         uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
-        for (int q = q0 + 8 * et; q < q1; q += 8 * 32 * kEpiWarps) {
+        constexpr int kStep = 8 * 32 * kEpiWarps;
+        auto convert_store = [&](int qq, float *re, float *im) {
+            // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                uint32_t wr[4], wi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    wr[e] = bf16_pair(re[2 * e], re[2 * e + 1]);
+                    wi[e] = bf16_pair(im[2 * e], im[2 * e + 1]);
+                    re[2 * e] -= __uint_as_float(wr[e] << 16);
+                    re[2 * e + 1] -= __uint_as_float(wr[e] & 0xFFFF0000u);
+                    im[2 * e] -= __uint_as_float(wi[e] << 16);
+                    im[2 * e + 1] -= __uint_as_float(wi[e] & 0xFFFF0000u);
+                }
+                st_hint_v4(dst + (size_t)(2 * part) * a.tile_plane + qq, wr[0], wr[1], wr[2], wr[3], pol_ring);
+                st_hint_v4(dst + (size_t)(2 * part + 1) * a.tile_plane + qq, wi[0], wi[1], wi[2], wi[3], pol_ring);
+            }
+        };
+        int q = q0 + 8 * et;
+        if constexpr (U > 1) {
+            // U positions per trip, all loads first: the latency of the sample loads is paid once per trip.  Only
+            // for trips that lie entirely inside the call's input; the rest goes through the guarded loop below.
+            for (; q + (U - 1) * kStep < q1; q += U * kStep) {
+                const long long p = pbase + q;
+                if (!(a.vec_ok && p >= 0 && p + (U - 1) * kStep + 7 < a.n_in)) break;
+                float re[U][8], im[U][8];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 xv = ld_hint_v4(x + p + u * kStep + 2 * e, pol_stream);
+                        re[u][2 * e] = xv.x;
+                        im[u][2 * e] = xv.y;
+                        re[u][2 * e + 1] = xv.z;
+                        im[u][2 * e + 1] = xv.w;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) convert_store(q + u * kStep, re[u], im[u]);
+            }
+        }
+        for (; q < q1; q += kStep) {
             const long long p = pbase + q;
             float re[8], im[8];
             if (a.vec_ok && p >= 0 && p + 7 < a.n_in) {
@@ -517,22 +560,7 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
                     im[e] = v.y;
                 }
             }
-            // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                uint32_t wr[4], wi[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    wr[e] = bf16_pair(re[2 * e], re[2 * e + 1]);
-                    wi[e] = bf16_pair(im[2 * e], im[2 * e + 1]);
-                    re[2 * e] -= __uint_as_float(wr[e] << 16);
-                    re[2 * e + 1] -= __uint_as_float(wr[e] & 0xFFFF0000u);
-                    im[2 * e] -= __uint_as_float(wi[e] << 16);
-                    im[2 * e + 1] -= __uint_as_float(wi[e] & 0xFFFF0000u);
-                }
-                st_hint_v4(dst + (size_t)(2 * part) * a.tile_plane + q, wr[0], wr[1], wr[2], wr[3], pol_ring);
-                st_hint_v4(dst + (size_t)(2 * part + 1) * a.tile_plane + q, wi[0], wi[1], wi[2], wi[3], pol_ring);
-            }
+            convert_store(q, re, im);
         }
     }
 }
@@ -657,10 +685,10 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {  // ===== 8 epilogue warps: chain flush into registers, split of the next tile, output =====
-        const int ew = warp - 2;        // 0..7
+        const int ew = warp - 2;        // 0..kEpiWarps-1
         const int wq = warp & 3;        // TMEM lane quarter this warp may read
-        const int half = ew >> 2;       // blocks [64 half, 64 half + 64) of the tile
-        const int et = ew * 32 + lane;  // 0..255
+        const int half = ew >> 2;       // blocks [kColsW half, kColsW half + kColsW) of the tile
+        const int et = ew * 32 + lane;  // 0..32 kEpiWarps - 1
         const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
         const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
         uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(2 * blockIdx.x) * buf_bytes;
@@ -677,16 +705,49 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
             const int next = tile + gridDim.x;
             uint8_t *nbuf = ring + (size_t)((it + 1) & 1) * buf_bytes;
-            float accr[64], acci[64];
-#pragma unroll
-            for (int i = 0; i < 64; ++i) accr[i] = acci[i] = 0.f;
-            for (int gi = 0; gi < a.ngroups; ++gi, ++use) {
+            // Slice gi of the next tile's split runs BEFORE the wait for chain gi: its ring buffer was last read by
+            // tile it-1, all of whose loads completed before that tile's last chain (flushed in the previous
+            // iteration) could finish.  The first slice runs while no accumulator register is live (3 positions
+            // per trip); with one chain per tile (short interpolator sub-filters) it is the whole split, and the
+            // next tile's loads and MMAs overlap this tile's flush and stores.
+            auto publish = [&]() {  // the next tile's planes are complete: let the producer's TMA read them
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_bar((it + 1) & 1));
+            };
+            if (next < a.ntiles) {
+                tc_split_range<BF, 1>(a, next, nbuf, 0, min(a.slice, a.tile_plane), et, pol_ring, pol_stream);
+                if (a.ngroups == 1) publish();
+            }
+            float accr[kColsW], acci[kColsW];
+            {
                 const uint32_t acc = use & 1u;
                 mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * 64;
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * kColsW;
 #pragma unroll
-                for (int cg = 0; cg < 4; ++cg) {
+                for (int cg = 0; cg < kColsW / 16; ++cg) {
+                    tmem_ld16(taddr + cg * 16, accr + cg * 16);
+                    tmem_ld16(taddr + kNB + cg * 16, acci + cg * 16);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                ++use;
+            }
+            for (int gi = 1; gi < a.ngroups; ++gi, ++use) {
+                if (next < a.ntiles) {
+                    tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
+                                       pol_stream);
+                    if (gi == a.ngroups - 1) publish();
+                }
+                const uint32_t acc = use & 1u;
+                mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * kColsW;
+#pragma unroll
+                for (int cg = 0; cg < kColsW / 16; ++cg) {
                     float re[16], im[16];
                     tmem_ld16(taddr + cg * 16, re);
                     tmem_ld16(taddr + kNB + cg * 16, im);
@@ -700,24 +761,19 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
-                // between two flushes: one slice of the next tile's planes (its buffer was last read by tile
-                // it-1, whose loads all completed before this tile's first chain could finish)
-                if (next < a.ntiles)
-                    tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
-                                       pol_stream);
-            }
-            if (next < a.ntiles) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ready_bar((it + 1) & 1));
             }
             const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
             float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
-            const long long n0 = (long long)tt * kTileSamples + (long long)(half * 64) * kBM + m;
+            const long long n0 = (long long)tt * kTileSamples + (long long)(half * kColsW) * kBM + m;
+            float2 *__restrict__ yp = y + n0;
+            if ((long long)(tt + 1) * kTileSamples <= a.n_out) {  // interior tile: constant offsets, no guards
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const long long n = n0 + (long long)i * kBM;
-                if (n < a.n_out) st_hint_v2(y + n, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
+                for (int i = 0; i < kColsW; ++i) st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kColsW; ++i)
+                    if (n0 + (long long)i * kBM < a.n_out)
+                        st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
             }
         }
     }

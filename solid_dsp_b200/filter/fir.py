@@ -290,7 +290,7 @@ class InterpolatingFIRFilter(_InterpHandle):
 
     @property
     def last_path(self) -> str:
-        """'tensor' when the last execute_block ran on the tcgen05 kernel (real taps, L = 2 / 4, long sub-filters)."""
+        """'tensor' when the last execute_block ran on the tcgen05 kernel (real taps, L = 2 / 4, sub-filters of more than 32 taps)."""
         return "tensor" if lib.sgpu_interp_last_path(self._h) == 1 else "ffma"
 
     def __str__(self):

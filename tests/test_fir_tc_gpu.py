@@ -156,14 +156,14 @@ def test_two_channels_and_linearity(torch, FIR):
 
 
 # ------------------------------------------------------------------ polyphase interpolator on the same kernel
-@pytest.mark.parametrize("L,T", [(4, 128), (2, 128), (4, 100), (4, 1024), (2, 777)])
+@pytest.mark.parametrize("L,T", [(4, 256), (2, 128), (4, 200), (4, 1024), (2, 777)])
 def test_interpolator_parity(torch, L, T):
     """InterpolatingFIRFilter (interp.rs:102-111, pfb.rs:85-90): block rows of 128 / L inputs, exact output count,
     padded sub-filters (T not a multiple of L), several channels in one launch, ragged tails."""
     from solid_dsp_b200.filter.fir import InterpolatingFIRFilter
     h = f32_taps(O.firdes_kaiser(T, 0.5 / L * 0.9, 80.0, 0.0))
     C = 3
-    n = (1 << 20) + 4321 if T < 1024 else (1 << 19) + 77
+    n = (1 << 22) // L + 4321  # n * L * C >= 2^23 outputs: the dispatcher's threshold for the tensor path
     x = torch.stack([_rand(torch, n, 40 + c) for c in range(C)])
     f = InterpolatingFIRFilter(h, L, n_channels=C)
     y = f.execute_block(x)
@@ -190,7 +190,7 @@ def test_interpolator_parity(torch, L, T):
 
 def test_interpolator_streaming_and_impulse(torch):
     from solid_dsp_b200.filter.fir import InterpolatingFIRFilter
-    L, T = 4, 128
+    L, T = 4, 384
     h = f32_taps(O.firdes_kaiser(T, 0.5 / L * 0.9, 80.0, 0.0))
     n1, n2 = (1 << 21) + 3, (1 << 21) + 4096 * 5 + 1
     x = _rand(torch, n1 + n2, 77)
