@@ -412,6 +412,7 @@ struct TcFusedArgs {
     int tiles_per_ch;     // tiles per channel (a tile = 128 blocks = 16384 outputs = 128 R inputs)
     int ntiles, nchunks, gchunks, ngroups;
     int slice;            // plane positions converted per chain flush (multiple of 8)
+    int nbuf;             // ring buffers per CTA (2..4): the split runs nbuf - 1 tiles ahead of the flush
     int vec_ok;
     float scale;
 };
@@ -579,7 +580,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };
     auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
     auto ready_bar = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
-    const uint32_t tmem_slot = bars + 8u * (2 * NS + 6);
+    const uint32_t tmem_slot = bars + 8u * (2 * NS + 8);
     auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
     auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
 
@@ -593,8 +594,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar(i), 1);
             mbar_init(tempty_bar(i), kEpiWarps);
-            mbar_init(ready_bar(i), kEpiWarps);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(ready_bar(i), kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -612,11 +613,15 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            int stage = 0, it = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-                mbar_wait(ready_bar(it & 1), (uint32_t)(it >> 1) & 1u);  // this tile's planes are in the ring
-                const int buf = 2 * (int)blockIdx.x + (it & 1);
+            int stage = 0, rb = 0;
+            uint32_t phase = 0, rphase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                mbar_wait(ready_bar(rb), rphase);  // this tile's planes are in the ring
+                const int buf = a.nbuf * (int)blockIdx.x + rb;
+                if (++rb == a.nbuf) {
+                    rb = 0;
+                    rphase ^= 1u;
+                }
                 for (int q = 0; q < a.nchunks; ++q) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), F::kStage);
@@ -691,33 +696,35 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int et = ew * 32 + lane;  // 0..32 kEpiWarps - 1
         const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
         const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
-        uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(2 * blockIdx.x) * buf_bytes;
+        uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(a.nbuf * blockIdx.x) * buf_bytes;
         const uint64_t pol_ring = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-        // first tile of this CTA: split it now
-        if ((int)blockIdx.x < a.ntiles) {
-            tc_split_range<BF>(a, blockIdx.x, ring, 0, a.tile_plane, et, pol_ring, pol_stream);
+        const int ahead = a.nbuf - 1;  // the split runs this many tiles ahead of the flush
+        auto publish = [&](int b) {    // a tile's planes are complete: let the producer's TMA read them
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(ready_bar(0));
+            if (lane == 0) mbar_arrive(ready_bar(b));
+        };
+        // the first `ahead` tiles of this CTA: split them now
+        for (int d = 0; d < ahead; ++d) {
+            const int t0 = (int)blockIdx.x + d * (int)gridDim.x;
+            if (t0 < a.ntiles) {
+                tc_split_range<BF>(a, t0, ring + (size_t)d * buf_bytes, 0, a.tile_plane, et, pol_ring, pol_stream);
+                publish(d);
+            }
         }
         uint32_t use = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-            const int next = tile + gridDim.x;
-            uint8_t *nbuf = ring + (size_t)((it + 1) & 1) * buf_bytes;
-            // Slice gi of the next tile's split runs BEFORE the wait for chain gi: its ring buffer was last read by
-            // tile it-1, all of whose loads completed before that tile's last chain (flushed in the previous
-            // iteration) could finish.  The first slice runs while no accumulator register is live (3 positions
-            // per trip); with one chain per tile (short interpolator sub-filters) it is the whole split, and the
-            // next tile's loads and MMAs overlap this tile's flush and stores.
-            auto publish = [&]() {  // the next tile's planes are complete: let the producer's TMA read them
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ready_bar((it + 1) & 1));
-            };
+        int wb = ahead;  // ring buffer the tile `ahead` tiles further on goes to: (it + ahead) mod nbuf
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int next = tile + ahead * (int)gridDim.x;
+            uint8_t *nbuf = ring + (size_t)wb * buf_bytes;
+            // Slice gi of that tile's split runs BEFORE the wait for chain gi: its ring buffer, (it - 1) mod nbuf, was
+            // last read by tile it-1, all of whose loads completed before that tile's last chain (flushed in the
+            // previous iteration) could finish.  With one chain per tile (short interpolator sub-filters) the first
+            // slice is the whole split, and a ring of four buffers keeps the split -> fence -> TMA -> MMA latency
+            // chain three tiles deep.
             if (next < a.ntiles) {
                 tc_split_range<BF, 1>(a, next, nbuf, 0, min(a.slice, a.tile_plane), et, pol_ring, pol_stream);
-                if (a.ngroups == 1) publish();
+                if (a.ngroups == 1) publish(wb);
             }
             float accr[kColsW], acci[kColsW];
             {
@@ -740,7 +747,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (next < a.ntiles) {
                     tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
                                        pol_stream);
-                    if (gi == a.ngroups - 1) publish();
+                    if (gi == a.ngroups - 1) publish(wb);
                 }
                 const uint32_t acc = use & 1u;
                 mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
@@ -775,6 +782,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (n0 + (long long)i * kBM < a.n_out)
                         st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
             }
+            if (++wb == a.nbuf) wb = 0;
         }
     }
 
@@ -836,7 +844,7 @@ struct FirTcState {
     bool smem_set = false;
     // fused kernel: per-CTA ring of two split tile buffers (format: 0 = TF32x3, 1 = BF16x3)
     void *d_ring = nullptr;
-    int ring_ctas = 0, tile_plane = 0, ring_fmt = -1;
+    int ring_ctas = 0, tile_plane = 0, ring_fmt = -1, ring_nbuf = 0;
     CUtensorMap tmRing;
     bool fused_smem_set[2] = {false, false};
     uint16_t *d_A16 = nullptr;   // [3][128][K] bf16: b1, b2, b3 of the band
@@ -970,20 +978,25 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
     const int R = st->R;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
-    if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt) {
+    const int nchains = (st->nchunks + std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks)) - 1) /
+                        std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
+    // one or two chains per tile (short sub-filters): the per-tile latency chain needs a deeper ring than two tiles
+    const int nbuf = std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", nchains <= 2 ? 4 : 2)));
+    if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
             cudaFree(st->d_ring);
         }
         st->d_ring = nullptr;
-        const size_t bytes = (size_t)sm_count * 2 * 2 * parts * tile_plane * elem;
+        const size_t bytes = (size_t)sm_count * nbuf * 2 * parts * tile_plane * elem;
         if (cudaMalloc(&st->d_ring, bytes) != cudaSuccess)
             return fail(SGPU_ERR_CUDA, "cudaMalloc(split ring, %zu bytes) failed", bytes);
         st->ring_ctas = sm_count;
         st->tile_plane = tile_plane;
         st->ring_fmt = fmt;
+        st->ring_nbuf = nbuf;
         const cuuint64_t gdim[4] = {(cuuint64_t)R, (cuuint64_t)(tile_plane / R), (cuuint64_t)(2 * parts),
-                                    (cuuint64_t)(2 * sm_count)};
+                                    (cuuint64_t)(nbuf * sm_count)};
         const cuuint64_t gstr[3] = {(cuuint64_t)R * elem, (cuuint64_t)tile_plane * elem,
                                     (cuuint64_t)tile_plane * elem * 2 * parts};
         const cuuint32_t box[4] = {kKC, kNB, (cuuint32_t)(2 * parts), 1};
@@ -1017,6 +1030,7 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.gchunks = std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
     a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
     a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.ngroups), 8);
+    a.nbuf = nbuf;
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
     a.scale = scale;
     const int grid = std::min(a.ntiles, sm_count);
