@@ -411,8 +411,10 @@ struct TcFusedArgs {
     int R, rsh;           // input samples per block row (128 / L); rsh = log2(R / 32)
     int tiles_per_ch;     // tiles per channel (a tile = 128 blocks = 16384 outputs = 128 R inputs)
     int ntiles, nchunks, gchunks, ngroups;
-    int slice;            // plane positions converted per chain flush (multiple of 8)
+    int slice;            // plane positions converted per slice (multiple of 8)
+    int nslices;          // the next tile's split is cut into this many slices (<= ngroups), one before each of the first chain waits
     int nbuf;             // ring buffers per CTA (2..4): the split runs nbuf - 1 tiles ahead of the flush
+    int dbg;              // experiments only (SGPU_FIR_TC_DBG): 1 = no MMAs issued, 2 = no TMA loads issued (results are garbage)
     int vec_ok;
     float scale;
 };
@@ -624,10 +626,14 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 for (int q = 0; q < a.nchunks; ++q) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), F::kStage);
-                    if constexpr (BF) tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
-                    else tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
-                    tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & ((1 << a.rsh) - 1)) * kKC, q >> a.rsh, 0, buf);
+                    if (a.dbg & 2) {
+                        mbar_arrive(full_bar(stage));
+                    } else {
+                        mbar_expect_tx(full_bar(stage), F::kStage);
+                        if constexpr (BF) tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
+                        else tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
+                        tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & ((1 << a.rsh) - 1)) * kKC, q >> a.rsh, 0, buf);
+                    }
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1u;
@@ -649,7 +655,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int q = q0; q < q1; ++q) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        if constexpr (BF) {
+                        if (a.dbg & 1) {
+                        } else if constexpr (BF) {
                             uint64_t da[3], db[3];
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
@@ -723,8 +730,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // slice is the whole split, and a ring of four buffers keeps the split -> fence -> TMA -> MMA latency
             // chain three tiles deep.
             if (next < a.ntiles) {
-                tc_split_range<BF, 1>(a, next, nbuf, 0, min(a.slice, a.tile_plane), et, pol_ring, pol_stream);
-                if (a.ngroups == 1) publish(wb);
+                tc_split_range<BF, BF ? 4 : 2>(a, next, nbuf, 0, min(a.slice, a.tile_plane), et, pol_ring, pol_stream);
+                if (a.nslices == 1) publish(wb);
             }
             float accr[kColsW], acci[kColsW];
             {
@@ -744,10 +751,10 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ++use;
             }
             for (int gi = 1; gi < a.ngroups; ++gi, ++use) {
-                if (next < a.ntiles) {
+                if (next < a.ntiles && gi < a.nslices) {
                     tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
                                        pol_stream);
-                    if (gi == a.ngroups - 1) publish(wb);
+                    if (gi == a.nslices - 1) publish(wb);
                 }
                 const uint32_t acc = use & 1u;
                 mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
@@ -1029,8 +1036,14 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.nchunks = st->nchunks;
     a.gchunks = std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
     a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
-    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.ngroups), 8);
+    // Slices of the next tile's split, one before each of the first chain waits.  Measured (tools/tc_probe.py, 2^27
+    // samples): one slice per chain is best for long bands (512 taps: 80.1 vs 76.3 Gsamp/s, 2048 taps: 28.7 vs 28.0),
+    // the whole split in one slice at the top of the tile (no accumulator register live, 4 positions per trip) for
+    // short ones (256 taps: 107 vs 104; one-chain interpolator tiles).
+    a.nslices = std::max(1, std::min(env_i("SGPU_FIR_TC_SLICES", a.nchunks >= 16 ? a.ngroups : 1), a.ngroups));
+    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.nslices), 8);
     a.nbuf = nbuf;
+    a.dbg = env_i("SGPU_FIR_TC_DBG", 0);
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
     a.scale = scale;
     const int grid = std::min(a.ntiles, sm_count);
