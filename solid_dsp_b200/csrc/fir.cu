@@ -650,7 +650,8 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         }
     }
     f->last_path = 0;
-    if (n_out > 0 && f->M == 1 && !f->complex_taps && f->scale_im == 0.0 && (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", 192) &&
+    if (n_out > 0 && f->M == 1 && (f->complex_taps || f->scale_im == 0.0) &&
+        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 128 : 192) &&
         n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 21) && env_int("SGPU_FIR_TC", 1)) {
         // long real-tap filters: banded-Toeplitz product on the tcgen05 tensor cores, 3 x TF32 (fir_tc.cu)
         const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
@@ -658,12 +659,12 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         const bool overlap = ib < ob + span_out && ob < ib + span_in;
         if (!f->tc_tried) {
             f->tc_tried = true;
-            int st = fir_tc_create(&f->tc, f->taps_f32.data(), (int)f->T);
+            int st = fir_tc_create(&f->tc, f->taps_f32.data(), (int)f->T, f->complex_taps);
             if (st) return st;
         }
         if (f->tc && !overlap) {
             int st = fir_tc_run(f->tc, d_in, n_in, in_stride, a.hist, (int)f->T - 1, d_out, out_stride, f->C,
-                                (float)f->scale_re, f->sm_count, s);
+                                (float)f->scale_re, (float)f->scale_im, f->sm_count, s);
             if (st) return st;
             f->last_path = 1;
             return SGPU_OK;
@@ -1147,11 +1148,11 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
         const bool overlap = ib < ob + span_out && ob < ib + span_in;
         if (!f->tc_tried) {
             f->tc_tried = true;
-            int st = fir_tc_create_pfb(&f->tc, f->phase_taps.data(), (int)f->L, (int)f->S);
+            int st = fir_tc_create_pfb(&f->tc, f->phase_taps.data(), (int)f->L, (int)f->S, false);
             if (st) return st;
         }
         if (f->tc && !overlap) {
-            int st = fir_tc_run(f->tc, d_in, n_in, istr, a.hist, (int)f->S, d_out, ostr, f->C, 1.f, f->sm_count, s);
+            int st = fir_tc_run(f->tc, d_in, n_in, istr, a.hist, (int)f->S, d_out, ostr, f->C, 1.f, 0.f, f->sm_count, s);
             if (st) return st;
             f->last_path = 1;
             return SGPU_OK;

@@ -360,20 +360,25 @@ constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
 //   BF16x3: b1/b2/b3 bf16 planes (2 B), 6 MMAs per K step of 16 (b1*b1, b1*b2, b2*b1, b2*b2, b1*b3, b3*b1: every
 //           product down to 2^-24 relative), SWIZZLE_64B rows of 32 bf16, 72 KB per K chunk of 32: the same tensor
 //           time per K (bf16 runs at twice the TF32 rate), 25 % less L2 -> shared-memory traffic, three stages.
-template <bool BF>
+template <bool BF, bool CT = false>
 struct Fmt {
+    static_assert(BF || !CT, "complex taps run in the BF16x3 format only");
     static constexpr int kParts = BF ? 3 : 2;                       // planes per operand
     static constexpr int kElem = BF ? 2 : 4;                        // bytes per element
     static constexpr int kRowBytes = kKC * kElem;                   // 64 / 128: the swizzle span
     static constexpr int kAPart = kBM * kRowBytes;                  // one A plane of a stage
     static constexpr int kBPart = kBN * kRowBytes;                  // one B plane (re rows then im rows) of a stage
-    static constexpr int kA = kParts * kAPart;
-    static constexpr int kStage = kParts * (kAPart + kBPart);       // 73728 / 98304
-    static constexpr int kNStages = BF ? 3 : 2;
+    static constexpr int kAParts = kParts * (CT ? 2 : 1);           // complex taps: Gr parts then Gi parts
+    static constexpr int kA = kAParts * kAPart;
+    static constexpr int kStage = kA + kParts * kBPart;             // 73728 (BF16x3) / 98304 (TF32x3, BF16x3 complex taps)
+    static constexpr int kNStages = (BF && !CT) ? 3 : 2;
     static constexpr int kKSteps = BF ? 2 : 4;                      // UMMAs along K per chunk (32-byte steps)
     static constexpr size_t kSmem = (size_t)kNStages * kStage + 1024 + 256;
     static constexpr uint32_t kIdesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24))
                                           : kIdescTf32;
+    // N = 128 halves for the cross terms of complex taps: D[:, re] -= Gi Xim (A negated), D[:, im] += Gi Xre
+    static constexpr uint32_t kIdescHalf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    static constexpr uint32_t kIdescHalfNegA = kIdescHalf | (1u << 13);
 };
 
 // K-major SWIZZLE_64B descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
@@ -416,7 +421,7 @@ struct TcFusedArgs {
     int nbuf;             // ring buffers per CTA (2..4): the split runs nbuf - 1 tiles ahead of the flush
     int dbg;              // experiments only (SGPU_FIR_TC_DBG): 1 = no MMAs issued, 2 = no TMA loads issued (results are garbage)
     int vec_ok;
-    float scale;
+    float scale, scale_im;  // complex scale only with complex taps (fir/mod.rs:211)
 };
 
 __device__ __forceinline__ float2 tc_fetch(const TcFusedArgs &a, const float2 *__restrict__ x,
@@ -568,11 +573,11 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
     }
 }
 
-template <bool BF>
+template <bool BF, bool CT>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcFusedArgs a) {
-    using F = Fmt<BF>;
+    using F = Fmt<BF, CT>;
     constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -672,6 +677,19 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 umma_bf16(d, da[1] + off, db[1] + off, F::kIdesc, 1u);
                                 umma_bf16(d, da[0] + off, db[2] + off, F::kIdesc, 1u);
                                 umma_bf16(d, da[2] + off, db[0] + off, F::kIdesc, 1u);
+                                if constexpr (CT) {
+                                    // complex taps g = gr + j gi: D_re -= Gi Xim, D_im += Gi Xre (dot_product/mod.rs:167:
+                                    // complex x complex), as N = 128 MMAs on the im / re row halves of the B planes
+                                    constexpr int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+#pragma unroll
+                                    for (int t = 0; t < 6; ++t) {
+                                        const uint64_t gi = umma_desc_sw64(stage_a(stage) + (3 + pa[t]) * F::kAPart) + off;
+                                        const uint64_t xre = db[pb[t]] + off;
+                                        const uint64_t xim = xre + (uint64_t)((kNB * F::kRowBytes) >> 4);
+                                        umma_bf16(d, gi, xim, F::kIdescHalfNegA, 1u);
+                                        umma_bf16(d + kNB, gi, xre, F::kIdescHalf, 1u);
+                                    }
+                                }
                             }
                         } else {
                             const uint64_t a_hi = umma_desc(stage_a(stage));
@@ -782,12 +800,19 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float2 *__restrict__ yp = y + n0;
             if ((long long)(tt + 1) * kTileSamples <= a.n_out) {  // interior tile: constant offsets, no guards
 #pragma unroll
-                for (int i = 0; i < kColsW; ++i) st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);
+                for (int i = 0; i < kColsW; ++i) {
+                    if constexpr (CT)
+                        st_hint_v2(yp + i * kBM, accr[i] * a.scale - acci[i] * a.scale_im, accr[i] * a.scale_im + acci[i] * a.scale, pol_stream);
+                    else st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < kColsW; ++i)
-                    if (n0 + (long long)i * kBM < a.n_out)
-                        st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);  // fir/mod.rs:211
+                    if (n0 + (long long)i * kBM < a.n_out) {  // fir/mod.rs:211
+                        if constexpr (CT)
+                            st_hint_v2(yp + i * kBM, accr[i] * a.scale - acci[i] * a.scale_im, accr[i] * a.scale_im + acci[i] * a.scale, pol_stream);
+                        else st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);
+                    }
             }
             if (++wb == a.nbuf) wb = 0;
         }
@@ -853,7 +878,8 @@ struct FirTcState {
     void *d_ring = nullptr;
     int ring_ctas = 0, tile_plane = 0, ring_fmt = -1, ring_nbuf = 0;
     CUtensorMap tmRing;
-    bool fused_smem_set[2] = {false, false};
+    bool fused_smem_set[4] = {false, false, false, false};
+    bool ctaps = false;          // complex taps: A16 holds Gr parts then Gi parts (BF16x3 only)
     uint16_t *d_A16 = nullptr;   // [3][128][K] bf16: b1, b2, b3 of the band
     CUtensorMap tmA16;
 };
@@ -861,7 +887,7 @@ struct FirTcState {
 // Banded matrix of a polyphase filter bank: output o = L n + p of the stream is sum_j tp[p][j] x[n - j]
 // (pfb.rs:85-90; L = 1, tp[0][j] = h[T-1-j] is the plain FIR).  A block of 128 outputs covers R = 128 / L inputs:
 //     A[m][k] = tp[m mod L][m / L + Koff - k],   B[b][k] = x[R b - Koff + k],   K = Koff + R.
-int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S) {
+int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S, bool complex_taps) {
     *out = nullptr;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SGPU_OK;
@@ -875,13 +901,15 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S) {
     st->Koff = (int)round_up((size_t)(S > 1 ? S - 1 : 1), kKC);
     st->K = st->Koff + st->R;
     st->nchunks = st->K / kKC;
-    auto tap = [&](int m, int k, float &g) -> bool {
+    const int tw = complex_taps ? 2 : 1;
+    st->ctaps = complex_taps;
+    auto tap = [&](int m, int k, float &g, int c = 0) -> bool {
         const int jj = m / L + st->Koff - k;
         if (jj < 0 || jj >= T) return false;
-        g = tp[(size_t)(m % L) * S + jj];
+        g = tp[((size_t)(m % L) * S + jj) * tw + c];
         return true;
     };
-    std::vector<float> A((size_t)2 * kBM * st->K, 0.f);
+    std::vector<float> A((size_t)2 * kBM * st->K, 0.f);  // TF32x3 band: real taps only (complex taps run as BF16x3)
     for (int m = 0; m < kBM; ++m)
         for (int k = 0; k < st->K; ++k) {
             float g;
@@ -909,26 +937,27 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S) {
         fir_tc_destroy(st);
         return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
-    {   // bf16 x 3 band for the BF16x3 format of the fused kernel
-        std::vector<uint16_t> A16((size_t)3 * kBM * st->K, 0);
-        for (int m = 0; m < kBM; ++m)
-            for (int k = 0; k < st->K; ++k) {
-                float g;
-                if (!tap(m, k, g)) continue;
-                for (int part = 0; part < 3; ++part) {
-                    const uint16_t b = host_bf16_rne(g);
-                    A16[((size_t)part * kBM + m) * st->K + k] = b;
-                    g -= host_bf16_to_f32(b);
+    {   // bf16 x 3 band for the BF16x3 format of the fused kernel; complex taps: the three Gr parts, then the Gi parts
+        std::vector<uint16_t> A16((size_t)3 * tw * kBM * st->K, 0);
+        for (int c = 0; c < tw; ++c)
+            for (int m = 0; m < kBM; ++m)
+                for (int k = 0; k < st->K; ++k) {
+                    float g;
+                    if (!tap(m, k, g, c)) continue;
+                    for (int part = 0; part < 3; ++part) {
+                        const uint16_t b = host_bf16_rne(g);
+                        A16[((size_t)(3 * c + part) * kBM + m) * st->K + k] = b;
+                        g -= host_bf16_to_f32(b);
+                    }
                 }
-            }
         if (cudaMalloc(&st->d_A16, A16.size() * sizeof(uint16_t)) != cudaSuccess ||
             cudaMemcpy(st->d_A16, A16.data(), A16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
             fir_tc_destroy(st);
             return fail(SGPU_ERR_CUDA, "upload of the bf16 banded tap matrix failed");
         }
-        const cuuint64_t gdim3[3] = {(cuuint64_t)st->K, (cuuint64_t)kBM, 3};
+        const cuuint64_t gdim3[3] = {(cuuint64_t)st->K, (cuuint64_t)kBM, (cuuint64_t)(3 * tw)};
         const cuuint64_t gstr3[2] = {(cuuint64_t)st->K * 2, (cuuint64_t)st->K * 2 * kBM};
-        const cuuint32_t box3[3] = {kKC, kBM, 3};
+        const cuuint32_t box3[3] = {kKC, kBM, (cuuint32_t)(3 * tw)};
         const cuuint32_t estr3[3] = {1, 1, 1};
         const CUresult r3 = enc(&st->tmA16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, st->d_A16, gdim3, gstr3, box3, estr3,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -942,10 +971,12 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S) {
     return SGPU_OK;
 }
 
-int fir_tc_create(FirTcState **out, const float *taps, int T) {
-    std::vector<float> tp((size_t)T);
-    for (int jj = 0; jj < T; ++jj) tp[jj] = taps[T - 1 - jj];  // g[j] = h[T-1-j] (fir/mod.rs:86)
-    return fir_tc_create_pfb(out, tp.data(), 1, T);
+int fir_tc_create(FirTcState **out, const float *taps, int T, bool complex_taps) {
+    const int tw = complex_taps ? 2 : 1;
+    std::vector<float> tp((size_t)T * tw);
+    for (int jj = 0; jj < T; ++jj)  // g[j] = h[T-1-j] (fir/mod.rs:86)
+        for (int c = 0; c < tw; ++c) tp[(size_t)jj * tw + c] = taps[(size_t)(T - 1 - jj) * tw + c];
+    return fir_tc_create_pfb(out, tp.data(), 1, T, complex_taps);
 }
 
 void fir_tc_destroy(FirTcState *st) {
@@ -964,24 +995,26 @@ int env_i(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <bool BF>
+template <bool BF, bool CT>
 int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, cudaStream_t s) {
-    using F = Fmt<BF>;
-    if (!st->fused_smem_set[BF]) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem));
-        st->fused_smem_set[BF] = true;
+    using F = Fmt<BF, CT>;
+    bool &set = st->fused_smem_set[(BF ? 1 : 0) + (CT ? 2 : 0)];
+    if (!set) {
+        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem));
+        set = true;
     }
-    fir_tc_fused_kernel<BF><<<grid, kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA, st->tmRing, a);
+    fir_tc_fused_kernel<BF, CT><<<grid, kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA, st->tmRing, a);
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
 }
 
 int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
-                     float2 *out, long long out_stride, size_t C, float scale, int sm_count, cudaStream_t s) {
+                     float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count,
+                     cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
     const char *fe = getenv("SGPU_FIR_TC_FMT");
-    const int fmt = (fe && fe[0] == 't') ? 0 : 1;  // default BF16x3; SGPU_FIR_TC_FMT=tf32 selects TF32x3
+    const int fmt = (fe && fe[0] == 't' && !st->ctaps) ? 0 : 1;  // default BF16x3; SGPU_FIR_TC_FMT=tf32 selects TF32x3
     const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
     const int R = st->R;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
@@ -1046,17 +1079,19 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.dbg = env_i("SGPU_FIR_TC_DBG", 0);
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
     a.scale = scale;
+    a.scale_im = scale_im;
     const int grid = std::min(a.ntiles, sm_count);
-    return fmt ? fir_tc_launch_fused<true>(st, a, grid, s) : fir_tc_launch_fused<false>(st, a, grid, s);
+    if (st->ctaps) return fir_tc_launch_fused<true, true>(st, a, grid, s);
+    return fmt ? fir_tc_launch_fused<true, false>(st, a, grid, s) : fir_tc_launch_fused<false, false>(st, a, grid, s);
 }
 
 }  // namespace
 
 int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
-               float2 *out, long long out_stride, size_t C, float scale, int sm_count, cudaStream_t s) {
+               float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count, cudaStream_t s) {
     if (n_in <= 0) return SGPU_OK;
-    if (env_i("SGPU_FIR_TC", 1) != 2 || C != 1 || st->L != 1)
-        return fir_tc_run_fused(st, in, n_in, in_stride, hist, H, out, out_stride, C, scale, sm_count, s);
+    if (env_i("SGPU_FIR_TC", 1) != 2 || C != 1 || st->L != 1 || st->ctaps)
+        return fir_tc_run_fused(st, in, n_in, in_stride, hist, H, out, out_stride, C, scale, scale_im, sm_count, s);
     // SGPU_FIR_TC=2: first generation (split pre-pass launch + one accumulation chain per tile), kept for comparison
     EncodeTiledFn enc = encode_fn();
     if (!st->smem_set) {

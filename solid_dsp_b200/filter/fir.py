@@ -60,7 +60,7 @@ class _FirHandle(Filter):
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value:
+        if h is not None and h.value and lib is not None:  # `lib` is already None at interpreter shutdown
             getattr(lib, self._destroy)(h)
             h.value = None
 

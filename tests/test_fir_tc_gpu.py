@@ -213,3 +213,34 @@ def test_interpolator_streaming_and_impulse(torch):
     assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
     assert np.max(np.abs(got[1:] - ref[:-1])) > 1e-3 * np.max(np.abs(ref))
     assert int(torch.count_nonzero(yz).item()) == int(np.count_nonzero(ref))
+
+
+# ------------------------------------------------------------------ complex taps (Coef = Complex<f64>) on the tensor kernel
+@pytest.mark.parametrize("T", [128, 512, 777])
+def test_complex_taps(torch, T):
+    """FIRFilter<Complex<f64>, Complex<f64>> (fir/mod.rs:181-186): complex taps and complex scale; the cross terms
+    run as N = 128 MMAs on the re / im halves of the split planes (D_re -= Gi Xim, D_im += Gi Xre)."""
+    from solid_dsp_b200.filter.fir import FIRFilter
+    k = np.arange(T)
+    hr = O.firdes_kaiser(T, 0.1, 80.0, 0.0) * np.exp(2j * np.pi * 0.05 * k)  # SURVEY 8d: config 2's complex-tap variant
+    h = f32_taps(hr.real) + 1j * f32_taps(hr.imag)
+    scale = 0.5 - 0.25j
+    n = 16384 * 300 + 4321
+    x = _rand(torch, n, 900 + T)
+    f = FIRFilter(h, scale)
+    y1 = f.execute_block(x[:n // 2])
+    assert f.last_path == "tensor"
+    y = torch.cat([y1, f.execute_block(x[n // 2:])])
+    for s in (0, T - 1, n // 2 - 100, n // 2 + 5, n - 2048):
+        lo = max(0, s - (T - 1))
+        ref = O.fir_fast(h, x[lo:s + 2048].cpu().numpy(), scale)[s - lo:]
+        assert nerr(y[s:s + 2048].cpu().numpy(), ref) <= TOL
+    import os
+    os.environ["SGPU_FIR_TC"] = "0"
+    try:
+        f2 = FIRFilter(h, scale)
+        y2 = f2.execute_block(x)
+        assert f2.last_path == "ffma"
+    finally:
+        del os.environ["SGPU_FIR_TC"]
+    assert (y - y2).abs().max().item() <= TOL * y2.abs().max().item()
