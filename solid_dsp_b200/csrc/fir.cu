@@ -1137,12 +1137,12 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
     f->last_path = 0;
-    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", 33) &&
+    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", f->L == 2 ? 17 : 33) &&
         n_in >= 128 * (128 / (long long)f->L) &&
         n_out * (long long)f->C >= (long long)env_int("SGPU_INTERP_TC_MIN_OUT", 1 << 23) && env_int("SGPU_FIR_TC", 1)) {
         // polyphase interpolator as a banded product on the tcgen05 tensor cores (fir_tc.cu): 128 outputs per block
-        // row = 128 / L inputs.  Measured (tools/tc_interp_probe.py, 256 ch x 2^20): sub-filters <= 32 taps stay on the
-        // walking kernel (430 vs 358 G out-samp/s at L = 4), longer ones are 1.4x (48 taps) ... 2.8x (256 taps) faster here
+        // row = 128 / L inputs.  Measured (tools/tc_interp_probe.py, 256 ch x 2^20, G out-samp/s): L = 4: sub-filters <= 32
+        // taps stay on the walking kernel (430 vs 422), 48 taps 373 vs 190, 256 taps 163 vs 58; L = 2: 24-32 taps 288 vs 263
         const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
         const size_t span_in = (size_t)((f->C - 1) * istr + n_in) * 8, span_out = (size_t)((f->C - 1) * ostr + n_out) * 8;
         const bool overlap = ib < ob + span_out && ob < ib + span_in;

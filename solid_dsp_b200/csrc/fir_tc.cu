@@ -354,6 +354,9 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 constexpr int kEpiWarps = 8;                          // 4 per TMEM lane quarter
 constexpr int kColsW = kNB / (kEpiWarps / 4);          // blocks (accumulator columns per re / im half) per epilogue warp
 constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
+constexpr int kOneWarps = 8;                           // one-chain kernel: groups of four epilogue warps (measured: 2 groups 422, 4 groups 373 G out-samp/s at L=4, S=32)
+constexpr int kOneThreads = 64 + 32 * kOneWarps;
+constexpr int kOneRing = 2 * (kOneWarps / 4);          // ring buffers per CTA of the one-chain kernel: every group splits its next tile ahead
 
 // Operand format of the fused kernel.
 //   TF32x3: hi/lo TF32 planes (4 B), 3 MMAs per K step of 8, SWIZZLE_128B rows of 32 floats, 96 KB per K chunk of 32.
@@ -466,7 +469,7 @@ __device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
 
 // plane positions [q0, q1) of tile `tile` (channel tile / tiles_per_ch, tile tt inside it): position q holds input
 // sample tt * 128 R - Koff + q of that channel
-template <bool BF, int U = 1>
+template <bool BF, int U = 1, int NTHR = 32 * kEpiWarps>
 __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
                                                int et, uint64_t pol_ring, uint64_t pol_stream) {
     const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
@@ -475,7 +478,7 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
     const long long pbase = (long long)tt * (kNB * a.R) - a.Koff;
     if constexpr (!BF) {
         float *__restrict__ dst = reinterpret_cast<float *>(dstv);
-        for (int q = q0 + 4 * et; q < q1; q += 4 * 32 * kEpiWarps) {
+        for (int q = q0 + 4 * et; q < q1; q += 4 * NTHR) {
             const long long p = pbase + q;
             float2 v[4];
             if (a.vec_ok && p >= 0 && p + 3 < a.n_in) {
@@ -506,7 +509,7 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
         }
     } else {
         uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
-        constexpr int kStep = 8 * 32 * kEpiWarps;
+        constexpr int kStep = 8 * NTHR;
         auto convert_store = [&](int qq, float *re, float *im) {
             // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
 #pragma unroll
@@ -573,8 +576,8 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
     }
 }
 
-template <bool BF, bool CT>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <bool BF, bool CT, bool ONE>
+__global__ void __launch_bounds__(ONE ? kOneThreads : kFusedThreads, 1)
 fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcFusedArgs a) {
     using F = Fmt<BF, CT>;
@@ -584,10 +587,10 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t bars = base + NS * F::kStage;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
-    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };
-    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
-    auto ready_bar = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
-    const uint32_t tmem_slot = bars + 8u * (2 * NS + 8);
+    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };       // 4 slots (ONE: one per group)
+    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };  // 2 slots
+    auto ready_bar = [&](int i) { return bars + 8u * (2 * NS + 6 + i); };   // up to 8 slots
+    const uint32_t tmem_slot = bars + 8u * (2 * NS + 14);
     auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
     auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
 
@@ -598,11 +601,9 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(tfull_bar(i), 1);
-            mbar_init(tempty_bar(i), kEpiWarps);
-        }
-        for (int i = 0; i < 4; ++i) mbar_init(ready_bar(i), kEpiWarps);
+        for (int i = 0; i < 4; ++i) mbar_init(tfull_bar(i), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(tempty_bar(i), ONE ? 4 : kEpiWarps);  // one-chain tiles: four warps per tile
+        for (int i = 0; i < 8; ++i) mbar_init(ready_bar(i), ONE ? 4 : kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -710,7 +711,9 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             phase ^= 1u;
                         }
                     }
-                    umma_commit(tfull_bar(acc));
+                    // ONE: a *full* barrier per warp group (tile mod 4): a parity wait is only safe for a waiter that is at
+                    // most one phase behind, and two groups share each accumulator
+                    umma_commit(tfull_bar(ONE ? (use % (kOneWarps / 4)) : acc));
                 }
             }
         }
@@ -729,6 +732,58 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(ready_bar(b));
         };
+        if constexpr (ONE) {
+            // One accumulation chain per tile (short interpolator sub-filters: K = 64 / 96).  Nothing has to be summed
+            // in registers, so a warp drains its whole TMEM lane quarter in batches of 16 columns, four warps serve a
+            // tile, and the groups of four warps take the tiles in turn: while one group waits for its sample loads
+            // (split of its next tile, NG tiles ahead, ring of 2 NG buffers) or for the ring stores to land
+            // (fence.proxy.async), the other flushes and stores.
+            constexpr int NG = kOneWarps / 4;
+            const int grp = ew >> 2;
+            const int et4 = (ew & 3) * 32 + lane;
+            int it = grp;
+            int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            if (tile < a.ntiles) {
+                tc_split_range<BF, BF ? 4 : 2, 128>(a, tile, ring + (size_t)(it & (kOneRing - 1)) * buf_bytes, 0, a.tile_plane,
+                                                     et4, pol_ring, pol_stream);
+                publish(it & (kOneRing - 1));
+            }
+            for (; tile < a.ntiles; it += NG, tile += NG * (int)gridDim.x) {
+                const int ntile = tile + NG * (int)gridDim.x;
+                if (ntile < a.ntiles) {
+                    tc_split_range<BF, BF ? 4 : 2, 128>(a, ntile, ring + (size_t)((it + NG) & (kOneRing - 1)) * buf_bytes, 0,
+                                                         a.tile_plane, et4, pol_ring, pol_stream);
+                    publish((it + NG) & (kOneRing - 1));
+                }
+                const uint32_t acc = (uint32_t)it & 1u;
+                mbar_wait(tfull_bar(grp), ((uint32_t)(it / NG)) & 1u);  // it = grp (mod NG): this group's own barrier
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN;
+                const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+                const long long n0 = (long long)tt * kTileSamples + m;
+                float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0;
+                const bool interior = (long long)(tt + 1) * kTileSamples <= a.n_out;
+#pragma unroll 2
+                for (int cg = 0; cg < kNB / 16; ++cg) {
+                    float re[16], im[16];
+                    tmem_ld16(taddr + cg * 16, re);
+                    tmem_ld16(taddr + kNB + cg * 16, im);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = cg * 16 + i;
+                        if (interior || n0 + (long long)j * kBM < a.n_out) {
+                            if constexpr (CT)
+                                st_hint_v2(yp + j * kBM, re[i] * a.scale - im[i] * a.scale_im, re[i] * a.scale_im + im[i] * a.scale, pol_stream);
+                            else st_hint_v2(yp + j * kBM, re[i] * a.scale, im[i] * a.scale, pol_stream);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+        } else {
         // the first `ahead` tiles of this CTA: split them now
         for (int d = 0; d < ahead; ++d) {
             const int t0 = (int)blockIdx.x + d * (int)gridDim.x;
@@ -816,6 +871,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (++wb == a.nbuf) wb = 0;
         }
+        }  // several chains per tile (!ONE)
     }
 
     tc_fence_before();
@@ -878,7 +934,7 @@ struct FirTcState {
     void *d_ring = nullptr;
     int ring_ctas = 0, tile_plane = 0, ring_fmt = -1, ring_nbuf = 0;
     CUtensorMap tmRing;
-    bool fused_smem_set[4] = {false, false, false, false};
+    bool fused_smem_set[8] = {false, false, false, false, false, false, false, false};
     bool ctaps = false;          // complex taps: A16 holds Gr parts then Gi parts (BF16x3 only)
     uint16_t *d_A16 = nullptr;   // [3][128][K] bf16: b1, b2, b3 of the band
     CUtensorMap tmA16;
@@ -995,15 +1051,17 @@ int env_i(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <bool BF, bool CT>
+template <bool BF, bool CT, bool ONE>
 int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, cudaStream_t s) {
     using F = Fmt<BF, CT>;
-    bool &set = st->fused_smem_set[(BF ? 1 : 0) + (CT ? 2 : 0)];
+    bool &set = st->fused_smem_set[(BF ? 1 : 0) + (CT ? 2 : 0) + (ONE ? 4 : 0)];
     if (!set) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem));
+        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF, CT, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)F::kSmem));
         set = true;
     }
-    fir_tc_fused_kernel<BF, CT><<<grid, kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA, st->tmRing, a);
+    fir_tc_fused_kernel<BF, CT, ONE><<<grid, ONE ? kOneThreads : kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA,
+                                                                                                st->tmRing, a);
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
@@ -1018,10 +1076,11 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
     const int R = st->R;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
-    const int nchains = (st->nchunks + std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks)) - 1) /
-                        std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
-    // one or two chains per tile (short sub-filters): the per-tile latency chain needs a deeper ring than two tiles
-    const int nbuf = std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", nchains <= 2 ? 4 : 2)));
+    // chunks per accumulation chain: 2 (64 taps); bands of up to 3 chunks run as ONE chain (the alternating-group epilogue)
+    const int gchunks = st->nchunks <= 3 ? st->nchunks : std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
+    const int nchains = (st->nchunks + gchunks - 1) / gchunks;
+    // one chain per tile: the one-chain kernel (four groups of warps, each four tiles ahead: ring of eight); two chains: measured no gain
+    const int nbuf = nchains == 1 ? kOneRing : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", nchains <= 2 ? 4 : 2)));
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
@@ -1067,7 +1126,7 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.tiles_per_ch = (int)tiles_per_ch;
     a.ntiles = (int)(tiles_per_ch * (long long)C);
     a.nchunks = st->nchunks;
-    a.gchunks = std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
+    a.gchunks = gchunks;
     a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
     // Slices of the next tile's split, one before each of the first chain waits.  Measured (tools/tc_probe.py, 2^27
     // samples): one slice per chain is best for long bands (512 taps: 80.1 vs 76.3 Gsamp/s, 2048 taps: 28.7 vs 28.0),
@@ -1081,8 +1140,12 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.scale = scale;
     a.scale_im = scale_im;
     const int grid = std::min(a.ntiles, sm_count);
-    if (st->ctaps) return fir_tc_launch_fused<true, true>(st, a, grid, s);
-    return fmt ? fir_tc_launch_fused<true, false>(st, a, grid, s) : fir_tc_launch_fused<false, false>(st, a, grid, s);
+    if (a.ngroups == 1) {
+        if (st->ctaps) return fir_tc_launch_fused<true, true, true>(st, a, grid, s);
+        return fmt ? fir_tc_launch_fused<true, false, true>(st, a, grid, s) : fir_tc_launch_fused<false, false, true>(st, a, grid, s);
+    }
+    if (st->ctaps) return fir_tc_launch_fused<true, true, false>(st, a, grid, s);
+    return fmt ? fir_tc_launch_fused<true, false, false>(st, a, grid, s) : fir_tc_launch_fused<false, false, false>(st, a, grid, s);
 }
 
 }  // namespace

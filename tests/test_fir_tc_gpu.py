@@ -156,11 +156,14 @@ def test_two_channels_and_linearity(torch, FIR):
 
 
 # ------------------------------------------------------------------ polyphase interpolator on the same kernel
-@pytest.mark.parametrize("L,T", [(4, 256), (2, 128), (4, 200), (4, 1024), (2, 777)])
-def test_interpolator_parity(torch, L, T):
+@pytest.mark.parametrize("L,T", [(4, 256), (2, 128), (4, 200), (4, 1024), (2, 777), (4, 128), (2, 64), (4, 90), (2, 30)])
+def test_interpolator_parity(torch, L, T, monkeypatch):
     """InterpolatingFIRFilter (interp.rs:102-111, pfb.rs:85-90): block rows of 128 / L inputs, exact output count,
     padded sub-filters (T not a multiple of L), several channels in one launch, ragged tails."""
     from solid_dsp_b200.filter.fir import InterpolatingFIRFilter
+    # sub-filters of <= 32 taps (one accumulation chain per tile, the alternating-group epilogue) are dispatched to the
+    # FP32 walking kernel by default: force them through the tensor kernel here
+    monkeypatch.setenv("SGPU_INTERP_TC_MIN_SUB", "1")
     h = f32_taps(O.firdes_kaiser(T, 0.5 / L * 0.9, 80.0, 0.0))
     C = 3
     n = (1 << 22) // L + 4321  # n * L * C >= 2^23 outputs: the dispatcher's threshold for the tensor path
