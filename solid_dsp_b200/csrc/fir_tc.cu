@@ -354,7 +354,7 @@ fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 constexpr int kEpiWarps = 8;                          // 4 per TMEM lane quarter
 constexpr int kColsW = kNB / (kEpiWarps / 4);          // blocks (accumulator columns per re / im half) per epilogue warp
 constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
-constexpr int kOneWarps = 8;                           // one-chain kernel: groups of four epilogue warps (measured: 2 groups 422, 4 groups 373 G out-samp/s at L=4, S=32)
+constexpr int kOneWarps = 8;                           // one-chain kernel: groups of four epilogue warps (measured at L=4, S=32: 2 groups 418-422, 3 groups 372, 4 groups 373 G out-samp/s)
 constexpr int kOneThreads = 64 + 32 * kOneWarps;
 constexpr int kOneRing = 2 * (kOneWarps / 4);          // ring buffers per CTA of the one-chain kernel: every group splits its next tile ahead
 
@@ -744,16 +744,16 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int it = grp;
             int tile = (int)blockIdx.x + it * (int)gridDim.x;
             if (tile < a.ntiles) {
-                tc_split_range<BF, BF ? 4 : 2, 128>(a, tile, ring + (size_t)(it & (kOneRing - 1)) * buf_bytes, 0, a.tile_plane,
+                tc_split_range<BF, BF ? 4 : 2, 128>(a, tile, ring + (size_t)(it % kOneRing) * buf_bytes, 0, a.tile_plane,
                                                      et4, pol_ring, pol_stream);
-                publish(it & (kOneRing - 1));
+                publish(it % kOneRing);
             }
             for (; tile < a.ntiles; it += NG, tile += NG * (int)gridDim.x) {
                 const int ntile = tile + NG * (int)gridDim.x;
                 if (ntile < a.ntiles) {
-                    tc_split_range<BF, BF ? 4 : 2, 128>(a, ntile, ring + (size_t)((it + NG) & (kOneRing - 1)) * buf_bytes, 0,
+                    tc_split_range<BF, BF ? 4 : 2, 128>(a, ntile, ring + (size_t)((it + NG) % kOneRing) * buf_bytes, 0,
                                                          a.tile_plane, et4, pol_ring, pol_stream);
-                    publish((it + NG) & (kOneRing - 1));
+                    publish((it + NG) % kOneRing);
                 }
                 const uint32_t acc = (uint32_t)it & 1u;
                 mbar_wait(tfull_bar(grp), ((uint32_t)(it / NG)) & 1u);  // it = grp (mod NG): this group's own barrier
@@ -763,19 +763,31 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const long long n0 = (long long)tt * kTileSamples + m;
                 float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0;
                 const bool interior = (long long)(tt + 1) * kTileSamples <= a.n_out;
-#pragma unroll 2
-                for (int cg = 0; cg < kNB / 16; ++cg) {
-                    float re[16], im[16];
-                    tmem_ld16(taddr + cg * 16, re);
-                    tmem_ld16(taddr + kNB + cg * 16, im);
-                    tmem_ld_wait();
+#pragma unroll 1
+                for (int sb = 0; sb < 2; ++sb) {  // two super-batches of 64 blocks: 8 TMEM loads in flight, one wait
+                    float re[64], im[64];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int j = cg * 16 + i;
-                        if (interior || n0 + (long long)j * kBM < a.n_out) {
+                    for (int cg = 0; cg < 4; ++cg) {
+                        tmem_ld16(taddr + sb * 64 + cg * 16, re + cg * 16);
+                        tmem_ld16(taddr + kNB + sb * 64 + cg * 16, im + cg * 16);
+                    }
+                    tmem_ld_wait();
+                    float2 *__restrict__ ys = yp + sb * 64 * kBM;
+                    if (interior) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) {
                             if constexpr (CT)
-                                st_hint_v2(yp + j * kBM, re[i] * a.scale - im[i] * a.scale_im, re[i] * a.scale_im + im[i] * a.scale, pol_stream);
-                            else st_hint_v2(yp + j * kBM, re[i] * a.scale, im[i] * a.scale, pol_stream);
+                                st_hint_v2(ys + i * kBM, re[i] * a.scale - im[i] * a.scale_im, re[i] * a.scale_im + im[i] * a.scale, pol_stream);
+                            else st_hint_v2(ys + i * kBM, re[i] * a.scale, im[i] * a.scale, pol_stream);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) {
+                            if (n0 + (long long)(sb * 64 + i) * kBM < a.n_out) {
+                                if constexpr (CT)
+                                    st_hint_v2(ys + i * kBM, re[i] * a.scale - im[i] * a.scale_im, re[i] * a.scale_im + im[i] * a.scale, pol_stream);
+                                else st_hint_v2(ys + i * kBM, re[i] * a.scale, im[i] * a.scale, pol_stream);
+                            }
                         }
                     }
                 }
