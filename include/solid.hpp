@@ -164,6 +164,8 @@ class FIRFilter : public Filter<cf32, cf32> {  // fir/mod.rs:58-316
         return v;
     }
     size_t channels() const { return sgpu_fir_channels(h_); }
+    /// true when the last execute_block ran on the tcgen05 tensor-core kernel (long filters; csrc/fir_tc.cu)
+    bool last_path_tensor() const { return sgpu_fir_last_path(h_) == 1; }
 
     std::vector<cf32> execute(cf32 sample) override { return execute_block(std::vector<cf32>{sample}); }  // :209
     // :235 -- channel-major [channels][n]; one channel by default
@@ -284,6 +286,7 @@ class InterpolatingFIRFilter : public Filter<cf32, cf32> {  // fir/interp.rs:6-1
     }
     size_t interpolation() const { return sgpu_interp_interpolation(h_); }  // :82
     size_t channels() const { return sgpu_interp_channels(h_); }
+    bool last_path_tensor() const { return sgpu_interp_last_path(h_) == 1; }
     std::vector<cf32> execute(cf32 sample) override { return execute_block(std::vector<cf32>{sample}); }  // :93
     std::vector<cf32> execute_block(const std::vector<cf32> &samples) override {                          // :102
         const size_t C = channels(), n = samples.size() / C, L = interpolation();
