@@ -469,7 +469,7 @@ __device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
 
 // plane positions [q0, q1) of tile `tile` (channel tile / tiles_per_ch, tile tt inside it): position q holds input
 // sample tt * 128 R - Koff + q of that channel
-template <bool BF, int U = 1, int NTHR = 32 * kEpiWarps>
+template <bool BF, int U = 1, int NTHR = 32 * kEpiWarps, bool EXTRA = false>
 __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
                                                int et, uint64_t pol_ring, uint64_t pol_stream) {
     const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
@@ -547,8 +547,32 @@ __device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, v
                         im[u][2 * e + 1] = xv.w;
                     }
                 }
+                // EXTRA: one more position in the same latency window when it is the last one of the range (a tile of
+                // 4096 + Koff positions over 128 threads leaves 4-8 positions after four full rounds)
+                float rx[8], ix[8];
+                bool extra = false;
+                if constexpr (EXTRA) {
+                    const int qe = q + U * kStep;
+                    extra = qe < q1 && qe + kStep >= q1 && p + (long long)U * kStep + 7 < a.n_in;
+                    if (extra) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 xv = ld_hint_v4(x + p + U * kStep + 2 * e, pol_stream);
+                            rx[2 * e] = xv.x;
+                            ix[2 * e] = xv.y;
+                            rx[2 * e + 1] = xv.z;
+                            ix[2 * e + 1] = xv.w;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) convert_store(q + u * kStep, re[u], im[u]);
+                if constexpr (EXTRA) {
+                    if (extra) {
+                        convert_store(q + U * kStep, rx, ix);
+                        q += kStep;
+                    }
+                }
             }
         }
         for (; q < q1; q += kStep) {
@@ -744,14 +768,14 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int it = grp;
             int tile = (int)blockIdx.x + it * (int)gridDim.x;
             if (tile < a.ntiles) {
-                tc_split_range<BF, BF ? 4 : 2, 128>(a, tile, ring + (size_t)(it % kOneRing) * buf_bytes, 0, a.tile_plane,
+                tc_split_range<BF, BF ? 4 : 2, 128, BF>(a, tile, ring + (size_t)(it % kOneRing) * buf_bytes, 0, a.tile_plane,
                                                      et4, pol_ring, pol_stream);
                 publish(it % kOneRing);
             }
             for (; tile < a.ntiles; it += NG, tile += NG * (int)gridDim.x) {
                 const int ntile = tile + NG * (int)gridDim.x;
                 if (ntile < a.ntiles) {
-                    tc_split_range<BF, BF ? 4 : 2, 128>(a, ntile, ring + (size_t)((it + NG) % kOneRing) * buf_bytes, 0,
+                    tc_split_range<BF, BF ? 4 : 2, 128, BF>(a, ntile, ring + (size_t)((it + NG) % kOneRing) * buf_bytes, 0,
                                                          a.tile_plane, et4, pol_ring, pol_stream);
                     publish((it + NG) % kOneRing);
                 }
