@@ -1,22 +1,34 @@
-// FIRFilter::execute_block (filter/fir/mod.rs:209-212,235-241 -> dot_product/mod.rs:159-170) for LONG real-tap
-// filters, as a banded-Toeplitz product on the tcgen05 tensor cores with a 3 x TF32 split.
+// FIRFilter::execute_block (filter/fir/mod.rs:209-212,235-241 -> dot_product/mod.rs:159-170) for LONG filters and
+// InterpolatingFIRFilter::execute_block (filter/fir/interp.rs:102-111 -> pfb.rs:85-90) for long sub-filters, as a
+// banded-Toeplitz product on the tcgen05 tensor cores (sm_100a).  DESIGN.md 4.9 has the measurements.
 //
-// The stream is cut into blocks of 128 outputs.  Block b needs the K = Koff + 128 inputs
-// x[128 b - Koff .. 128 b + 127] (Koff = T-1 rounded up to 32), so with
-//     A[m][k] = g[m + Koff - k]   (g[i] = h[T-1-i], zero outside 0..T-1; the same 128 x K band for every block)
-//     B[b][k] = x[128 b - Koff + k]
-// the outputs are  y[128 b + m] = scale * sum_k A[m][k] B[b][k]  -- a GEMM whose N dimension runs over blocks and
-// over (re, im).  FP32 accuracy comes from splitting both operands into two TF32 numbers (round-to-nearest
-// hi, lo = rn(x - hi)) and issuing three MMAs per K step: hi*hi + lo*hi + hi*lo (the lo*lo term is < 2^-22
-// relative).  A split pre-pass de-interleaves the cf32 samples into four f32 planes (re_hi, im_hi, re_lo, im_lo);
-// because 32 | 128, chunk q of row b of B is the plain 2-D box (column 32 (q mod 4), row b + q / 4) of a plane
-// viewed as [rows][128], so TMA builds the overlapping Toeplitz rows with no extra copies and the 5x re-reads
-// hit L2.
+// Formulation.  The output stream is cut into blocks of 128 outputs; a block covers R = 128 / L inputs (L = 1: FIR).
+// With Koff = (taps per phase - 1) rounded up to 32 and K = Koff + R,
+//     A[m][k] = tp[m mod L][m / L + Koff - k]   (the same 128 x K band for every block; FIR: tp[0][j] = h[T-1-j])
+//     B[b][k] = x[R b - Koff + k]
+//     y[128 b + m] = scale * sum_k A[m][k] B[b][k]
+// -- a GEMM with M = 128, N = 256 (128 blocks x {re, im}: real taps act on both parts alike) and K = Koff + R.
+// Because 32 | R, K-chunk q of row b of B is the plain box (column 32 (q mod R/32), row b + q / (R/32)) of the sample
+// plane viewed as [rows][R]: TMA builds the overlapping Toeplitz rows, the re-reads are L2 hits.
 //
-// Kernel: persistent, one CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one thread,
-// tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256 = 128 blocks x {re, im}), warps 2-5 = epilogue
-// (tcgen05.ld 32x32b -> scale -> coalesced float2 stores).  Two 96 KB smem stages (SWIZZLE_128B, K chunk of 32
-// floats), two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Precision.  f32 accuracy on a 16-bit-input pipe: x = b1 + b2 + b3 (three bf16 terms, each the rounded residual of
+// the previous ones), likewise the taps, six MMAs per K step (b1h1, b1h2, b2h1, b2h2, b1h3, b3h1: everything down to
+// 2^-24).  A TF32x3 variant (hi / lo planes, three MMAs at half the rate) is kept.  The tensor core truncates the
+// addend toward zero when it aligns it to the f32 accumulator (measured: tools/tc_accum_probe.py), which makes the
+// error LINEAR in the number of sequential MMAs, so the K loop of a tile is cut into chains of two K-chunks that
+// are summed in f32 registers by the epilogue warps (round to nearest).
+//
+// Kernels.
+//   fir_tc_fused_kernel<BF, CT, ONE>  (the product): persistent, one CTA per SM; warp 0 = TMA producer, warp 1 = one
+//       thread issuing tcgen05.mma (cta_group::1, M 128 x N 256), warps 2-9 = epilogue.  The epilogue warps also
+//       split the NEXT tile's cf32 samples into the bf16 / tf32 planes, into a per-CTA ring in global memory that
+//       stays in L2 (evict_last) and is read back by TMA: no pre-pass launch, no stream-sized scratch.
+//       CT: complex taps (Gr and Gi parts in A, cross terms as N = 128 MMAs with the negate-A bit).
+//       ONE: bands of <= 3 K-chunks (short interpolator sub-filters) are a single chain per tile: each warp drains its
+//       TMEM lane quarter straight to global memory and two groups of four warps alternate tiles.
+//   fir_tc_split_kernel + fir_tc_kernel  (SGPU_FIR_TC=2): the first generation (split pre-pass over the whole
+//       stream, one chain per tile), kept for comparison: it shows the accumulator bias (1.2e-5 at 2048 taps).
+// Every mbarrier wait is bounded (4 s, then trap): a protocol error is a CUDA error, not a hung GPU.
 #include "fir_tc.cuh"
 
 #include <cuda.h>
