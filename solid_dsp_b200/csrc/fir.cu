@@ -678,27 +678,32 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         a.RS = rows | 1;
         const size_t stage_b = std::max<size_t>((size_t)(kR / 2) * a.RS + 1, 32 * (kR / 2 + 1)) * sizeof(float4);
         const size_t taps_b = (size_t)(f->Qpad + kTapSkew) * sizeof(float);
-        constexpr int TPW = 8;
         const int ns = env_int("SGPU_FIR_NS", 1);
         int st = SGPU_OK;
         bool done = false;
-#define LAUNCH_FWARP(NWV, MB, NSV, ONEV)                                                      \
+#define LAUNCH_FWARP(NWV, MB, NSV, ONEV, TPWV)                                                \
     do {                                                                                      \
         const size_t smem = (size_t)NWV * NSV * stage_b + taps_b;                             \
         if (smem <= (size_t)kMaxSmem) {                                                       \
-            auto kern = fir_warp_kernel<kR, NWV, MB, TPW, NSV, ONEV>;                         \
+            auto kern = fir_warp_kernel<kR, NWV, MB, TPWV, NSV, ONEV>;                        \
             st = set_smem(kern, smem);                                                        \
             if (st) return st;                                                                \
-            const long long per_block = 32LL * kR * TPW * NWV;                                \
+            const long long per_block = 32LL * kR * TPWV * NWV;                               \
             dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);       \
             kern<<<grid, NWV * 32, smem, s>>>(a);                                             \
             done = true;                                                                      \
         }                                                                                     \
     } while (0)
-        if (f->Qpad == kR) LAUNCH_FWARP(4, 4, 1, true);  // <= 16 taps: single tap chunk
-        else if (ns == 2) LAUNCH_FWARP(4, 3, 2, false);
-        else LAUNCH_FWARP(4, 4, 1, false);
-        if (!done && f->Qpad != kR) LAUNCH_FWARP(1, 1, 1, false);  // very long filters: one warp per block
+        // Eight tiles per warp amortise the tap staging on long streams, but a short call (BASELINE config 1: 64 taps
+        // x 2^20 samples = 64 blocks of 16384 outputs) would leave most of the chip idle: one tile per warp there.
+        const bool small = (n_out + 16383) / 16384 * (long long)f->C < 4LL * f->sm_count && env_int("SGPU_FIR_SMALL", 1);
+        if (f->Qpad == kR) {  // <= 16 taps: single tap chunk
+            if (small) LAUNCH_FWARP(4, 4, 1, true, 1);
+            else LAUNCH_FWARP(4, 4, 1, true, 8);
+        } else if (ns == 2) LAUNCH_FWARP(4, 3, 2, false, 8);
+        else if (small) LAUNCH_FWARP(4, 4, 1, false, 1);
+        else LAUNCH_FWARP(4, 4, 1, false, 8);
+        if (!done && f->Qpad != kR) LAUNCH_FWARP(1, 1, 1, false, 8);  // very long filters: one warp per block
 #undef LAUNCH_FWARP
         if (done) {
             SGPU_LAUNCH_CHECK();
