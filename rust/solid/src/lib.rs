@@ -112,6 +112,8 @@ pub mod filter {
             pub fn get_scale(&self) -> f64 { let (mut re, mut im) = (0.0, 0.0); unsafe { sys::sgpu_fir_get_scale(self.h, &mut re, &mut im) }; re }
             pub fn len(&self) -> usize { unsafe { sys::sgpu_fir_len(self.h) } }
             pub fn is_empty(&self) -> bool { self.len() == 0 }
+            /// true when the last execute_block ran on the tcgen05 tensor-core kernel (not part of the reference API)
+            pub fn last_path_tensor(&self) -> bool { unsafe { sys::sgpu_fir_last_path(self.h) == 1 } }
             /// stored (reversed) order -- fir/mod.rs:176
             pub fn coefficients(&self) -> Vec<f64> { let mut v = vec![0.0; self.len()]; unsafe { sys::sgpu_fir_coefficients(self.h, v.as_mut_ptr()) }; v }
             pub(crate) fn run(&mut self, samples: &[Complex<f32>]) -> Vec<Complex<f32>> {
@@ -187,6 +189,7 @@ pub mod filter {
                 pub fn len(&self) -> usize { unsafe { sys::sgpu_interp_interpolation(self.h) } }
                 pub fn is_empty(&self) -> bool { self.len() == 0 }
                 pub fn interpolation(&self) -> usize { self.len() }
+                pub fn last_path_tensor(&self) -> bool { unsafe { sys::sgpu_interp_last_path(self.h) == 1 } }
                 pub fn coefficents(&self) -> Vec<f64> {
                     let mut v = vec![0.0; self.len() * unsafe { sys::sgpu_interp_sub_len(self.h) }];
                     unsafe { sys::sgpu_interp_coefficients(self.h, v.as_mut_ptr()) }; v
