@@ -52,7 +52,7 @@ def _check_windows(h, x, y, starts, width=2048, hist=None):
     return worst
 
 
-@pytest.mark.parametrize("T", [192, 200, 512, 777, 2048])
+@pytest.mark.parametrize("T", [112, 128, 200, 512, 777, 2048])
 def test_parity_random(torch, FIR, T):
     h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
     # ragged: last tile partial, not a multiple of 128; 310 tiles = up to 3 tiles per CTA (ring + barrier phases)
