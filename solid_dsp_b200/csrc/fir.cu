@@ -651,7 +651,7 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     }
     f->last_path = 0;
     if (n_out > 0 && f->M == 1 && (f->complex_taps || f->scale_im == 0.0) &&
-        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 128 : 112) &&
+        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) &&
         n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 15) && env_int("SGPU_FIR_TC", 1)) {
         // (calls of 2^17 ... 2^21 samples: 47-65 us on this path against 74-123 us for the FFMA2 kernel, whose blocks
         //  each walk 16384 outputs -- tools/tc_probe.py with SGPU_FIR_TC_MIN_SAMPLES=1)

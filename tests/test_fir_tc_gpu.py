@@ -219,7 +219,7 @@ def test_interpolator_streaming_and_impulse(torch):
 
 
 # ------------------------------------------------------------------ complex taps (Coef = Complex<f64>) on the tensor kernel
-@pytest.mark.parametrize("T", [128, 512, 777])
+@pytest.mark.parametrize("T", [56, 64, 128, 512, 777])
 def test_complex_taps(torch, T):
     """FIRFilter<Complex<f64>, Complex<f64>> (fir/mod.rs:181-186): complex taps and complex scale; the cross terms
     run as N = 128 MMAs on the re / im halves of the split planes (D_re -= Gi Xim, D_im += Gi Xre)."""
