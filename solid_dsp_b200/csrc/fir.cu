@@ -651,7 +651,7 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     }
     f->last_path = 0;
     if (n_out > 0 && f->M == 1 && (f->complex_taps || f->scale_im == 0.0) &&
-        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) &&
+        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) && f->T <= 16384 /* band matrix: 768 B per tap */ &&
         n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 15) && env_int("SGPU_FIR_TC", 1)) {
         // (calls of 2^17 ... 2^21 samples: 47-65 us on this path against 74-123 us for the FFMA2 kernel, whose blocks
         //  each walk 16384 outputs -- tools/tc_probe.py with SGPU_FIR_TC_MIN_SAMPLES=1)
@@ -1144,7 +1144,7 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
     f->last_path = 0;
-    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", f->L == 2 ? 17 : 33) &&
+    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", f->L == 2 ? 17 : 33) && f->S <= 16384 &&
         n_in >= 128 * (128 / (long long)f->L) &&
         n_out * (long long)f->C >= (long long)env_int("SGPU_INTERP_TC_MIN_OUT", 1 << 23) && env_int("SGPU_FIR_TC", 1)) {
         // polyphase interpolator as a banded product on the tcgen05 tensor cores (fir_tc.cu): 128 outputs per block
