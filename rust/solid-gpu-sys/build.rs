@@ -10,7 +10,8 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda_home = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
     let nvcc = PathBuf::from(&cuda_home).join("bin/nvcc");
-    let sources = ["common.cu", "fir.cu", "iir.cu", "dot.cu"];
+    // keep in step with SRCS in solid_dsp_b200/csrc/Makefile
+    let sources = ["common.cu", "fir.cu", "fir_tc.cu", "iir.cu", "dot.cu", "autocorr.cu"];
     let mut objects = Vec::new();
     for src in sources.iter() {
         let obj = out.join(format!("{}.o", src));
