@@ -77,3 +77,16 @@ def test_no_cpu_fallback_without_gpu(ffi):
     with pytest.raises(SolidGpuError) as e:
         FIRFilter([1.0, 2.0, 3.0], 1.0)
     assert e.value.status == ffi.ERR_NO_DEVICE
+
+
+def test_rust_sys_build_compiles_the_same_sources_as_the_makefile():
+    """rust/solid-gpu-sys/build.rs (the -sys crate the north star asks for; no Rust toolchain here to run it) must list
+    exactly the CUDA sources libsolid_gpu.so is built from."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    mk = (root / "solid_dsp_b200" / "csrc" / "Makefile").read_text()
+    srcs = re.search(r"^SRCS\s*:=\s*(.+)$", mk, re.M).group(1).split()
+    rs = (root / "rust" / "solid-gpu-sys" / "build.rs").read_text()
+    listed = re.findall(r'"([a-z_]+\.cu)"', re.search(r"let sources = \[(.+?)\];", rs, re.S).group(1))
+    assert sorted(listed) == sorted(srcs)
