@@ -90,3 +90,12 @@ def test_rust_sys_build_compiles_the_same_sources_as_the_makefile():
     rs = (root / "rust" / "solid-gpu-sys" / "build.rs").read_text()
     listed = re.findall(r'"([a-z_]+\.cu)"', re.search(r"let sources = \[(.+?)\];", rs, re.S).group(1))
     assert sorted(listed) == sorted(srcs)
+
+
+def test_rust_sys_crate_declares_every_prototype_of_the_header():
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    header = set(re.findall(r"\b(sgpu_[a-z0-9_]+)\s*\(", (root / "include" / "solid_gpu.h").read_text()))
+    rust = set(re.findall(r"pub fn (sgpu_[a-z0-9_]+)\s*\(", (root / "rust" / "solid-gpu-sys" / "src" / "lib.rs").read_text()))
+    assert header == rust, (sorted(header - rust), sorted(rust - header))
