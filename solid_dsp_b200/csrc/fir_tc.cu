@@ -391,10 +391,11 @@ struct Fmt {
     static constexpr size_t kSmem = (size_t)kNStages * kStage + 1024 + 256;
     static constexpr uint32_t kIdesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24))
                                           : kIdescTf32;
-    // N = 128 halves for the cross terms of complex taps: D[:, re] -= Gi Xim (A negated), D[:, im] += Gi Xre
-    static constexpr uint32_t kIdescHalf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-    static constexpr uint32_t kIdescHalfNegA = kIdescHalf | (1u << 13);
 };
+
+// bf16 MMA with N = 128: the cross terms of complex taps, D[:, re] -= Gi Xim (negate-A bit), D[:, im] += Gi Xre
+constexpr uint32_t kIdescBf16Half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+constexpr uint32_t kIdescBf16HalfNegA = kIdescBf16Half | (1u << 13);
 
 // K-major SWIZZLE_64B descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
@@ -723,8 +724,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         const uint64_t gi = umma_desc_sw64(stage_a(stage) + (3 + pa[t]) * F::kAPart) + off;
                                         const uint64_t xre = db[pb[t]] + off;
                                         const uint64_t xim = xre + (uint64_t)((kNB * F::kRowBytes) >> 4);
-                                        umma_bf16(d, gi, xim, F::kIdescHalfNegA, 1u);
-                                        umma_bf16(d + kNB, gi, xre, F::kIdescHalf, 1u);
+                                        umma_bf16(d, gi, xim, kIdescBf16HalfNegA, 1u);
+                                        umma_bf16(d + kNB, gi, xre, kIdescBf16Half, 1u);
                                     }
                                 }
                             }
