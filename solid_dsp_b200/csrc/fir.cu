@@ -653,9 +653,11 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     if (n_out > 0 && f->M == 1 && (f->complex_taps || f->scale_im == 0.0) &&
         (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) && f->T <= 16384 /* band matrix: 768 B per tap */ &&
         n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 15) && env_int("SGPU_FIR_TC", 1)) {
-        // (calls of 2^17 ... 2^21 samples: 47-65 us on this path against 74-123 us for the FFMA2 kernel, whose blocks
-        //  each walk 16384 outputs -- tools/tc_probe.py with SGPU_FIR_TC_MIN_SAMPLES=1)
-        // long real-tap filters: banded-Toeplitz product on the tcgen05 tensor cores, 3 x TF32 (fir_tc.cu)
+        // Long filters (real or complex taps): banded-Toeplitz product on the tcgen05 tensor cores, BF16x3 split
+        // (fir_tc.cu).  Thresholds from measurements: tools/tc_taps_crossover.py (real taps: 96 taps 141 vs
+        // 146 Gsamp/s for the FFMA2 kernel, 128 taps 133 vs 114; complex taps: 32 taps 140 vs 163, 64 taps 122 vs 103) and
+        // tools/tc_probe.py with SGPU_FIR_TC_MIN_SAMPLES=1 (calls of 2^17 ... 2^21 samples: 47-65 us per call against
+        // 74-123 us for the FFMA2 kernel, whose blocks each walk 16384 outputs).
         const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
         const size_t span_in = (size_t)((f->C - 1) * in_stride + n_in) * 8, span_out = (size_t)((f->C - 1) * out_stride + n_out) * 8;
         const bool overlap = ib < ob + span_out && ob < ib + span_in;
