@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the filtering hot path on B200, one JSON line per run.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir|decim|interp|iir_batch|iir_scan|autocorr]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fir|fir64|decim|interp|iir_batch|iir_scan|autocorr|ddc]
     python bench.py --impl reference ...        # the reference's CPU path (restated oracle) on host cores
     torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU)
 
@@ -12,16 +12,20 @@ whole stream: halo write + FIR execute_block on every rank.
 
 `value`   : complex Gsamples/s with inputs resident in HBM (device pointers through the C ABI).
 `e2e`     : same metric through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region.
-`roofline`: the dominant kernel against the FP32-FMA peak measured live (libsgpu_peakbench) and
-            against the measured HBM copy peak (MEASURED_PEAKS.json).
+`roofline`: the dominant kernel -- timed with CUDA events around execute_block INSIDE the timed loop that
+            gives `value` -- against the binding peak: FP32 FMA measured live (libsgpu_peakbench), the measured
+            HBM copy peak or the measured bf16 tensor rate (MEASURED_PEAKS.json).
 `cpu_baseline`: the restated reference CPU path (oracle/, structural: Window memmove + to_vec +
             sequential DotProduct per sample) on the box's host cores, bounded sample.
+`workloads`: (default run at N = 1 only) the other BASELINE configs, each with value, kernel time, both roofline
+            fractions, oracle parity, clocks and a 1-core cpu_baseline.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -41,6 +45,8 @@ WORKLOADS = {
     # name: description, flop per unit, bytes per unit, unit
     "fir": dict(desc="BASELINE configs[1]: single-stream 512-tap FIR (real Kaiser taps, complex f32 samples) over 2^30 samples",
                 flop_per_unit=2048.0, bytes_per_unit=16.0, unit="input sample"),
+    "fir64": dict(desc="BASELINE configs[0]: single-channel 64-tap windowed-sinc low-pass over 2^20 samples per call (the reference's CPU-runnable case)",
+                  flop_per_unit=256.0, bytes_per_unit=16.0, unit="input sample"),
     "decim": dict(desc="BASELINE configs[2]: decimator M=8, 256 taps, 4096 channels x 2^20 samples",
                   flop_per_unit=128.0, bytes_per_unit=9.0, unit="input sample"),
     "interp": dict(desc="BASELINE configs[3]: interpolator L=4, 128 taps, 1024 channels x 2^20 inputs",
@@ -49,28 +55,80 @@ WORKLOADS = {
                       flop_per_unit=144.0, bytes_per_unit=16.0, unit="sample"),
     "iir_scan": dict(desc="BASELINE configs[4b]: 8-section biquad cascade, one stream of 2^28 samples (chunked scan)",
                      flop_per_unit=144.0, bytes_per_unit=16.0, unit="sample"),
-    # widening, not a BASELINE config: 8 flop per lag product + 2 complex adds per output
+    # widening, not BASELINE configs
     "autocorr": dict(desc="SURVEY 8f: AutoCorrelator window 64, delay 16, 1024 channels x 2^20 samples",
                      flop_per_unit=16.0, bytes_per_unit=16.0, unit="sample"),
+    "ddc": dict(desc="SURVEY 8f: NCO mix-down fused into the decimator (DDC): M=8, 256 taps, 4096 channels x 2^20 samples",
+                flop_per_unit=136.0, bytes_per_unit=9.0, unit="input sample"),
 }
 AUTOCORR_SHAPE = (64, 16)
+DDC_FREQ = 0.1234  # radians per sample of the mix-down NCO
+FIR64_ROWS = 32    # fir64: the calls rotate over 32 buffers of 2^20 samples (512 MB in + out: every call reads cold data)
+SHAPES = {  # channels, log2(samples per channel)
+    "decim": (4096, 20), "interp": (1024, 20), "iir_batch": (65536, 14), "iir_scan": (1, 28), "autocorr": (1024, 20),
+    "ddc": (4096, 20),
+}
+
+# (pole radius, pole angle / pi) of the benchmark's biquad sections: conjugate pole pairs, double zero at z = -1, unit DC
+# gain (the reference has no SOS designer); the same table as solid_dsp_b200.filter.iirdes, kept
+# here so that the reference arm imports nothing of the product
+_SECTION_TABLE = [(0.50, 0.10), (0.60, 0.14), (0.70, 0.18), (0.78, 0.22), (0.84, 0.26), (0.88, 0.30), (0.92, 0.34), (0.95, 0.38)]
 
 
 def f32_taps(h):
     return np.asarray(h, dtype=np.float32).astype(np.float64)
 
 
-def workload_taps(name):
-    from solid_dsp_b200.filter import firdes, iirdes
+def bench_sections():
+    ff, fb = [], []
+    for r, th in _SECTION_TABLE:
+        a1 = -2.0 * r * math.cos(math.pi * th)
+        a2 = r * r
+        g = (1.0 + a1 + a2) / 4.0
+        ff += [g, 2.0 * g, g]
+        fb += [1.0, a1, a2]
+    return f32_taps(ff), f32_taps(fb)
+
+
+def workload_taps(name, impl="ours"):
+    """Taps of a workload.  The reference arm designs them with the oracle's restatement of firdes_kaiser (bit-identical
+    to the product's, tests/test_oracle_golden.py) so that process never loads the product library."""
+    if impl == "reference":
+        import oracle as O
+        kaiser = O.firdes_kaiser
+    else:
+        from solid_dsp_b200.filter import firdes
+        kaiser = firdes.firdes_kaiser
     if name == "fir":
-        return f32_taps(firdes.firdes_kaiser(512, 0.1, 80.0, 0.0))
-    if name == "decim":
-        return f32_taps(firdes.firdes_kaiser(256, 0.5 / 8 * 0.9, 80.0, 0.0))
+        return f32_taps(kaiser(512, 0.1, 80.0, 0.0))
+    if name == "fir64":
+        return f32_taps(kaiser(64, 0.25, 60.0, 0.0))
+    if name in ("decim", "ddc"):
+        return f32_taps(kaiser(256, 0.5 / 8 * 0.9, 80.0, 0.0))
     if name == "interp":
-        return f32_taps(firdes.firdes_kaiser(128, 0.5 / 4 * 0.9, 80.0, 0.0))
+        return f32_taps(kaiser(128, 0.5 / 4 * 0.9, 80.0, 0.0))
     if name == "autocorr":
         return AUTOCORR_SHAPE
-    return iirdes.stable_lowpass_sections(8)
+    return bench_sections()
+
+
+def workload_config(name, world, log2_samples):
+    """The `config` object: identical in both arms."""
+    W = WORKLOADS[name]
+    if name == "fir":
+        shape = {"samples": 1 << log2_samples, "taps": 512, "segments": world, "halo": 511}
+    elif name == "fir64":
+        shape = {"samples_per_call": 1 << 20, "taps": 64, "buffers": FIR64_ROWS}
+    else:
+        chans, lg = SHAPES[name]
+        if log2_samples != 30:
+            lg = log2_samples
+        shape = {"channels": chans, "samples_per_channel": 1 << lg}
+    l2 = ("the calls rotate over 32 input / output buffer pairs (512 MB): every call reads data that is not in the 126 MB L2"
+          if name == "fir64" else "inputs (>= 2 GiB per rank) exceed the 126 MB L2; no explicit flush")
+    par = (f"stream segments x{world} with halo" if name in ("fir", "iir_scan") else
+           ("replicas" if name == "fir64" else f"channels x{world}"))
+    return {"workload": W["desc"], "name": name, **shape, "l2": l2, "parallelism": par}
 
 
 # --------------------------------------------------------------------------------- clocks sampler
@@ -87,7 +145,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -97,6 +155,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms to start: wait until it has delivered a sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
 
     def stop(self):
         if self.proc is None:
@@ -133,10 +197,10 @@ def cpu_reference_path(name: str, n_threads: int, budget_s: float, native: bool 
     workload.  Returns (units_per_second, sample description, seconds)."""
     import oracle as O
     rng = np.random.default_rng(1234)
-    taps = workload_taps(name)
+    taps = workload_taps(name, "reference")
 
     def run(n_units, n_in):
-        if name == "fir":
+        if name in ("fir", "fir64"):
             T = len(taps)
             # stream segments, each primed with T-1 preroll samples through the public API
             x = (rng.uniform(-1, 1, n_units * n_in + T) + 1j * rng.uniform(-1, 1, n_units * n_in + T))
@@ -145,10 +209,12 @@ def cpu_reference_path(name: str, n_threads: int, budget_s: float, native: bool 
             O.run_units("fir", x, n_in, n_units, n_in, out, n_in, n_threads, coefs=taps, preroll=T - 1,
                         x_offset=T - 1, native=native)
             return time.perf_counter() - t0, n_units * n_in
-        if name == "decim":
+        if name in ("decim", "ddc"):
             x = rng.uniform(-1, 1, n_units * n_in) + 1j * rng.uniform(-1, 1, n_units * n_in)
             out = np.zeros(n_units * (n_in // 8 + 1), dtype=np.complex128)
             t0 = time.perf_counter()
+            if name == "ddc":  # NCO::mix_down per sample (nco/mod.rs:141-172 semantics, oracle restatement) in front of the decimator
+                x = O.nco_mix_down_block(x.reshape(n_units, n_in), DDC_FREQ, n_threads=n_threads).reshape(-1)
             O.run_units("decim", x, n_in, n_units, n_in, out, n_in // 8 + 1, n_threads, coefs=taps, decimation=8,
                         native=native)
             return time.perf_counter() - t0, n_units * n_in
@@ -190,10 +256,12 @@ def cpu_reference_path(name: str, n_threads: int, budget_s: float, native: bool 
 
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path (restated oracle; the
-    reference is Rust and cannot be built here), all host threads, bounded sample per step."""
+    reference is Rust and cannot be built here), all host threads, bounded sample per step.  This process imports
+    oracle/ only -- never the product package or its library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
     name = args.workload
     per_step_budget = max(1.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
@@ -210,7 +278,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[name]["desc"], "name": name},
+        "config": workload_config(name, world, args.log2_samples),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,18 +287,280 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------- GPU arm
+_PEAKS = None
+
+
 def measure_peaks():
-    from solid_dsp_b200 import _ffi
-    P = _ffi.peak_lib()
-    best = 0.0
-    detail = {}
-    for variant, nm in ((0, "ffma_scalar"), (1, "ffma2_packed")):
-        ms, fl = C.c_double(), C.c_double()
-        if P.sgpu_peak_fma(variant, 8, 400, 3, C.byref(ms), C.byref(fl)) == 0:
-            tf = fl.value / ms.value / 1e9
-            detail[nm] = tf
-            best = max(best, tf)
-    return best, detail
+    global _PEAKS
+    if _PEAKS is None:
+        from solid_dsp_b200 import _ffi
+        P = _ffi.peak_lib()
+        best = 0.0
+        detail = {}
+        for variant, nm in ((0, "ffma_scalar"), (1, "ffma2_packed")):
+            ms, fl = C.c_double(), C.c_double()
+            if P.sgpu_peak_fma(variant, 8, 400, 3, C.byref(ms), C.byref(fl)) == 0:
+                tf = fl.value / ms.value / 1e9
+                detail[nm] = tf
+                best = max(best, tf)
+        _PEAKS = (best, detail)
+    return _PEAKS
+
+
+def file_peaks():
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    out = {"hbm": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "bf16": 1590.0, "bf16_src": "fallback (B200_PROFILING.md)"}
+    if peaks_file.exists():
+        pk = json.loads(peaks_file.read_text())
+        out["hbm"] = float(pk["hbm_gbs"])
+        out["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+        out["bf16"] = float(pk.get("bf16_tflops_sustained") or pk["bf16_tflops"])
+        out["bf16_src"] = ("measured (MEASURED_PEAKS.json, bf16_tflops_sustained: the kernel runs for several ms back to "
+                           "back under the power cap)")
+    return out
+
+
+class Workload:
+    """One workload on this rank: inputs in HBM, the filter handle, step() and the timed loop."""
+
+    def __init__(self, name, args, world, rank, dev, dist):
+        import torch
+        from solid_dsp_b200 import sharding
+        from solid_dsp_b200.filter.fir import DecimatingFIRFilter, FIRFilter, InterpolatingFIRFilter
+        from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
+        self.name, self.args, self.world, self.rank, self.dev, self.dist = name, args, world, rank, dev, dist
+        self.torch = torch
+        self.taps = workload_taps(name)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1000 + rank)
+
+        def rand_c(shape):
+            t = torch.empty(tuple(shape) + (2,), dtype=torch.float32, device=dev)
+            t.uniform_(-1.0, 1.0, generator=gen)
+            return torch.view_as_complex(t)
+
+        self.halo_prev = None
+        self.seg_first = 0
+        self.kernel_events = []
+        taps = self.taps
+        if name == "fir":
+            n_total = 1 << args.log2_samples
+            self.seg_first, n_loc = sharding.shard_stream(n_total, 1, world, rank)
+            self.x = rand_c((n_loc,))
+            self.filt = FIRFilter(taps, 1.0)
+            T = len(taps)
+            self.halo_prev = torch.zeros(T - 1, dtype=torch.complex64, device=dev)
+            self.units_total = n_total
+
+            def step():
+                # halo: last T-1 samples of the previous rank's segment (rank 0: zeros = fresh filter)
+                sharding.exchange_halo(self.x, self.halo_prev, rank, world, dist)
+                self.filt.write(self.halo_prev)
+                return self._timed(lambda: self.filt.execute_block(self.x))
+        elif name == "fir64":
+            self.x = rand_c((FIR64_ROWS, 1 << 20))
+            self.filt = FIRFilter(taps, 1.0)
+            self.units_total = (1 << 20) * world  # every rank runs its own replica of the single-channel case
+            self.it = 0
+            self.out = torch.empty_like(self.x)
+            from solid_dsp_b200 import _ffi
+            got = _ffi.c_size()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            n = 1 << 20
+
+            def call():  # straight through the C ABI (device pointers): no per-call output allocation
+                r = self.it % FIR64_ROWS
+                self.it += 1
+                _ffi.check(_ffi.lib.sgpu_fir_execute_block(self.filt._h, self.x[r].data_ptr(), n, n, self.out[r].data_ptr(), n,
+                                                           C.byref(got), _ffi.DEVICE, stream))
+                return self.out[r]
+
+            def step():
+                return self._timed(call)
+        else:
+            chans, lg = SHAPES[name]
+            n_per = 1 << (lg if args.log2_samples == 30 else args.log2_samples)
+            if name == "iir_scan":
+                c_loc = 1  # one stream: time segments per rank, warm-up halo from the previous rank (DESIGN.md 6)
+                self.units_total = n_per
+            else:
+                _, c_loc = sharding.shard_channels(chans, world, rank)
+                self.units_total = chans * n_per * (4 if name == "interp" else 1)
+            n_loc = n_per
+            if name == "iir_scan" and world > 1:
+                self.seg_first, n_loc = sharding.shard_stream(n_per, 32, world, rank)
+            self.x = rand_c((c_loc, n_loc))
+            if name == "decim":
+                self.filt = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
+            elif name == "ddc":
+                from solid_dsp_b200.filter.ddc import DigitalDownConverter
+                self.filt = DigitalDownConverter(taps, 1.0, 8, DDC_FREQ, n_channels=c_loc)
+            elif name == "interp":
+                self.filt = InterpolatingFIRFilter(taps, 4, n_channels=c_loc)
+            elif name == "autocorr":
+                from solid_dsp_b200.filter.auto_correlator import AutoCorrelator
+                self.filt = AutoCorrelator(*taps, n_channels=c_loc)
+            else:
+                self.filt = IIRFilter(taps[0], taps[1], IIRFilterType.SecondOrder, n_channels=c_loc)
+            if name == "iir_scan" and world > 1:
+                warm = self.filt.decay_length()
+                assert warm > 0, "the benchmark cascade decays"
+                self.halo_prev = torch.zeros(warm, dtype=torch.complex64, device=dev)
+
+                def step():
+                    sharding.exchange_halo(self.x[0], self.halo_prev, rank, world, dist)
+                    return self._timed(lambda: sharding.iir_segment(self.filt, self.x, self.halo_prev.unsqueeze(0), rank))
+            else:
+                def step():
+                    return self._timed(lambda: self.filt.execute_block(self.x))
+        self.step = step
+
+    def _timed(self, fn):
+        """CUDA events around the execute_block call(s) of a step, on the stream they are launched on."""
+        torch = self.torch
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        y = fn()
+        k1.record()
+        self.kernel_events.append((k0, k1))
+        return y
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run_timed(self, warmup, steps, sample_clocks=True):
+        """W warm-up steps, K timed steps between barriers; device time, max over ranks."""
+        torch, dist = self.torch, self.dist
+        from solid_dsp_b200 import launch_count
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        sampler = None
+        if self.rank == 0 and sample_clocks:
+            sampler = ClockSampler(self.dev.index)
+            sampler.start()
+            sampler.wait_first()
+        self.kernel_events = []
+        l0 = launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        y = None
+        for _ in range(steps):
+            y = self.step()
+        e1.record()
+        self.barrier()
+        ms_total = e0.elapsed_time(e1)
+        ms_kernel = sum(a.elapsed_time(b) for a, b in self.kernel_events) / steps
+        launches = launch_count() - l0
+        # short runs (fir64: 200 calls of ~10 us) end before nvidia-smi has taken a sample under load: keep the same
+        # step going for the sampler for another 0.5 s (untimed, after the counters were read)
+        if sampler is not None and ms_total < 500.0:
+            t_end = time.perf_counter() + 0.5
+            while time.perf_counter() < t_end:
+                for _ in range(50):
+                    self.step()
+                torch.cuda.synchronize()
+        self.kernel_events = []
+        clocks = sampler.stop() if sampler is not None else None
+        if self.world > 1:
+            t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total, ms_kernel = float(t[0].item()), float(t[1].item())
+            lt = torch.tensor([launches], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            launches = int(lt.item())
+        self.last_y = y
+        ms_step = ms_total / steps
+        return {"ms_step": ms_step, "ms_kernel": ms_kernel, "value": self.units_total / (ms_step * 1e-3) / 1e9,
+                "launches": launches, "clocks": clocks}
+
+    def parity(self):
+        """Oracle check of the timed buffers on EVERY rank (the first outputs of rank r > 0 depend on the halo it
+        received); the worst error over the ranks is reported."""
+        torch, dist = self.torch, self.dist
+        y = self.step()  # known entry state (halo / fresh history) for the buffers that get checked
+        torch.cuda.synchronize()
+        p = spot_check(self.name, self.taps, self.filt, self.x, y, self.halo_prev, self.rank)
+        if self.world > 1:
+            t = torch.tensor([p["max_normalised_error"]], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p["max_normalised_error_rank0"] = p["max_normalised_error"]
+            p["max_normalised_error"] = float(t.item())
+            p["ok"] = bool(p["max_normalised_error"] <= 1e-5)
+            p["ranks_checked"] = self.world
+        return p
+
+    def roofline(self, ms_kernel):
+        name, W = self.name, WORKLOADS[self.name]
+        peak_fma, peak_detail = measure_peaks()
+        fp = file_peaks()
+        units_rank = self.units_total / self.world
+        ach_tflops = W["flop_per_unit"] * units_rank / (ms_kernel * 1e-3) / 1e12
+        ach_gbs = W["bytes_per_unit"] * units_rank / (ms_kernel * 1e-3) / 1e9
+        t_fma = W["flop_per_unit"] / (peak_fma * 1e12)
+        t_hbm = W["bytes_per_unit"] / (fp["hbm"] * 1e9)
+        bound = "fma" if t_fma >= t_hbm else "hbm"
+        # Long FIR: the library runs it on the tcgen05 tensor cores (csrc/fir_tc.cu, a banded-Toeplitz GEMM with a
+        # 16-bit operand split), so the binding roofline is the tensor pipe (measured bf16 dense rate).
+        tensor = None
+        on_tensor = name == "fir" and getattr(self.filt, "last_path", "ffma") == "tensor"
+        if on_tensor:
+            T_ = len(self.taps)
+            koff = (T_ - 1 + 31) // 32 * 32
+            band = (koff + 128) / T_  # band of Koff + 128 columns per 128 outputs, zeros included
+            fmt = os.environ.get("SGPU_FIR_TC_FMT", "f16")
+            products = 6.0 if fmt.startswith("b") else 3.0
+            # one f32-accurate real product = `products` 16-bit products (F16x2 block floating point: f1h1, f1h2, f2h1;
+            # BF16x3: six), so the pipe's f32-equivalent peak is the measured 16-bit dense rate / products; `executed`
+            # counts every 16-bit flop the pipe really does
+            executed = products * band
+            f32_eq_peak = fp["bf16"] / products
+            tensor = {"achieved_tflops": ach_tflops, "peak_tflops": f32_eq_peak, "frac": ach_tflops / f32_eq_peak,
+                      "peak_source": f"f32-equivalent tensor peak = 16-bit dense / {products:.0f} "
+                                     f"({'BF16x3: 6' if products == 6 else 'F16x2 block floating point: 3'} MMAs per f32 product); 16-bit dense: " + fp["bf16_src"],
+                      "bf16_peak_tflops": fp["bf16"], "algorithmic_frac_of_bf16_peak": ach_tflops / fp["bf16"],
+                      "executed_16bit_tflops": ach_tflops * executed, "executed_frac_of_bf16_peak": ach_tflops * executed / fp["bf16"],
+                      "executed_over_algorithmic": executed, "band_overhead": band, "products_per_f32_product": products,
+                      "note": "algorithmic flops = 4 per real x complex tap; the tensor pipe executes `products` 16-bit MMAs per K step "
+                              "over a band of (Koff+128)/T columns (Toeplitz zeros), i.e. products x band times the algorithmic flops"}
+            bound = "tensor"
+        # DRAM bytes (read + write) of one launch of the dominant kernel at this workload's full size,
+        # from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture
+        # (tools/profile_round.sh -> tools/traffic_json.py); only valid for the default sizes at N = 1.
+        traffic, traffic_detail = None, None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists() and self.world == 1 and self.args.log2_samples == 30:
+            traffic_detail = json.loads(tf.read_text()).get(name)
+            if traffic_detail:
+                traffic = traffic_detail.get("dram_bytes")
+        kernel = {"fir": "fir_tc_fused_kernel (tcgen05.mma kind::f16, TMA, TMEM) + fir_tc_post_kernel" if on_tensor else "fir_warp_kernel<R=16>",
+                  "fir64": "fir_warp_kernel<R=16> (one launch per call, history written by the same kernel)",
+                  "decim": "fir_decim_warp_kernel<M=8,PS=4>", "ddc": "fir_decim_warp_kernel<M=8,PS=4,NCO mix>",
+                  "interp": "fir_interp_walk_kernel<L=4,K=5>", "iir_batch": "iir_sos_kernel<8>",
+                  "iir_scan": "iir_sos_kernel<8> (chunked scan)", "autocorr": "autocorr_kernel"}[name]
+        r = {
+            "bound": bound,
+            "achieved": ach_gbs if bound == "hbm" else ach_tflops,
+            "peak": {"fma": peak_fma, "hbm": fp["hbm"], "tensor": tensor and tensor["peak_tflops"]}[bound],
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+            "frac": {"fma": ach_tflops / peak_fma, "hbm": ach_gbs / fp["hbm"], "tensor": tensor and tensor["frac"]}[bound],
+            "traffic": traffic,
+            "traffic_detail": traffic_detail,
+            "kernel": kernel,
+            "kernel_ms_per_launch": ms_kernel,
+            "timed": "CUDA events around execute_block inside the timed loop that gives `value`",
+            "algorithmic": {"flop_per_unit": W["flop_per_unit"], "bytes_per_unit": W["bytes_per_unit"], "unit": W["unit"],
+                            "units_per_launch": units_rank},
+            "fma": {"achieved_tflops": ach_tflops, "peak_tflops": peak_fma, "frac": ach_tflops / peak_fma,
+                    "peak_source": "measured live: libsgpu_peakbench FFMA chains (fp32, non-tensor)", "detail": peak_detail},
+            "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": fp["hbm"], "frac": ach_gbs / fp["hbm"], "peak_source": fp["hbm_src"]},
+        }
+        if tensor:
+            r["tensor"] = tensor
+        return r, on_tensor
 
 
 def run_gpu_arm(args):
@@ -246,202 +576,18 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from solid_dsp_b200 import _ffi, launch_count, sharding
-    from solid_dsp_b200.filter.fir import DecimatingFIRFilter, FIRFilter, InterpolatingFIRFilter
-    from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
 
     name = args.workload
-    W = WORKLOADS[name]
-    taps = workload_taps(name)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1000 + rank)
-
-    def rand_c(shape):
-        t = torch.empty(tuple(shape) + (2,), dtype=torch.float32, device=dev)
-        t.uniform_(-1.0, 1.0, generator=gen)
-        return torch.view_as_complex(t)
-
-    halo_prev = None
-    if name == "fir":
-        n_total = 1 << args.log2_samples
-        _, n_loc = sharding.shard_stream(n_total, 1, world, rank)
-        x = rand_c((n_loc,))
-        filt = FIRFilter(taps, 1.0)
-        T = len(taps)
-        halo_prev = torch.zeros(T - 1, dtype=torch.complex64, device=dev)
-        units_total = n_total
-        shape_desc = {"samples": n_total, "taps": T, "segments": world, "halo": T - 1}
-
-        def step():
-            # halo: last T-1 samples of the previous rank's segment (rank 0: zeros = fresh filter)
-            sharding.exchange_halo(x, halo_prev, rank, world, dist)
-            filt.write(halo_prev)
-            return filt.execute_block(x)
-    else:
-        chans = {"decim": 4096, "interp": 1024, "iir_batch": 65536, "iir_scan": 1, "autocorr": 1024}[name]
-        n_per = 1 << {"decim": 20, "interp": 20, "iir_batch": 14, "iir_scan": 28, "autocorr": 20}[name]
-        if args.log2_samples != 30:
-            n_per = 1 << args.log2_samples
-        if name == "iir_scan":
-            c_loc = 1  # one stream: time segments per rank, warm-up halo from the previous rank
-            units_total = n_per
-        else:
-            _, c_loc = sharding.shard_channels(chans, world, rank)
-            units_total = chans * n_per * (4 if name == "interp" else 1)
-        n_loc = n_per
-        if name == "iir_scan" and world > 1:
-            _, n_loc = sharding.shard_stream(n_per, 32, world, rank)
-        x = rand_c((c_loc, n_loc))
-        if name == "decim":
-            filt = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
-        elif name == "interp":
-            filt = InterpolatingFIRFilter(taps, 4, n_channels=c_loc)
-        elif name == "autocorr":
-            from solid_dsp_b200.filter.auto_correlator import AutoCorrelator
-            filt = AutoCorrelator(*taps, n_channels=c_loc)
-        else:
-            filt = IIRFilter(taps[0], taps[1], IIRFilterType.SecondOrder, n_channels=c_loc)
-        shape_desc = {"channels": chans, "samples_per_channel": n_per}
-        if name == "iir_scan" and world > 1:
-            warm = filt.decay_length()
-            assert warm > 0, "the benchmark cascade decays"
-            halo_prev = torch.zeros(warm, dtype=torch.complex64, device=dev)
-            shape_desc.update({"segments": world, "halo": warm})
-
-            def step():
-                sharding.exchange_halo(x[0], halo_prev, rank, world, dist)
-                return sharding.iir_segment(filt, x, halo_prev.unsqueeze(0), rank)
-        else:
-            def step():
-                return filt.execute_block(x)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing: W warm-up, K timed steps between barriers, max over ranks
-    y = None
-    for _ in range(args.warmup):
-        y = step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    l0 = launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        y = step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = launch_count() - l0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    ms_step = ms_total / args.steps
-    value = units_total / (ms_step * 1e-3) / 1e9
-
-    # ---- dominant kernel alone (execute_block only) for the roofline, CUDA events on the same stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    k0.record()
-    for _ in range(args.steps):
-        y = filt.execute_block(x)
-    k1.record()
-    torch.cuda.synchronize()
-    ms_kernel = k0.elapsed_time(k1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- parity spot check on the timed buffers (oracle = checker; rank 0, small windows)
-    parity = None
-    if not args.no_check:
-        y = step()  # known entry state (halo / fresh history) for the buffers that get checked
-        torch.cuda.synchronize()
-        if rank == 0:
-            parity = spot_check(name, taps, filt, x, y, halo_prev)
-
+    wl = Workload(name, args, world, rank, dev, dist)
+    res = wl.run_timed(args.warmup, args.steps)
+    parity = None if args.no_check else wl.parity()
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(name, taps, x, world, rank, dev, units_total, args)
-
+        e2e = measure_e2e(name, wl.taps, wl.x, world, rank, dev, wl.units_total, args)
+    line = None
     if rank == 0:
-        peak_fma, peak_detail = measure_peaks()
-        units_rank = units_total / world
-        ach_tflops = W["flop_per_unit"] * units_rank / (ms_kernel * 1e-3) / 1e12
-        ach_gbs = W["bytes_per_unit"] * units_rank / (ms_kernel * 1e-3) / 1e9
-        peaks_file = ROOT / "MEASURED_PEAKS.json"
-        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        if peaks_file.exists():
-            hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
-            hbm_src = "measured (MEASURED_PEAKS.json)"
-        t_fma = W["flop_per_unit"] / (peak_fma * 1e12)
-        t_hbm = W["bytes_per_unit"] / (hbm_peak * 1e9)
-        bound = "fma" if t_fma >= t_hbm else "hbm"
-        # Long real-tap FIR: the library runs it on the tcgen05 tensor cores (csrc/fir_tc.cu, BF16x3 over a
-        # banded-Toeplitz GEMM), so the binding roofline is the tensor pipe (measured bf16 dense rate).
-        tensor = None
-        if name == "fir" and getattr(filt, "last_path", "ffma") == "tensor":
-            bf16_peak, bf16_src = 1590.0, "fallback (B200_PROFILING.md)"
-            if peaks_file.exists():
-                pk = json.loads(peaks_file.read_text())
-                bf16_peak = float(pk.get("bf16_tflops_sustained") or pk["bf16_tflops"])
-                bf16_src = ("measured (MEASURED_PEAKS.json, bf16_tflops_sustained: the kernel runs for several ms "
-                            "back to back under the power cap)")
-            T_ = len(taps)
-            koff = (T_ - 1 + 31) // 32 * 32
-            band = (koff + 128) / T_            # band of Koff + 128 columns per 128 outputs, zeros included
-            # one f32-accurate real product = 6 bf16 products (b1b1, b1b2, b2b1, b2b2, b1b3, b3b1), so the pipe's
-            # f32-equivalent peak is the measured bf16 rate / 6; `executed` counts every bf16 flop the pipe really does
-            executed = 6.0 * band
-            f32_eq_peak = bf16_peak / 6.0
-            tensor = {"achieved_tflops": ach_tflops, "peak_tflops": f32_eq_peak, "frac": ach_tflops / f32_eq_peak,
-                      "peak_source": "f32-equivalent tensor peak = bf16 dense / 6 (BF16x3 split: 6 bf16 MMAs per f32 product); bf16: " + bf16_src,
-                      "bf16_peak_tflops": bf16_peak,
-                      "executed_bf16_tflops": ach_tflops * executed, "executed_frac_of_bf16_peak": ach_tflops * executed / bf16_peak,
-                      "executed_over_algorithmic": executed, "band_overhead": band,
-                      "note": "algorithmic flops = 4 per real x complex tap; the tensor pipe executes 6 bf16 MMAs per K step "
-                              "over a band of (Koff+128)/T columns (Toeplitz zeros), i.e. 6 x band times the algorithmic flops"}
-            bound = "tensor"
-        # DRAM bytes (read + write) of one launch of the dominant kernel at this workload's full size,
-        # from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` capture
-        # (tools/profile_round.sh -> tools/traffic_json.py); only valid for the default sizes at N = 1.
-        traffic, traffic_detail = None, None
-        tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists() and world == 1 and args.log2_samples == 30:
-            traffic_detail = json.loads(tf.read_text()).get(name)
-            if traffic_detail:
-                traffic = traffic_detail.get("dram_bytes")
-        roofline = {
-            "bound": bound,
-            "achieved": ach_gbs if bound == "hbm" else ach_tflops,
-            "peak": {"fma": peak_fma, "hbm": hbm_peak, "tensor": tensor and tensor["peak_tflops"]}[bound],
-            "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-            "frac": {"fma": ach_tflops / peak_fma, "hbm": ach_gbs / hbm_peak,
-                     "tensor": tensor and tensor["frac"]}[bound],
-            "traffic": traffic,
-            "traffic_detail": traffic_detail,
-            "kernel": {"fir": "fir_tc_fused_kernel<BF16x3> (tcgen05.mma kind::f16, TMA, TMEM)" if tensor else "fir_warp_kernel<R=16>", "decim": "fir_decim_kernel<R=16>",
-                       "interp": "fir_interp_kernel<R=16>", "iir_batch": "iir_sos_kernel<8>",
-                       "iir_scan": "iir_sos_kernel<8> (fused warm-up scan, one launch)",
-                       "autocorr": "autocorr_kernel"}[name],
-            "kernel_ms_per_launch": ms_kernel,
-            "algorithmic": {"flop_per_unit": W["flop_per_unit"], "bytes_per_unit": W["bytes_per_unit"], "unit": W["unit"],
-                            "units_per_launch": units_rank},
-            "fma": {"achieved_tflops": ach_tflops, "peak_tflops": peak_fma, "frac": ach_tflops / peak_fma,
-                    "peak_source": "measured live: libsgpu_peakbench FFMA chains (fp32, non-tensor)", "detail": peak_detail},
-            "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
-        }
-        if tensor:
-            roofline["tensor"] = tensor
+        roofline, on_tensor = wl.roofline(res["ms_kernel"])
         cpu = None
         if world == 1 and not args.no_cpu:
             rate1, what1, _ = cpu_reference_path(name, 1, args.cpu_seconds)
@@ -449,28 +595,64 @@ def run_gpu_arm(args):
             rateN, whatN, _ = cpu_reference_path(name, cores, args.cpu_seconds)
             cpu = {"value": rate1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": what1,
                    "all_cores": {"value": rateN / 1e9, "cores": cores, "sample": whatN}}
+        fmt = os.environ.get("SGPU_FIR_TC_FMT", "f16")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None,
-            "dtype": "f32 (BF16x3 split on the tensor cores: 6 bf16 MMAs per product, f32 accumulation)" if tensor else "f32", "data": "synthetic",
-            "config": {"workload": W["desc"], "name": name, **shape_desc,
-                       "l2": "inputs (>= 2 GiB per rank) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"stream segments x{world} with halo" if name in ("fir", "iir_scan") else f"channels x{world}"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_step"], "higher_is_better": True,
+            "scaling": "weak" if name == "fir64" else "strong", "vs_baseline": None,
+            "dtype": ("f32 (16-bit operand split on the tensor cores, f32 accumulation: "
+                      + ("BF16x3, 6 MMAs per product)" if fmt.startswith("b") else "F16x2 block floating point, 3 MMAs per product)"))
+            if on_tensor else "f32", "data": "synthetic",
+            "config": workload_config(name, world, args.log2_samples),
+            "e2e": e2e, "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity,
         }
+    del wl
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs (default run, one GPU): driver-visible numbers for every config
+    if name == "fir" and world == 1 and args.log2_samples == 30 and not args.no_workloads:
+        block = {}
+        for other in ("fir64", "decim", "interp", "iir_batch", "iir_scan"):
+            try:
+                block[other] = run_side_workload(other, args, dev, dist)
+            except Exception as e:  # noqa: BLE001  (a failing side workload must not take the headline line with it)
+                block[other] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        line["workloads"] = block
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def spot_check(name, taps, filt, x, y, halo_prev):
+def run_side_workload(name, args, dev, dist):
+    """One of the other BASELINE configs at its full size, about 5 s: device-resident value, kernel time, both roofline
+    denominators, oracle parity, clocks, 1-core cpu_baseline."""
+    wl = Workload(name, args, 1, 0, dev, dist)
+    steps = 200 if name == "fir64" else 10
+    res = wl.run_timed(3, steps)
+    parity = None if args.no_check else wl.parity()
+    roofline, _ = wl.roofline(res["ms_kernel"])
+    cpu = None
+    if not args.no_cpu:
+        rate1, what1, _ = cpu_reference_path(name, 1, min(args.cpu_seconds, 3.0))
+        cpu = {"value": rate1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": what1}
+    out = {"config": workload_config(name, 1, args.log2_samples), "value": res["value"], "unit": UNIT, "steps": steps,
+           "warmup": 3, "ms_per_step": res["ms_step"], "kernel_ms": res["ms_kernel"], "gpu_launches": res["launches"],
+           "clocks": res["clocks"],
+           "roofline": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel")},
+           "roofline_frac_fma": roofline["fma"]["frac"], "roofline_frac_hbm": roofline["hbm"]["frac"],
+           "parity": parity, "cpu_baseline": cpu}
+    if name in ("decim", "interp"):
+        out["unit_note"] = "decim: input samples/s; interp: output samples/s"
+    return out
+
+
+def spot_check(name, taps, filt, x, y, halo_prev, rank=0):
     """Oracle check of a few windows of the buffers that were just timed."""
     import oracle as O
-    import torch
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(7 + rank)
     worst = 0.0
     windows = []
 
@@ -480,6 +662,7 @@ def spot_check(name, taps, filt, x, y, halo_prev):
     if name == "fir":
         T = len(taps)
         n = x.shape[0]
+        # window 0 = the first 4096 outputs: on rank r > 0 they depend on the halo received from rank r - 1
         for start in [0] + [int(s) for s in rng.integers(T, max(T + 1, n - 4096), 3)] + [n - 4096]:
             start = max(0, min(start, n - 4096))
             lo = max(0, start - (T - 1))
@@ -491,7 +674,19 @@ def spot_check(name, taps, filt, x, y, halo_prev):
             e = nerr(y[start:start + 4096].cpu().numpy(), ref)
             windows.append([start, e])
             worst = max(worst, e)
-    elif name == "decim":
+    elif name == "fir64":
+        # the handle streams over the rotating rows: check the row of the last call on a fresh handle
+        from solid_dsp_b200.filter.fir import FIRFilter
+        row = int(rng.integers(0, x.shape[0]))
+        got = FIRFilter(taps, 1.0).execute_block(x[row]).cpu().numpy()
+        xs = x[row].cpu().numpy()
+        for start in (0, 500000, (1 << 20) - 8192):
+            lo = max(0, start - 63)
+            ref = O.fir_fast(taps, xs[lo:start + 8192])[start - lo:]
+            e = nerr(got[start:start + 8192], ref)
+            windows.append([row, start, e])
+            worst = max(worst, e)
+    elif name in ("decim", "ddc"):
         # the timed handle streams (history = tail of the previous step): compare outputs that
         # depend only on this call's inputs, i.e. skip the first ceil(T/M) of every window
         skip = len(taps) // 8 + 1
@@ -499,6 +694,8 @@ def spot_check(name, taps, filt, x, y, halo_prev):
         for c in rng.integers(0, x.shape[0], 3):
             for start in (0, (n // 2) & ~7, n - (1 << 15)):
                 xs = x[int(c), start:start + (1 << 15)].cpu().numpy()
+                if name == "ddc":  # the NCO phase at sample `start` of this step: the handle's phase advanced n per step
+                    xs = O.nco_mix_down_block(xs[None, :], DDC_FREQ, phase0=filt.phase_at(start))[0]
                 ref = O.fir_fast(taps, xs, 1.0, 8)[skip:]
                 got = y[int(c), start // 8 + skip:start // 8 + skip + len(ref)].cpu().numpy()
                 e = nerr(got, ref)
@@ -557,14 +754,20 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
     from solid_dsp_b200.filter.fir import DecimatingFIRFilter, FIRFilter, InterpolatingFIRFilter
     from solid_dsp_b200.filter.iir import IIRFilter, IIRFilterType
 
+    if name == "fir64":
+        x = x[0]
     two_d = x.dim() == 2
     c_loc = x.shape[0] if two_d else 1
     n_in = x.shape[-1]
-    if name == "fir":
+    if name in ("fir", "fir64"):
         f = FIRFilter(taps, 1.0)
         n_out = n_in
     elif name == "decim":
         f = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
+        n_out = n_in // 8
+    elif name == "ddc":
+        from solid_dsp_b200.filter.ddc import DigitalDownConverter
+        f = DigitalDownConverter(taps, 1.0, 8, DDC_FREQ, n_channels=c_loc)
         n_out = n_in // 8
     elif name == "interp":
         f = InterpolatingFIRFilter(taps, 4, n_channels=c_loc)
@@ -579,9 +782,11 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
     hin = torch.empty((c_loc, n_in), dtype=torch.complex64, pin_memory=True)
     hout = torch.empty((c_loc, n_out), dtype=torch.complex64, pin_memory=True)
     hin.copy_(x.reshape(c_loc, n_in))
-    fn = {"fir": _ffi.lib.sgpu_fir_execute_block, "decim": _ffi.lib.sgpu_fir_execute_block,
-          "interp": _ffi.lib.sgpu_interp_execute_block,
+    fn = {"fir": _ffi.lib.sgpu_fir_execute_block, "fir64": _ffi.lib.sgpu_fir_execute_block,
+          "decim": _ffi.lib.sgpu_fir_execute_block, "interp": _ffi.lib.sgpu_interp_execute_block,
           "autocorr": _ffi.lib.sgpu_autocorr_execute_block}.get(name, _ffi.lib.sgpu_iir_execute_block)
+    if name == "ddc":
+        fn = _ffi.lib.sgpu_ddc_execute_block
     got = _ffi.c_size()
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -589,7 +794,7 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
         _ffi.check(fn(f._h, hin.data_ptr(), n_in, n_in, hout.data_ptr(), n_out, C.byref(got), _ffi.HOST, stream))
 
     step()  # warm-up (allocates the handle's staging buffers)
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 3)) if name != "fir64" else 50
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -602,8 +807,8 @@ def measure_e2e(name, taps, x, world, rank, dev, units_total, args):
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    h2d = c_loc * n_in * 8 * world if name != "fir" else n_in * 8 * world
-    d2h = c_loc * n_out * 8 * world if name != "fir" else n_out * 8 * world
+    h2d = c_loc * n_in * 8 * world
+    d2h = c_loc * n_out * 8 * world
     checksum = complex(hout[0, :16].sum().item())
     return {"value": units_total / (dt / steps) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * dt / steps,
@@ -622,6 +827,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the block of the other BASELINE configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

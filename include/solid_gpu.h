@@ -11,11 +11,14 @@
  *   - Every function returns an int status: SGPU_OK (0) or a negative sgpu_status.
  *     Construction errors map one-to-one onto the reference's error enums; execute never
  *     fails in the reference, here it can only fail with SGPU_ERR_CUDA / _CAPACITY /
- *     _INVALID_ARGUMENT.  sgpu_last_error() returns a thread-local message.
+ *     _INVALID_ARGUMENT (the latter includes `in` and `out` ranges that overlap: execute_block
+ *     is not an in-place operation, the kernels read a tile's halo while other blocks already
+ *     write outputs).  sgpu_last_error() returns a thread-local message.
  *   - Samples are cf32: interleaved (re, im) floats, 8 bytes per sample.  Buffers are
  *     channel-major: channel c starts at base + c * stride (stride in SAMPLES).  One
- *     "channel" is one reference filter object; all channels of a handle share the taps
- *     and advance in lock-step.
+ *     "channel" is one reference filter object; the channels of a handle advance in
+ *     lock-step and share the taps unless the handle was made by a *_create_per_channel
+ *     constructor (every reference object owns its coefficients, fir/mod.rs:79-88).
  *   - Coefficients cross the boundary as doubles (the reference's Coef = f64 /
  *     Complex<f64>) and are rounded once to f32 inside; arithmetic is f32 FMA.
  *   - `mem` says where `in`/`out` live.  SGPU_DEVICE: pointers are device pointers on the
@@ -103,6 +106,14 @@ uint64_t sgpu_launch_count(void);
 int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
                     double scale_re, double scale_im, int is_decimator, size_t decimation,
                     sgpu_fir **out);
+/* As sgpu_fir_create, but every channel owns its taps: taps holds n_channels * n_taps values
+ * (x2 when complex), channel c uses [c * n_taps, (c + 1) * n_taps) -- n_channels independent
+ * FIRFilter::new / DecimatingFIRFilter::new objects of equal length in one handle.  These
+ * handles run on the FP32 kernels (the tensor-core band matrix is shared by all channels). */
+int sgpu_fir_create_per_channel(const double *taps, size_t n_taps, sgpu_tapkind kind,
+                                size_t n_channels, double scale_re, double scale_im,
+                                int is_decimator, size_t decimation, sgpu_fir **out);
+int sgpu_fir_taps_per_channel(const sgpu_fir *f); /* 1 for a *_per_channel handle */
 int sgpu_fir_destroy(sgpu_fir *f); /* Drop */
 /* #[derive(Clone)] fir/mod.rs:58 -- deep copy incl. history and decimator phase */
 int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out);
@@ -131,6 +142,8 @@ int sgpu_fir_last_path(const sgpu_fir *f);
 /* FIRFilter::coefficients (fir/mod.rs:176-178): the STORED (reversed) order, as doubles of
  * the f32 values used on the device.  out: n_taps (REAL) or 2*n_taps (COMPLEX) doubles. */
 int sgpu_fir_coefficients(const sgpu_fir *f, double *out);
+/* The same for one channel of a *_per_channel handle (any handle: channel < n_channels). */
+int sgpu_fir_channel_coefficients(const sgpu_fir *f, size_t channel, double *out);
 /* Streaming state (what Window + current_item hold): history = last T-1 inputs per channel,
  * oldest first, [n_channels][T-1] cf32 on the HOST; current_item as in fir/decim.rs:8. */
 int sgpu_fir_get_state(sgpu_fir *f, float *history, uint64_t *current_item);
@@ -150,6 +163,9 @@ int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapkind kind, siz
                        size_t interpolation, sgpu_interp **out);
 int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
                     size_t filters, double scale_re, double scale_im, sgpu_interp **out);
+/* Every channel owns its taps ([n_channels][n_taps]), see sgpu_fir_create_per_channel. */
+int sgpu_interp_create_per_channel(const double *taps, size_t n_taps, sgpu_tapkind kind,
+                                   size_t n_channels, size_t interpolation, sgpu_interp **out);
 int sgpu_interp_destroy(sgpu_interp *f);
 int sgpu_interp_clone(const sgpu_interp *f, sgpu_interp **out);
 /* Filter::execute_block (fir/interp.rs:102-111): *n_out = n_in * L per channel. */

@@ -53,6 +53,11 @@ extern "C" {
     pub fn sgpu_fir_create(taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
                            scale_re: c_double, scale_im: c_double, is_decimator: c_int,
                            decimation: size_t, out: *mut *mut sgpu_fir) -> c_int;
+    pub fn sgpu_fir_create_per_channel(taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
+                                       scale_re: c_double, scale_im: c_double, is_decimator: c_int,
+                                       decimation: size_t, out: *mut *mut sgpu_fir) -> c_int;
+    pub fn sgpu_fir_taps_per_channel(f: *const sgpu_fir) -> c_int;
+    pub fn sgpu_fir_channel_coefficients(f: *const sgpu_fir, channel: size_t, out: *mut c_double) -> c_int;
     pub fn sgpu_fir_destroy(f: *mut sgpu_fir) -> c_int;
     pub fn sgpu_fir_clone(f: *const sgpu_fir, out: *mut *mut sgpu_fir) -> c_int;
     pub fn sgpu_fir_execute_block(f: *mut sgpu_fir, input: *const c_float, n_in: size_t, in_stride: size_t,
@@ -77,6 +82,8 @@ extern "C" {
     pub fn sgpu_pfb_create(taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
                            filters: size_t, scale_re: c_double, scale_im: c_double,
                            out: *mut *mut sgpu_interp) -> c_int;
+    pub fn sgpu_interp_create_per_channel(taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
+                                          interpolation: size_t, out: *mut *mut sgpu_interp) -> c_int;
     pub fn sgpu_interp_destroy(f: *mut sgpu_interp) -> c_int;
     pub fn sgpu_interp_clone(f: *const sgpu_interp, out: *mut *mut sgpu_interp) -> c_int;
     pub fn sgpu_interp_execute_block(f: *mut sgpu_interp, input: *const c_float, n_in: size_t,

@@ -79,13 +79,14 @@ class OutBuf:
 
 
 def as_doubles(coefs):
-    """-> (contiguous float64 view for the ABI, tap kind, n_taps, original array)"""
+    """-> (contiguous float64 view for the ABI, tap kind, n_taps, original array).  A 2-D array [C, T] means one tap
+    set per channel (n_taps = T)."""
     a = np.asarray(coefs)
     if np.iscomplexobj(a):
         a = np.ascontiguousarray(a, dtype=np.complex128)
-        return a.view(np.float64), _ffi.TAPS_COMPLEX, a.shape[0], a
+        return a.view(np.float64), _ffi.TAPS_COMPLEX, a.shape[-1], a
     a = np.ascontiguousarray(a, dtype=np.float64)
-    return a, _ffi.TAPS_REAL, a.shape[0], a
+    return a, _ffi.TAPS_REAL, a.shape[-1], a
 
 
 def dptr(a):

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "sgpu_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4 + [c_sizep]),
     "sgpu_launch_count": (C.c_uint64, []),
     "sgpu_fir_create": (C.c_int, [c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, C.c_int, c_size, vpp]),
+    "sgpu_fir_create_per_channel": (C.c_int, [c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, C.c_int, c_size, vpp]),
+    "sgpu_fir_taps_per_channel": (C.c_int, [vp]),
+    "sgpu_fir_channel_coefficients": (C.c_int, [vp, c_size, c_dp]),
     "sgpu_fir_destroy": (C.c_int, [vp]),
     "sgpu_fir_clone": (C.c_int, [vp, vpp]),
     "sgpu_fir_execute_block": (C.c_int, [vp, vp, c_size, c_size, vp, c_size, c_sizep, C.c_int, vp]),
@@ -75,6 +78,7 @@ PROTOTYPES = {
     "sgpu_fir_reset": (C.c_int, [vp]),
     "sgpu_interp_create": (C.c_int, [c_dp, c_size, C.c_int, c_size, c_size, vpp]),
     "sgpu_pfb_create": (C.c_int, [c_dp, c_size, C.c_int, c_size, c_size, C.c_double, C.c_double, vpp]),
+    "sgpu_interp_create_per_channel": (C.c_int, [c_dp, c_size, C.c_int, c_size, c_size, vpp]),
     "sgpu_interp_destroy": (C.c_int, [vp]),
     "sgpu_interp_clone": (C.c_int, [vp, vpp]),
     "sgpu_interp_execute_block": (C.c_int, [vp, vp, c_size, c_size, vp, c_size, c_sizep, C.c_int, vp]),

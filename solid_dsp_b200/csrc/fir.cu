@@ -7,7 +7,6 @@
 //   Window::push / to_vec               window/mod.rs:63-71,44-51  (history: hist_update_kernel)
 //   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
 #include "fir_core.cuh"
-#include "fir_pipe.cuh"
 #include "fir_tc.cuh"
 #include "sgpu_common.cuh"
 
@@ -21,7 +20,9 @@ struct FirArgs {
     const float2 *in;
     float2 *out;
     const float2 *hist;  // [C][T-1], oldest first (state entering this call)
-    const float *taps;   // [nsets][Qpad] taps (x2 floats when PACKED), device
+    float2 *hist_new;    // [C][T-1]: state leaving this call, written by the last block of every channel (NULL: not here)
+    const float *taps;   // [nsets][Qpad] taps (x2 floats for complex taps), device; channel c reads taps + c * tap_stride
+    long long tap_stride;  // floats between the tap images of two channels (0: all channels share one image)
     long long in_stride, out_stride;
     long long n_in, n_out;  // per channel
     int T;                  // taps of the full filter
@@ -51,6 +52,27 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// new history = last T-1 samples of (old history ++ x[0..n_in))   (Window::push, window/mod.rs:63-71), written by the
+// LAST block of every channel's grid row before it starts on its tile: execute_block is one launch.  The old and the
+// new tail are different buffers (ping-pong), so the blocks that still read the old one are not disturbed.
+__device__ __forceinline__ void hist_tail_update(const FirArgs &a, const int ch, const int tid, const int nthr) {
+    if (a.hist_new == nullptr || blockIdx.x != gridDim.x - 1) return;
+    const int H = a.T - 1;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ ho = a.hist + (long long)ch * H;
+    float2 *__restrict__ hn = a.hist_new + (long long)ch * H;
+    for (int i = tid; i < H; i += nthr) {
+        const long long s = a.n_in - H + i;
+        float2 v;
+        if (s >= 0) v = x[s];
+        else {
+            const long long h = (long long)H + s;
+            v = h >= 0 ? ho[h] : make_float2(0.f, 0.f);
+        }
+        hn[i] = v;
+    }
+}
 
 // --------------------------------------------------------------------------------------------
 // FIR (M1 = true) and decimating FIR.  Block = NT threads, tile = NT*R outputs of one channel.
@@ -83,10 +105,11 @@ __global__ void __launch_bounds__(NT, MINB) fir_decim_kernel(const FirArgs a) {
     const long long m_base = (long long)blockIdx.x * (OT * R);
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
+    hist_tail_update(a, ch, tid, NT);
 
     {  // taps image -> shared memory
         const int n4 = M * (Qpad * TW + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
     }
@@ -256,10 +279,11 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_kernel(const FirArgs a) {
     const long long n_base = (long long)blockIdx.x * (OT * R);
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);  // a.T - 1 = S samples kept
+    hist_tail_update(a, ch, tid, NT);
 
     {
         const int n4 = L * (Qpad * TW + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
     }
@@ -337,12 +361,12 @@ __global__ void hist_update_kernel(const float2 *__restrict__ in, long long in_s
 // hist holds the last S-1 samples; the window's newest element is hist[S-2] ... the PFB window
 // has capacity S, so the bank keeps S samples: we store S-1 "history" plus the newest in `last`.
 __global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const float *__restrict__ taps,
-                                 int Qpad, int tw, int phase, float2 *__restrict__ out, int C) {
+                                 long long tap_stride, int Qpad, int tw, int phase, float2 *__restrict__ out, int C) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= C) return;
     // window (newest first) = hist[S-1], hist[S-2], ..., hist[0]  with hist of S samples
     const float2 *h = hist + (long long)ch * S;
-    const float *g = taps + (size_t)phase * (Qpad * tw + kTapSkew);
+    const float *g = taps + (long long)ch * tap_stride + (size_t)phase * (Qpad * tw + kTapSkew);
     float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < S; ++j) {
         const float2 w = h[S - 1 - j];
@@ -357,6 +381,53 @@ __global__ void pfb_phase_kernel(const float2 *__restrict__ hist, int S, const f
         }
     }
     out[ch] = acc;
+}
+
+// --------------------------------------------------------------------------------------------
+// Direct form, one thread per output: the path for shapes whose tile does not fit the 227 KB of shared memory (the
+// reference takes any decimation / interpolation factor and any length: fir/decim.rs:27-42, fir/interp.rs:27-54),
+// e.g. 256 taps at M = 64.  Sequential dot product in the reference's order (dot_product/mod.rs:159-170) over the
+// tap image in global memory.  INTERP = false: y[m] = scale * sum_k g[k] x[m M + (M-1-c0) - k], g[q M + p] at
+// image[p][q];  INTERP = true: y[n L + p] = sum_j image[p][j] x[n - j] (a.M = L, a.T - 1 = S).
+template <bool INTERP, bool CT>
+__global__ void __launch_bounds__(128) fir_direct_kernel(const FirArgs a) {
+    constexpr int TW = CT ? 2 : 1;
+    const int ch = blockIdx.y;
+    hist_tail_update(a, ch, threadIdx.x, 128);
+    const long long o = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (o >= a.n_out) return;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
+    const float *__restrict__ img = a.taps + (long long)ch * a.tap_stride;
+    const int rs = a.Qpad * TW + kTapSkew;
+    float yr = 0.f, yi = 0.f;
+    auto mac = [&](const float *g, const float2 w) {
+        if constexpr (CT) {  // (gr + j gi)(wx + j wy)
+            yr += g[0] * w.x - g[1] * w.y;
+            yi += g[0] * w.y + g[1] * w.x;
+        } else {
+            yr = fmaf(g[0], w.x, yr);
+            yi = fmaf(g[0], w.y, yi);
+        }
+    };
+    if constexpr (INTERP) {
+        const long long n = o / a.M;
+        const float *g = img + (size_t)(o - n * a.M) * rs;
+        const int S = a.T - 1;
+        for (int j = 0; j < S; ++j) mac(g + (size_t)j * TW, fetch_sample(x, hist, n - j, a.n_in, a.T));
+        a.out[(long long)ch * a.out_stride + o] = make_float2(yr, yi);  // no scale: pfb.rs:85-90
+    } else {
+        const long long n = o * a.M + (a.M - 1 - a.c0);
+        int p = 0, q = 0;
+        for (int k = 0; k < a.T; ++k) {
+            mac(img + (size_t)p * rs + (size_t)q * TW, fetch_sample(x, hist, n - k, a.n_in, a.T));
+            if (++p == a.M) { p = 0; ++q; }
+        }
+        float2 y;
+        if constexpr (CT) y = make_float2(yr * a.scale_re - yi * a.scale_im, yr * a.scale_im + yi * a.scale_re);
+        else y = make_float2(yr * a.scale_re, yi * a.scale_re);
+        a.out[(long long)ch * a.out_stride + o] = y;
+    }
 }
 
 #include "fir_walk.cuh"
@@ -405,17 +476,20 @@ struct sgpu_fir {
     int device = 0, sm_count = 0;
     size_t T = 0, C = 0, M = 1;
     bool is_decim = false, complex_taps = false, packed = true;
+    bool per_channel = false;     // every channel owns its taps (one reference object per channel, fir/mod.rs:79-88)
     double scale_re = 1.0, scale_im = 0.0;
-    std::vector<float> taps_f32;  // caller order h[0..T), rounded to f32 (x2 when complex)
+    std::vector<float> taps_f32;  // caller order h[0..T), rounded to f32 (x2 when complex); [C][T] when per_channel
     uint64_t current_item = 0;    // fir/decim.rs:8
     size_t ch_off = 0;            // first channel of the block being launched (grids carry <= 65535 channels in y)
     int Q = 0, Qpad = 0;          // taps per phase
-    float *d_taps = nullptr;      // tap image
+    size_t img_floats = 0;        // floats of one tap image
+    float *d_taps = nullptr;      // tap image(s)
     float2 *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
+    bool hist_written = false;    // the launch of this call wrote the new history tail into d_hist[cur ^ 1]
     Staging stage;
     HostPipe pipe;
-    FirTcState *tc = nullptr;     // tensor-core path for long real-tap filters (fir_tc.cu), built on first use
+    FirTcState *tc = nullptr;     // tensor-core path for long filters (fir_tc.cu), built on first use
     bool tc_tried = false;
     int last_path = 0;            // 0 = FFMA2 kernels, 1 = tensor cores
 };
@@ -429,23 +503,27 @@ static int fir_upload_taps(sgpu_fir *f) {
     // sub-filters of <= 16 taps: single-chunk instantiations of the warp-private kernels (no zero padding to 32)
     if (f->Q <= kR && !f->complex_taps && f->packed && (f->M == 1 || f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32))
         f->Qpad = kR;
-    // g[k] = h[T-1-k] (REVERSE, fir/mod.rs:86); phase p filter: g_p[q] = g[q*M + p]
-    std::vector<float> ph((size_t)M * f->Q * tw, 0.f);
-    for (int k = 0; k < T; ++k)
-        for (int c = 0; c < tw; ++c)
-            ph[((size_t)(k % M) * f->Q + k / M) * tw + c] = f->taps_f32[(size_t)(T - 1 - k) * tw + c];
-    std::vector<float> img;
-    build_tap_image(ph, M, f->Q, f->Qpad, tw, img);
+    const size_t nimg = f->per_channel ? f->C : 1;
+    std::vector<float> all, img, ph((size_t)M * f->Q * tw);
+    for (size_t c = 0; c < nimg; ++c) {
+        // g[k] = h[T-1-k] (REVERSE, fir/mod.rs:86); phase p filter: g_p[q] = g[q*M + p]
+        std::fill(ph.begin(), ph.end(), 0.f);
+        const float *h = f->taps_f32.data() + c * (size_t)T * tw;
+        for (int k = 0; k < T; ++k)
+            for (int cc = 0; cc < tw; ++cc) ph[((size_t)(k % M) * f->Q + k / M) * tw + cc] = h[(size_t)(T - 1 - k) * tw + cc];
+        build_tap_image(ph, M, f->Q, f->Qpad, tw, img);
+        f->img_floats = img.size();
+        all.insert(all.end(), img.begin(), img.end());
+    }
     if (f->d_taps) cudaFree(f->d_taps);
     f->d_taps = nullptr;
-    SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
-    SGPU_CUDA(cudaMemcpy(f->d_taps, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SGPU_CUDA(cudaMalloc(&f->d_taps, all.size() * sizeof(float)));
+    SGPU_CUDA(cudaMemcpy(f->d_taps, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
     return SGPU_OK;
 }
 
-SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
-                                double scale_re, double scale_im, int is_decimator, size_t decimation,
-                                sgpu_fir **out) {
+static int fir_create_impl(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels, bool per_channel,
+                           double scale_re, double scale_im, int is_decimator, size_t decimation, sgpu_fir **out) {
     if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "fir_create: out is NULL");
     *out = nullptr;
     if (n_taps == 0 || !taps)  // fir/mod.rs:80-82, decim.rs:28-29
@@ -453,7 +531,7 @@ SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind 
     if (is_decimator && decimation < 1)  // decim.rs:30-31
         return fail(SGPU_ERR_FIR_DECIMATION_LESS_THAN_ONE, "FIR Filter Error DecimationLessThanOne");
     if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "fir_create: n_channels == 0");
-    if (n_taps > (1u << 20) || (is_decimator && decimation > 4096))
+    if (n_taps > (1u << 20) || (is_decimator && decimation > (1u << 20)))
         return fail(SGPU_ERR_UNSUPPORTED, "fir_create: n_taps/decimation beyond supported range");
     int dev = 0, sms = 0;
     int st = require_device(&dev, &sms);
@@ -469,10 +547,12 @@ SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind 
     f->scale_re = scale_re;
     f->scale_im = scale_im;
     f->complex_taps = kind == SGPU_TAPS_COMPLEX;
+    f->per_channel = per_channel;
     f->packed = f->complex_taps ? true : packed_default();
     const size_t tw = f->complex_taps ? 2 : 1;
-    f->taps_f32.resize(n_taps * tw);
-    for (size_t i = 0; i < n_taps * tw; ++i) f->taps_f32[i] = (float)taps[i];
+    const size_t nt = n_taps * tw * (per_channel ? n_channels : 1);
+    f->taps_f32.resize(nt);
+    for (size_t i = 0; i < nt; ++i) f->taps_f32[i] = (float)taps[i];
     st = fir_upload_taps(f);
     if (st) { sgpu_fir_destroy(f); return st; }
     const size_t hbytes = n_channels * (n_taps > 1 ? n_taps - 1 : 1) * sizeof(float2);
@@ -485,6 +565,18 @@ SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind 
     }
     *out = f;
     return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_fir_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                double scale_re, double scale_im, int is_decimator, size_t decimation,
+                                sgpu_fir **out) {
+    return fir_create_impl(taps, n_taps, kind, n_channels, false, scale_re, scale_im, is_decimator, decimation, out);
+}
+
+SGPU_EXPORT int sgpu_fir_create_per_channel(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                            double scale_re, double scale_im, int is_decimator, size_t decimation,
+                                            sgpu_fir **out) {
+    return fir_create_impl(taps, n_taps, kind, n_channels, true, scale_re, scale_im, is_decimator, decimation, out);
 }
 
 SGPU_EXPORT int sgpu_fir_destroy(sgpu_fir *f) {
@@ -508,6 +600,7 @@ SGPU_EXPORT size_t sgpu_fir_len(const sgpu_fir *f) { return f ? f->T : 0; }
 SGPU_EXPORT size_t sgpu_fir_decimation(const sgpu_fir *f) { return f ? f->M : 0; }
 SGPU_EXPORT size_t sgpu_fir_channels(const sgpu_fir *f) { return f ? f->C : 0; }
 SGPU_EXPORT int sgpu_fir_last_path(const sgpu_fir *f) { return f ? f->last_path : 0; }
+SGPU_EXPORT int sgpu_fir_taps_per_channel(const sgpu_fir *f) { return f && f->per_channel ? 1 : 0; }
 
 SGPU_EXPORT int sgpu_fir_set_scale(sgpu_fir *f, double re, double im) {
     if (!f) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
@@ -521,13 +614,16 @@ SGPU_EXPORT int sgpu_fir_get_scale(const sgpu_fir *f, double *re, double *im) {
     if (im) *im = f->scale_im;
     return SGPU_OK;
 }
-SGPU_EXPORT int sgpu_fir_coefficients(const sgpu_fir *f, double *out) {
+SGPU_EXPORT int sgpu_fir_channel_coefficients(const sgpu_fir *f, size_t channel, double *out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    if (channel >= f->C) return fail(SGPU_ERR_INVALID_ARGUMENT, "channel %zu >= %zu", channel, f->C);
     const size_t tw = f->complex_taps ? 2 : 1;
+    const float *h = f->taps_f32.data() + (f->per_channel ? channel * f->T * tw : 0);
     for (size_t i = 0; i < f->T; ++i)  // stored (reversed) order
-        for (size_t c = 0; c < tw; ++c) out[i * tw + c] = (double)f->taps_f32[(f->T - 1 - i) * tw + c];
+        for (size_t c = 0; c < tw; ++c) out[i * tw + c] = (double)h[(f->T - 1 - i) * tw + c];
     return SGPU_OK;
 }
+SGPU_EXPORT int sgpu_fir_coefficients(const sgpu_fir *f, double *out) { return sgpu_fir_channel_coefficients(f, 0, out); }
 
 namespace {
 
@@ -537,7 +633,13 @@ int set_smem(K kernel, size_t bytes) {
     return SGPU_OK;
 }
 
-// Enqueue the history update for a handle (ping-pong) on `s`.
+// [ib, ib + span_in) and [ob, ob + span_out) share a byte
+bool ranges_overlap(const void *in, size_t span_in, const void *out, size_t span_out) {
+    const char *ib = reinterpret_cast<const char *>(in), *ob = reinterpret_cast<const char *>(out);
+    return span_in && span_out && ib < ob + span_out && ob < ib + span_in;
+}
+
+// Enqueue the stand-alone history update for a handle (ping-pong) on `s`: write / push, and calls that produce no output.
 int enqueue_hist_update(const float2 *d_in, long long in_stride, long long n_in, float2 *hist[2], int &cur,
                         size_t C, size_t H, cudaStream_t s) {
     if (H == 0 || n_in == 0) return SGPU_OK;
@@ -577,7 +679,9 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     a.in = d_in;
     a.out = d_out;
     a.hist = f->d_hist[f->cur] + f->ch_off * (f->T - 1);
-    a.taps = f->d_taps;
+    a.hist_new = f->d_hist[f->cur ^ 1] + f->ch_off * (f->T - 1);  // every kernel below writes the new tail itself
+    a.taps = f->d_taps + (f->per_channel ? f->ch_off * f->img_floats : 0);
+    a.tap_stride = f->per_channel ? (long long)f->img_floats : 0;
     a.in_stride = in_stride;
     a.out_stride = out_stride;
     a.n_in = n_in;
@@ -590,91 +694,30 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (out_stride % 2 == 0);
     a.scale_re = (float)f->scale_re;
     a.scale_im = (float)f->scale_im;
-    const int tw = 1;
-    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8) && f->packed && !f->complex_taps &&
-        f->Qpad % (2 * kR) == 0 && env_int("SGPU_PIPE_DEC", 0)) {
-        // persistent multi-stage decimator (fir_pipe.cuh).  Measured SLOWER than the one-tile-per-block
-        // kernel below on B200 (257 vs 338 G input samples/s on config 3's shape: the ring spends shared
-        // memory on in-flight stages instead of resident warps), so it is opt-in for experiments only.
-        int PS = f->M >= 4 ? 4 : 2;
-        const int want = env_int("SGPU_DEC_PS", 0);
-        if ((want == 2 || want == 4) && want <= (int)f->M) PS = want;
-        int NS = env_int("SGPU_PIPE_STAGES", 3);
-        if (NS < 2 || NS > 3) NS = 3;
-        const int OT = kNT / PS;
-        const int rows = f->Qpad / kR + OT;
-        const int RS = rows | 1;
-        const size_t plane_f4 = (size_t)(kR / 2) * RS + 1;
-        const size_t taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * tw * sizeof(float);
-        auto smem_for = [&](int ns) { return (size_t)ns * f->M * plane_f4 * sizeof(float4) + taps_b; };
-        while (NS > 2 && smem_for(NS) > (size_t)kMaxSmem) --NS;
-        const long long tiles_total = ((n_out + (long long)OT * kR - 1) / ((long long)OT * kR)) * (long long)f->C;
-        if (smem_for(NS) <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
-            FirPipeArgs pa{};
-            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur] + f->ch_off * (f->T - 1); pa.taps = f->d_taps;
-            pa.in_stride = in_stride; pa.out_stride = out_stride; pa.n_in = n_in; pa.n_out = n_out;
-            pa.tiles_per_ch = (int)((n_out + (long long)OT * kR - 1) / ((long long)OT * kR));
-            pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
-            pa.T = (int)f->T; pa.M = (int)f->M; pa.c0 = (int)f->current_item; pa.Qpad = f->Qpad; pa.RS = RS;
-            pa.vec_out = a.vec_out; pa.scale_re = (float)f->scale_re;
-            const size_t smem = smem_for(NS);
-            int st = SGPU_OK;
-            int per_sm = 0;
-#define LAUNCH_DPIPE(PK, PSV, NSV)                                                                     \
-    do {                                                                                               \
-        void (*kern)(const FirPipeArgs) = nullptr;                                                     \
-        switch ((int)f->M / PSV) {                                                                     \
-            case 1: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 1, NSV, 1>; break;                  \
-            case 2: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 2, NSV, 1>; break;                  \
-            default: kern = fir_decim_pipe_kernel<kR, PK, kNT, PSV, 4, NSV, 1>; break;                 \
-        }                                                                                              \
-        st = set_smem(kern, smem);                                                                     \
-        if (st) return st;                                                                             \
-        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smem));            \
-        long long blocks = (long long)f->sm_count * (per_sm > 0 ? per_sm : 1);                         \
-        if (blocks > pa.total_tiles) blocks = pa.total_tiles;                                          \
-        kern<<<(unsigned)blocks, kNT, smem, s>>>(pa);                                                  \
-    } while (0)
-#define LAUNCH_DPIPE_NS(PK, PSV)                      \
-    do {                                              \
-        if (NS == 2) LAUNCH_DPIPE(PK, PSV, 2);        \
-        else LAUNCH_DPIPE(PK, PSV, 3);                \
-    } while (0)
-            if (PS == 4) LAUNCH_DPIPE_NS(true, 4);
-            else LAUNCH_DPIPE_NS(true, 2);
-#undef LAUNCH_DPIPE_NS
-#undef LAUNCH_DPIPE
-            SGPU_LAUNCH_CHECK();
-            count_launch();
-            return SGPU_OK;
-        }
-    }
     f->last_path = 0;
-    if (n_out > 0 && f->M == 1 && (f->complex_taps || f->scale_im == 0.0) &&
-        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) && f->T <= 16384 /* band matrix: 768 B per tap */ &&
+    if (n_out <= 0) return SGPU_OK;  // a decimator call shorter than one period: the caller enqueues the history update
+    if (f->M == 1 && !f->per_channel && (f->complex_taps || f->scale_im == 0.0) &&
+        (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) && f->T <= 16384 /* band matrix: 512 B per tap */ &&
         n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 15) && env_int("SGPU_FIR_TC", 1)) {
-        // Long filters (real or complex taps): banded-Toeplitz product on the tcgen05 tensor cores, BF16x3 split
-        // (fir_tc.cu).  Thresholds from measurements: tools/tc_taps_crossover.py (real taps: 96 taps 141 vs
-        // 146 Gsamp/s for the FFMA2 kernel, 128 taps 133 vs 114; complex taps: 32 taps 140 vs 163, 64 taps 122 vs 103) and
-        // tools/tc_probe.py with SGPU_FIR_TC_MIN_SAMPLES=1 (calls of 2^17 ... 2^21 samples: 47-65 us per call against
-        // 74-123 us for the FFMA2 kernel, whose blocks each walk 16384 outputs).
-        const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
-        const size_t span_in = (size_t)((f->C - 1) * in_stride + n_in) * 8, span_out = (size_t)((f->C - 1) * out_stride + n_out) * 8;
-        const bool overlap = ib < ob + span_out && ob < ib + span_in;
+        // Long filters (real or complex taps): banded-Toeplitz product on the tcgen05 tensor cores (fir_tc.cu, DESIGN
+        // 4.9).  Thresholds from measurements: tools/tc_taps_crossover.py and tools/tc_probe.py with
+        // SGPU_FIR_TC_MIN_SAMPLES=1 (calls of 2^17 ... 2^21 samples: 47-65 us per call against 74-123 us for the
+        // FFMA2 kernel, whose blocks each walk 16384 outputs).
         if (!f->tc_tried) {
             f->tc_tried = true;
-            int st = fir_tc_create(&f->tc, f->taps_f32.data(), (int)f->T, f->complex_taps);
-            if (st) return st;
+            // a failed set-up is not fatal: the FP32 kernels below serve the call, the reason stays in sgpu_last_error
+            if (fir_tc_create(&f->tc, f->taps_f32.data(), (int)f->T, f->complex_taps) != SGPU_OK) f->tc = nullptr;
         }
-        if (f->tc && !overlap) {
-            int st = fir_tc_run(f->tc, d_in, n_in, in_stride, a.hist, (int)f->T - 1, d_out, out_stride, f->C,
-                                (float)f->scale_re, (float)f->scale_im, f->sm_count, s);
+        if (f->tc) {
+            int st = fir_tc_run(f->tc, d_in, n_in, in_stride, a.hist, (int)f->T - 1, f->T > 1 ? a.hist_new : nullptr, d_out,
+                                out_stride, f->C, (float)f->scale_re, (float)f->scale_im, f->sm_count, s);
             if (st) return st;
             f->last_path = 1;
+            f->hist_written = true;
             return SGPU_OK;
         }
     }
-    if (n_out > 0 && f->M == 1 && f->packed && !f->complex_taps && env_int("SGPU_FIR_WARP", 1)) {
+    if (f->M == 1 && f->packed && !f->complex_taps && env_int("SGPU_FIR_WARP", 1)) {
         // plain FIR, warp-private tiles (fir_walk.cuh)
         const int rows = f->Qpad / kR + 32;
         a.RS = rows | 1;
@@ -710,44 +753,12 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         if (done) {
             SGPU_LAUNCH_CHECK();
             count_launch();
+            f->hist_written = true;
             return SGPU_OK;
         }
     }
-    if (n_out > 0 && (f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32) && f->packed && !f->complex_taps &&
+    if ((f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32) && f->packed && !f->complex_taps &&
         env_int("SGPU_DEC_WARP", 1)) {
-        if (f->Qpad == 2 * kR && env_int("SGPU_DEC_WALK", 0)) {
-            // walking decimator (fir_walk.cuh): one phase per lane, K runs per lane
-            int st = SGPU_OK;
-            bool done = false;
-#define LAUNCH_DWALK(MV, KV, NWV, MB)                                                                      \
-    do {                                                                                                   \
-        constexpr int G_ = 32 / MV, ROWS_ = 2 + G_ * KV, RS_ = ROWS_ | 1;                                  \
-        constexpr size_t warp_f4 = (size_t)MV * ((kR / 2) * RS_ + 1) + 32 * (kR / 2 + 1);                  \
-        const size_t smem = NWV * warp_f4 * sizeof(float4) + (size_t)MV * (2 * kR + kTapSkew) * sizeof(float); \
-        if (smem <= (size_t)kMaxSmem) {                                                                    \
-            auto kern = fir_decim_walk_kernel<kR, MV, KV, NWV, MB, 8>;                                     \
-            st = set_smem(kern, smem);                                                                     \
-            if (st) return st;                                                                             \
-            const long long per_block = (long long)G_ * KV * kR * 8 * NWV;                                 \
-            dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);                    \
-            kern<<<grid, NWV * 32, smem, s>>>(a);                                                          \
-            done = true;                                                                                   \
-        }                                                                                                  \
-    } while (0)
-            if (f->M == 8) {
-                // measured on config 3's shape: K=3 362, K=5 347 G in-samp/s against 404 for
-                // fir_decim_warp_kernel -- fewer instructions per FFMA2 (0.2 vs 0.42) but only 6-10
-                // resident warps per SM, so the 8-byte de-interleave loads are exposed: opt-in only
-                if (env_int("SGPU_DEC_WALK_K", 3) == 5) LAUNCH_DWALK(8, 5, 4, 1);
-                else LAUNCH_DWALK(8, 3, 2, 5);
-            }
-#undef LAUNCH_DWALK
-            if (done) {
-                SGPU_LAUNCH_CHECK();
-                count_launch();
-                return SGPU_OK;
-            }
-        }
         // warp-private tiles (fir_walk.cuh)
         int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
         if (PS != 1 && PS != 2 && PS != 4) PS = 4;
@@ -804,12 +815,11 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         if (done) {
             SGPU_LAUNCH_CHECK();
             count_launch();
+            f->hist_written = true;
             return SGPU_OK;
         }
     }
-    if (n_out > 0 && f->Qpad % (2 * fir_R(f)) != 0)
-        return fail(SGPU_ERR_UNSUPPORTED, "single-chunk tap image: the warp-private kernels are disabled (SGPU_*_WARP=0)");
-    if (n_out > 0) {
+    {
         const bool m1 = f->M == 1;
         const int R = fir_R(f);
         const int twc = f->complex_taps ? 2 : 1;
@@ -822,11 +832,20 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
         a.RS = rows | 1;
         const size_t plane_f4 = (size_t)(R / 2) * a.RS + 1;
         const size_t smem = f->M * plane_f4 * sizeof(float4) + (size_t)f->M * (f->Qpad * twc + kTapSkew) * sizeof(float);
-        if (smem > (size_t)kMaxSmem)
-            return fail(SGPU_ERR_UNSUPPORTED, "filter too long for one shared-memory tile (%zu bytes needed)", smem);
+        int st;
+        if (smem > (size_t)kMaxSmem || f->Qpad % (2 * R) != 0) {
+            // the tile (all M phase planes + the taps) does not fit one SM's shared memory, e.g. 256 taps at M = 64:
+            // direct form, one thread per output.  Any factor and any length the reference takes is served.
+            dim3 grid((unsigned)ceil_div((size_t)n_out, 128), (unsigned)f->C);
+            if (f->complex_taps) fir_direct_kernel<false, true><<<grid, 128, 0, s>>>(a);
+            else fir_direct_kernel<false, false><<<grid, 128, 0, s>>>(a);
+            SGPU_LAUNCH_CHECK();
+            count_launch();
+            f->hist_written = true;
+            return SGPU_OK;
+        }
         const long long tiles = (n_out + (long long)OT * R - 1) / ((long long)OT * R);
         dim3 grid((unsigned)tiles, (unsigned)f->C);
-        int st;
 #define LAUNCH_FIR(RV, PK, M1, MINB, PSV, CTV)                                              \
     do {                                                                                    \
         auto kern = fir_decim_kernel<RV, PK, M1, kNT, MINB, PSV, CTV>;                      \
@@ -855,6 +874,7 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
 #undef LAUNCH_FIR
         SGPU_LAUNCH_CHECK();
         count_launch();
+        f->hist_written = true;
     }
     return SGPU_OK;
 }
@@ -871,14 +891,20 @@ SGPU_EXPORT int sgpu_fir_execute_block(sgpu_fir *f, const float *in, size_t n_in
     if (!in || (n_out && !out)) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
     if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
     if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    // the kernels read a tile's halo while other blocks already write their outputs: in and out must be disjoint
+    if (n_out && ranges_overlap(in, ((f->C - 1) * in_stride + n_in) * 8, out, ((f->C - 1) * out_stride + n_out) * 8))
+        return fail(SGPU_ERR_INVALID_ARGUMENT, "in and out overlap: execute_block is not an in-place operation");
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
-    // one pass over device-resident samples: kernel + history update + phase counter
+    // one pass over device-resident samples: ONE kernel computes the outputs and writes the new history tail (the
+    // tensor path: two launches, fir_tc.cuh); only the phase counter lives on the host
     auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,
                    cudaStream_t st_) -> int {
+        f->hist_written = false;
         int st = fir_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
         if (st) return st;
-        st = enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->T - 1, st_);
+        if (f->hist_written) f->cur ^= 1;
+        else st = enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->T - 1, st_);
         if (st) return st;
         if (f->is_decim) f->current_item = (f->current_item + nc) % f->M;  // decim.rs:116
         return SGPU_OK;
@@ -953,7 +979,7 @@ SGPU_EXPORT int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out) {
     std::vector<double> taps(f->taps_f32.size());
     for (size_t i = 0; i < taps.size(); ++i) taps[i] = (double)f->taps_f32[i];
     sgpu_fir *c = nullptr;
-    int st = sgpu_fir_create(taps.data(), f->T, f->complex_taps ? SGPU_TAPS_COMPLEX : SGPU_TAPS_REAL, f->C,
+    int st = fir_create_impl(taps.data(), f->T, f->complex_taps ? SGPU_TAPS_COMPLEX : SGPU_TAPS_REAL, f->C, f->per_channel,
                              f->scale_re, f->scale_im, f->is_decim, f->M, &c);
     if (st) return st;
     if (f->T > 1) {
@@ -974,12 +1000,15 @@ struct sgpu_interp {
     size_t T = 0, C = 0, L = 1, S = 0;  // S = sub-filter length
     bool packed = true, complex_taps = false;
     double scale_re = 1.0, scale_im = 0.0;  // stored, never applied (pfb.rs:85-90)
-    std::vector<float> phase_taps;           // [L][S][tw]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first)
+    bool per_channel = false;                // every channel owns its taps
+    std::vector<float> phase_taps;           // [L][S][tw]: hp[p][j] = hpad[p + (S-1-j)*L] (newest first); [C][L][S][tw] when per_channel
     size_t ch_off = 0;                       // first channel of the block being launched
     int Qpad = 0;
+    size_t img_floats = 0;                   // floats of one tap image
     float *d_taps = nullptr;
     float2 *d_hist[2] = {nullptr, nullptr};  // S samples per channel: the PFB window (oldest first)
     int cur = 0;
+    bool hist_written = false;               // the launch of this call wrote the new window into d_hist[cur ^ 1]
     Staging stage;
     HostPipe pipe;
     FirTcState *tc = nullptr;  // tensor-core path (fir_tc.cu): real taps, L in {2, 4}, sub-filters of more than 32 taps
@@ -987,20 +1016,28 @@ struct sgpu_interp {
     int last_path = 0;
 };
 
-static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S (complex: x2) values */) {
+static int interp_build(sgpu_interp *f, const double *taps_eff /* [C when per_channel][eff_stride] values, L*S (complex: x2) used */,
+                        size_t eff_stride) {
     const int L = (int)f->L, S = (int)f->S, tw = f->complex_taps ? 2 : 1;
-    f->phase_taps.assign((size_t)L * S * tw, 0.f);
-    for (int p = 0; p < L; ++p)
-        for (int j = 0; j < S; ++j)
-            for (int c = 0; c < tw; ++c)
-                f->phase_taps[((size_t)p * S + j) * tw + c] = (float)taps_eff[(p + (size_t)(S - 1 - j) * L) * tw + c];
+    const size_t nimg = f->per_channel ? f->C : 1, per = (size_t)L * S * tw;
+    f->phase_taps.assign(nimg * per, 0.f);
     f->Qpad = (int)round_up((size_t)S, 2 * (f->complex_taps ? 8 : kR));
     if (S <= kR && !f->complex_taps && f->packed && (L == 2 || L == 4 || L == 8 || L == 16 || L == 32))
         f->Qpad = kR;  // single-chunk walking kernel
-    std::vector<float> img;
-    build_tap_image(f->phase_taps, L, S, f->Qpad, tw, img);
-    SGPU_CUDA(cudaMalloc(&f->d_taps, img.size() * sizeof(float)));
-    SGPU_CUDA(cudaMemcpy(f->d_taps, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> all, img, one(per);
+    for (size_t ch = 0; ch < nimg; ++ch) {
+        const double *te = taps_eff + ch * eff_stride;
+        for (int p = 0; p < L; ++p)
+            for (int j = 0; j < S; ++j)
+                for (int c = 0; c < tw; ++c)
+                    one[((size_t)p * S + j) * tw + c] = (float)te[(p + (size_t)(S - 1 - j) * L) * tw + c];
+        std::copy(one.begin(), one.end(), f->phase_taps.begin() + ch * per);
+        build_tap_image(one, L, S, f->Qpad, tw, img);
+        f->img_floats = img.size();
+        all.insert(all.end(), img.begin(), img.end());
+    }
+    SGPU_CUDA(cudaMalloc(&f->d_taps, all.size() * sizeof(float)));
+    SGPU_CUDA(cudaMemcpy(f->d_taps, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
     // window of S samples; kernels treat the last S-1 as "history" (T-1 with T = S)
     const size_t hbytes = f->C * (size_t)S * sizeof(float2);
     for (int i = 0; i < 2; ++i) {
@@ -1010,11 +1047,11 @@ static int interp_build(sgpu_interp *f, const double *taps_eff /* L*S (complex: 
     return SGPU_OK;
 }
 
-static int interp_create_common(const double *taps_eff, size_t n_eff, size_t n_taps, size_t n_channels,
-                                size_t L, size_t S, double sre, double sim, bool complex_taps, sgpu_interp **out) {
-    (void)n_eff;
+static int interp_create_common(const double *taps_eff, size_t eff_stride, size_t n_taps, size_t n_channels,
+                                size_t L, size_t S, double sre, double sim, bool complex_taps, bool per_channel,
+                                sgpu_interp **out) {
     if (n_channels == 0) return fail(SGPU_ERR_INVALID_ARGUMENT, "n_channels == 0");
-    if (L > 4096 || S > (1u << 20)) return fail(SGPU_ERR_UNSUPPORTED, "interpolation/sub-filter too large");
+    if (L > (1u << 20) || S > (1u << 20)) return fail(SGPU_ERR_UNSUPPORTED, "interpolation/sub-filter too large");
     int dev = 0, sms = 0;
     int st = require_device(&dev, &sms);
     if (st) return st;
@@ -1029,15 +1066,16 @@ static int interp_create_common(const double *taps_eff, size_t n_eff, size_t n_t
     f->scale_re = sre;
     f->scale_im = sim;
     f->complex_taps = complex_taps;
+    f->per_channel = per_channel;
     f->packed = complex_taps ? true : packed_default();
-    st = interp_build(f, taps_eff);
+    st = interp_build(f, taps_eff, eff_stride);
     if (st) { sgpu_interp_destroy(f); return st; }
     *out = f;
     return SGPU_OK;
 }
 
-SGPU_EXPORT int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
-                                   size_t interpolation, sgpu_interp **out) {
+static int interp_create_impl(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels, bool per_channel,
+                              size_t interpolation, sgpu_interp **out) {
     if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
     if (n_taps == 0 || !taps)  // interp.rs:28-29
@@ -1049,9 +1087,20 @@ SGPU_EXPORT int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapki
     const float q = (float)n_taps / (float)interpolation;
     const size_t S = (q == floorf(q)) ? (size_t)q : (size_t)ceilf(q);
     const size_t eff = S * interpolation;  // interp.rs:43
-    std::vector<double> padded((eff > n_taps ? eff : n_taps) * tw, 0.0);
-    for (size_t i = 0; i < n_taps * tw; ++i) padded[i] = taps[i];
-    return interp_create_common(padded.data(), eff, n_taps, n_channels, interpolation, S, 1.0, 0.0, tw == 2, out);
+    const size_t stride = (eff > n_taps ? eff : n_taps) * tw, nimg = per_channel ? n_channels : 1;
+    std::vector<double> padded(stride * nimg, 0.0);
+    for (size_t ch = 0; ch < nimg; ++ch)
+        for (size_t i = 0; i < n_taps * tw; ++i) padded[ch * stride + i] = taps[ch * n_taps * tw + i];
+    return interp_create_common(padded.data(), stride, n_taps, n_channels, interpolation, S, 1.0, 0.0, tw == 2, per_channel, out);
+}
+
+SGPU_EXPORT int sgpu_interp_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                   size_t interpolation, sgpu_interp **out) {
+    return interp_create_impl(taps, n_taps, kind, n_channels, false, interpolation, out);
+}
+SGPU_EXPORT int sgpu_interp_create_per_channel(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                                               size_t interpolation, sgpu_interp **out) {
+    return interp_create_impl(taps, n_taps, kind, n_channels, true, interpolation, out);
 }
 
 SGPU_EXPORT int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
@@ -1065,8 +1114,8 @@ SGPU_EXPORT int sgpu_pfb_create(const double *taps, size_t n_taps, sgpu_tapkind 
     const size_t S = n_taps / filters;  // pfb.rs:32 (truncating)
     if (S == 0)  // reference: Window::new(0) assertion panic (window/mod.rs:18)
         return fail(SGPU_ERR_FIR_NOT_ENOUGH_FILTERS, "FIR Filter Error NotEnoughFilters (filters > taps)");
-    return interp_create_common(taps, S * filters, n_taps, n_channels, filters, S, scale_re, scale_im,
-                                kind == SGPU_TAPS_COMPLEX, out);
+    return interp_create_common(taps, 0, n_taps, n_channels, filters, S, scale_re, scale_im,
+                                kind == SGPU_TAPS_COMPLEX, false, out);
 }
 
 SGPU_EXPORT int sgpu_interp_destroy(sgpu_interp *f) {
@@ -1102,7 +1151,8 @@ SGPU_EXPORT int sgpu_interp_coefficients(const sgpu_interp *f, double *out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     // pfb.rs:71-73: each DotProduct's stored order = rev_sub_coefs; rev_sub[S-1-idx] = h[p + idx*L]
     // so stored[i] = h[p + (S-1-i)*L] = phase_taps[p][i]
-    for (size_t i = 0; i < f->phase_taps.size(); ++i) out[i] = (double)f->phase_taps[i];
+    const size_t per = f->L * f->S * (f->complex_taps ? 2 : 1);  // channel 0 when every channel owns its taps
+    for (size_t i = 0; i < per; ++i) out[i] = (double)f->phase_taps[i];
     return SGPU_OK;
 }
 
@@ -1132,7 +1182,9 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     // the kernel's history convention is "T-1 samples before x[0]" with T = S+1 here: the PFB
     // window keeps S samples, of which the interpolator only ever reads the newest S-1 as past.
     a.hist = f->d_hist[f->cur] + f->ch_off * f->S;
-    a.taps = f->d_taps;
+    a.hist_new = f->d_hist[f->cur ^ 1] + f->ch_off * f->S;  // every kernel below writes the new window itself
+    a.taps = f->d_taps + (f->per_channel ? f->ch_off * f->img_floats : 0);
+    a.tap_stride = f->per_channel ? (long long)f->img_floats : 0;
     a.in_stride = istr;
     a.out_stride = ostr;
     a.n_in = n_in;
@@ -1146,24 +1198,23 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     a.scale_re = 1.f;
     const int tw = f->complex_taps ? 2 : 1;
     f->last_path = 0;
-    if (n_out > 0 && !f->complex_taps && (f->L == 2 || f->L == 4) && (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", f->L == 2 ? 17 : 33) && f->S <= 16384 &&
+    if (n_out > 0 && !f->complex_taps && !f->per_channel && (f->L == 2 || f->L == 4) &&
+        (long long)f->S >= env_int("SGPU_INTERP_TC_MIN_SUB", f->L == 2 ? 17 : 33) && f->S <= 16384 &&
         n_in >= 128 * (128 / (long long)f->L) &&
         n_out * (long long)f->C >= (long long)env_int("SGPU_INTERP_TC_MIN_OUT", 1 << 23) && env_int("SGPU_FIR_TC", 1)) {
         // polyphase interpolator as a banded product on the tcgen05 tensor cores (fir_tc.cu): 128 outputs per block
         // row = 128 / L inputs.  Measured (tools/tc_interp_probe.py, 256 ch x 2^20, G out-samp/s): L = 4: sub-filters <= 32
         // taps stay on the walking kernel (430 vs 422), 48 taps 373 vs 190, 256 taps 163 vs 58; L = 2: 24-32 taps 288 vs 263
-        const char *ib = reinterpret_cast<const char *>(d_in), *ob = reinterpret_cast<const char *>(d_out);
-        const size_t span_in = (size_t)((f->C - 1) * istr + n_in) * 8, span_out = (size_t)((f->C - 1) * ostr + n_out) * 8;
-        const bool overlap = ib < ob + span_out && ob < ib + span_in;
         if (!f->tc_tried) {
             f->tc_tried = true;
-            int st = fir_tc_create_pfb(&f->tc, f->phase_taps.data(), (int)f->L, (int)f->S, false);
-            if (st) return st;
+            if (fir_tc_create_pfb(&f->tc, f->phase_taps.data(), (int)f->L, (int)f->S, false) != SGPU_OK) f->tc = nullptr;
         }
-        if (f->tc && !overlap) {
-            int st = fir_tc_run(f->tc, d_in, n_in, istr, a.hist, (int)f->S, d_out, ostr, f->C, 1.f, 0.f, f->sm_count, s);
+        if (f->tc) {
+            int st = fir_tc_run(f->tc, d_in, n_in, istr, a.hist, (int)f->S, a.hist_new, d_out, ostr, f->C, 1.f, 0.f,
+                                f->sm_count, s);
             if (st) return st;
             f->last_path = 1;
+            f->hist_written = true;
             return SGPU_OK;
         }
     }
@@ -1204,53 +1255,8 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
 #undef LAUNCH_IWALK
         SGPU_LAUNCH_CHECK();
         count_launch();
+        f->hist_written = true;
         return SGPU_OK;
-    }
-    if (f->Qpad % (2 * (f->complex_taps ? 8 : kR)) != 0)
-        return fail(SGPU_ERR_UNSUPPORTED, "single-chunk tap image: the walking kernel is disabled (SGPU_WALK=0)");
-    if (!f->complex_taps && env_int("SGPU_PIPE", 1)) {
-        // persistent multi-stage interpolator (fir_pipe.cuh)
-        int PSp = f->L >= 4 ? 4 : (f->L >= 2 ? 2 : 1);
-        const int wantp = env_int("SGPU_INT_PS", 0);
-        if ((wantp == 1 || wantp == 2 || wantp == 4) && wantp <= (int)f->L) PSp = wantp;
-        const int OTp = kNT / PSp;
-        const int rowsp = f->Qpad / kR + OTp;
-        const int RSp = rowsp | 1;
-        const size_t stage_f4 = (size_t)(kR / 2) * RSp + 1;
-        const size_t smemp = 3 * stage_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad + kTapSkew) * tw * sizeof(float);
-        const long long tiles_total = ((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR)) * (long long)f->C;
-        if (smemp <= (size_t)kMaxSmem && tiles_total < (1ll << 31)) {
-            FirPipeArgs pa{};
-            pa.in = d_in; pa.out = d_out; pa.hist = f->d_hist[f->cur] + f->ch_off * f->S; pa.taps = f->d_taps;
-            pa.in_stride = istr; pa.out_stride = ostr; pa.n_in = n_in; pa.n_out = n_out;
-            pa.tiles_per_ch = (int)((n_in + (long long)OTp * kR - 1) / ((long long)OTp * kR));
-            pa.total_tiles = (long long)pa.tiles_per_ch * (long long)f->C;
-            pa.T = (int)f->S + 1; pa.M = (int)f->L; pa.c0 = 0; pa.Qpad = f->Qpad; pa.RS = RSp;
-            pa.vec_out = 0; pa.scale_re = 1.f;
-            int st = SGPU_OK;
-            int per_sm = 0;
-#define LAUNCH_IPIPE(PK, PSV)                                                                          \
-    do {                                                                                               \
-        auto kern = fir_interp_pipe_kernel<kR, PK, kNT, PSV, 3, 1>;                                    \
-        st = set_smem(kern, smemp);                                                                    \
-        if (st) return st;                                                                             \
-        SGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smemp));           \
-        long long blocks = (long long)f->sm_count * (per_sm > 0 ? per_sm : 1);                         \
-        if (blocks > pa.total_tiles) blocks = pa.total_tiles;                                          \
-        kern<<<(unsigned)blocks, kNT, smemp, s>>>(pa);                                                 \
-    } while (0)
-            if (PSp == 4) {
-                if (f->packed) LAUNCH_IPIPE(true, 4); else LAUNCH_IPIPE(false, 4);
-            } else if (PSp == 2) {
-                if (f->packed) LAUNCH_IPIPE(true, 2); else LAUNCH_IPIPE(false, 2);
-            } else {
-                if (f->packed) LAUNCH_IPIPE(true, 1); else LAUNCH_IPIPE(false, 1);
-            }
-#undef LAUNCH_IPIPE
-            SGPU_LAUNCH_CHECK();
-            count_launch();
-            return SGPU_OK;
-        }
     }
     int PS = f->L >= 2 ? 2 : 1;
     const int want = env_int("SGPU_INT_PS", 0);
@@ -1262,8 +1268,17 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
     const size_t plane_f4 = (size_t)(R / 2) * a.RS + 1;
     const size_t smem = plane_f4 * sizeof(float4) + f->L * (size_t)(f->Qpad * tw + kTapSkew) * sizeof(float) +
                         (size_t)OT * (R * f->L + 1) * sizeof(float2);
-    if (smem > (size_t)kMaxSmem)
-        return fail(SGPU_ERR_UNSUPPORTED, "interpolator tile needs %zu bytes of shared memory", smem);
+    if (smem > (size_t)kMaxSmem || f->Qpad % (2 * R) != 0) {
+        // L tap sets + the staged outputs of a tile do not fit one SM's shared memory (e.g. complex taps at L >= 28, any
+        // L beyond ~100): direct form, one thread per output.  Every factor the reference takes is served.
+        dim3 grid((unsigned)ceil_div((size_t)n_out, 128), (unsigned)f->C);
+        if (f->complex_taps) fir_direct_kernel<true, true><<<grid, 128, 0, s>>>(a);
+        else fir_direct_kernel<true, false><<<grid, 128, 0, s>>>(a);
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+        f->hist_written = true;
+        return SGPU_OK;
+    }
     const long long tiles = ((long long)n_in + (long long)OT * R - 1) / ((long long)OT * R);
     dim3 grid((unsigned)tiles, (unsigned)f->C);
     int st;
@@ -1288,6 +1303,7 @@ int interp_launch_block(sgpu_interp *f, const float2 *d_in, long long n_in, long
 #undef LAUNCH_INT
     SGPU_LAUNCH_CHECK();
     count_launch();
+    f->hist_written = true;
     return SGPU_OK;
 }
 }  // namespace
@@ -1302,12 +1318,19 @@ SGPU_EXPORT int sgpu_interp_execute_block(sgpu_interp *f, const float *in, size_
     if (!in || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
     if (f->C > 1 && in_stride < n_in) return fail(SGPU_ERR_INVALID_ARGUMENT, "in_stride < n_in");
     if (out_stride < n_out) return fail(SGPU_ERR_CAPACITY, "out capacity %zu < %zu outputs", out_stride, n_out);
+    if (ranges_overlap(in, ((f->C - 1) * in_stride + n_in) * 8, out, ((f->C - 1) * out_stride + n_out) * 8))
+        return fail(SGPU_ERR_INVALID_ARGUMENT, "in and out overlap: execute_block is not an in-place operation");
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
     auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,
                    cudaStream_t st_) -> int {
+        f->hist_written = false;
         int st = interp_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
         if (st) return st;
+        if (f->hist_written) {
+            f->cur ^= 1;
+            return SGPU_OK;
+        }
         return enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->S, st_);
     };
     if (mem == SGPU_DEVICE)
@@ -1354,7 +1377,8 @@ SGPU_EXPORT int sgpu_interp_execute_phase(sgpu_interp *f, size_t index, float *o
     }
     const int tw = f->complex_taps ? 2 : 1;
     pfb_phase_kernel<<<(unsigned)ceil_div(f->C, 128), 128, 0, s>>>(f->d_hist[f->cur], (int)f->S, f->d_taps,
-                                                                     f->Qpad, tw, (int)index, d_out, (int)f->C);
+                                                                     f->per_channel ? (long long)f->img_floats : 0, f->Qpad, tw,
+                                                                     (int)index, d_out, (int)f->C);
     SGPU_LAUNCH_CHECK();
     count_launch();
     if (mem == SGPU_HOST) {
@@ -1395,15 +1419,16 @@ SGPU_EXPORT int sgpu_interp_clone(const sgpu_interp *f, sgpu_interp **out) {
     if (!f || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(f->device);
     // rebuild the effective tap vector hpad[p + (S-1-j)*L] = phase_taps[p][j]
-    const size_t tw = f->complex_taps ? 2 : 1;
-    std::vector<double> eff(f->L * f->S * tw);
-    for (size_t p = 0; p < f->L; ++p)
-        for (size_t j = 0; j < f->S; ++j)
-            for (size_t c2 = 0; c2 < tw; ++c2)
-                eff[(p + (f->S - 1 - j) * f->L) * tw + c2] = (double)f->phase_taps[(p * f->S + j) * tw + c2];
+    const size_t tw = f->complex_taps ? 2 : 1, per = f->L * f->S * tw, nimg = f->per_channel ? f->C : 1;
+    std::vector<double> eff(per * nimg);
+    for (size_t ch = 0; ch < nimg; ++ch)
+        for (size_t p = 0; p < f->L; ++p)
+            for (size_t j = 0; j < f->S; ++j)
+                for (size_t c2 = 0; c2 < tw; ++c2)
+                    eff[ch * per + (p + (f->S - 1 - j) * f->L) * tw + c2] = (double)f->phase_taps[ch * per + (p * f->S + j) * tw + c2];
     sgpu_interp *c = nullptr;
-    int st = interp_create_common(eff.data(), f->L * f->S, f->T, f->C, f->L, f->S, f->scale_re, f->scale_im,
-                                  f->complex_taps, &c);
+    int st = interp_create_common(eff.data(), per, f->T, f->C, f->L, f->S, f->scale_re, f->scale_im,
+                                  f->complex_taps, f->per_channel, &c);
     if (st) return st;
     SGPU_CUDA(cudaDeviceSynchronize());
     SGPU_CUDA(cudaMemcpy(c->d_hist[c->cur], f->d_hist[f->cur], f->C * f->S * sizeof(float2),

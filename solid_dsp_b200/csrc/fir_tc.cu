@@ -11,29 +11,46 @@
 // Because 32 | R, K-chunk q of row b of B is the plain box (column 32 (q mod R/32), row b + q / (R/32)) of the sample
 // plane viewed as [rows][R]: TMA builds the overlapping Toeplitz rows, the re-reads are L2 hits.
 //
-// Precision.  f32 accuracy on a 16-bit-input pipe: x = b1 + b2 + b3 (three bf16 terms, each the rounded residual of
-// the previous ones), likewise the taps, six MMAs per K step (b1h1, b1h2, b2h1, b2h2, b1h3, b3h1: everything down to
-// 2^-24).  A TF32x3 variant (hi / lo planes, three MMAs at half the rate) is kept.  The tensor core truncates the
-// addend toward zero when it aligns it to the f32 accumulator (measured: tools/tc_accum_probe.py), which makes the
-// error LINEAR in the number of sequential MMAs, so the K loop of a tile is cut into chains of two K-chunks that
-// are summed in f32 registers by the epilogue warps (round to nearest).
+// Precision: f32 accuracy on a 16-bit-input pipe, two operand formats.
+//   F16x2 (default for multi-chain tiles with R = 128 / 64): block floating point.  Every group of 64 consecutive
+//       samples is scaled by a power of two that puts its largest component into [2^14, 2^15) and split into two fp16
+//       terms x = f1 + f2 (22 significand bits; the absolute error is <= 2^-25 in scaled units, i.e. 2^-39 of the
+//       group's peak); the taps likewise with one global power of two.  THREE MMAs per K step (f1 h1, f1 h2, f2 h1;
+//       the dropped f2 h2 is <= 2^-22 per product).  A group is exactly the K extent of one accumulation chain of one
+//       output block, so the epilogue undoes the scale when it adds the finished chain into its f32 registers (one
+//       FFMA per value instead of one FADD).  Split error measured on the CPU in f64: <= 1.3e-7 of the peak output
+//       (tests/test_tc_formulation.py), below the accumulator's own rounding.
+//   BF16x3 (one-chain tiles, L = 4, SGPU_FIR_TC_FMT=bf16): x = b1 + b2 + b3, three bf16 terms (the f32 exponent range,
+//       no scaling), SIX MMAs per K step (b1h1, b1h2, b2h1, b2h2, b1h3, b3h1: everything down to 2^-24).
+// The tensor core truncates the addend toward zero when it aligns it to the f32 accumulator (measured:
+// tools/tc_accum_probe.py), which makes the error LINEAR in the number of sequential MMAs, so the K loop of a tile
+// is cut into chains of two K-chunks that are summed in f32 registers by the epilogue warps (round to nearest).
+//
+// Non-finite samples.  In the banded product the structural zeros of A still multiply the samples of the block row
+// (0 x Inf = NaN), and a block-floating group that holds an Inf / NaN has no scale.  The split therefore flags every
+// tile whose samples contain an exponent of all ones, and fir_tc_post_kernel -- launched behind the tensor kernel on
+// the same stream -- recomputes the flagged tiles with plain sequential f32 FMAs in the reference's order
+// (dot_product/mod.rs:159-170), so a non-finite sample reaches exactly the outputs it reaches in the reference
+// (fir/mod.rs:209-212).  The same launch writes the handle's new history tail (window/mod.rs:63-71).
 //
 // Kernels.
-//   fir_tc_fused_kernel<BF, CT, ONE>  (the product): persistent, one CTA per SM; warp 0 = TMA producer, warp 1 = one
+//   fir_tc_fused_kernel<F16, CT, ONE>  (the product): persistent, one CTA per SM; warp 0 = TMA producer, warp 1 = one
 //       thread issuing tcgen05.mma (cta_group::1, M 128 x N 256), warps 2-9 = epilogue.  The epilogue warps also
-//       split the NEXT tile's cf32 samples into the bf16 / tf32 planes, into a per-CTA ring in global memory that
-//       stays in L2 (evict_last) and is read back by TMA: no pre-pass launch, no stream-sized scratch.
+//       split the NEXT tile's cf32 samples into the 16-bit planes, into a per-CTA ring in global memory that stays in
+//       L2 (evict_last) and is read back by TMA: no pre-pass launch, no stream-sized scratch.
 //       CT: complex taps (Gr and Gi parts in A, cross terms as N = 128 MMAs with the negate-A bit).
 //       ONE: bands of <= 3 K-chunks (short interpolator sub-filters) are a single chain per tile: each warp drains its
 //       TMEM lane quarter straight to global memory and two groups of four warps alternate tiles.
-//   fir_tc_split_kernel + fir_tc_kernel  (SGPU_FIR_TC=2): the first generation (split pre-pass over the whole
-//       stream, one chain per tile), kept for comparison: it shows the accumulator bias (1.2e-5 at 2048 taps).
+//   fir_tc_post_kernel: fix-up of flagged tiles + history update (see above).
 // Every mbarrier wait is bounded (4 s, then trap): a protocol error is a CUDA error, not a hung GPU.
 #include "fir_tc.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
+#include <type_traits>
 
 namespace sgpu {
 namespace {
@@ -41,25 +58,10 @@ namespace {
 constexpr int kBM = 128;                 // outputs per block (UMMA M)
 constexpr int kNB = 128;                 // blocks per tile
 constexpr int kBN = 2 * kNB;             // UMMA N: re columns then im columns
-constexpr int kKC = 32;                  // floats per K chunk = one 128-byte swizzle row
-constexpr int kUK = 8;                   // K of one tf32 UMMA
-constexpr int kStages = 2;
-constexpr int kABytes = 2 * kBM * kKC * 4;   // A_hi, A_lo
-constexpr int kBBytes = 4 * kNB * kKC * 4;   // re_hi, im_hi, re_lo, im_lo
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kKC = 32;                  // elements per K chunk = one 64-byte swizzle row of 16-bit operands
 constexpr int kTileSamples = kBM * kNB;  // 16384 outputs per tile
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr long long kSegSamples = 1ll << 27;  // scratch planes cover one segment (2 GiB of planes)
-
-struct TcArgs {
-    float2 *out;       // output sample 0 of this segment
-    long long n_out;   // outputs of this segment
-    int ntiles;
-    int nchunks;
-    float scale;
-};
+constexpr int kGroup = 64;               // plane positions that share one block-floating scale = one chain of 2 K-chunks
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -102,12 +104,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
                                             int c2) {
     asm volatile(
@@ -115,7 +111,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
     asm volatile(
@@ -129,35 +124,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, f32 accumulation, issued by one thread for the CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart);
-// the tile base is 1024-byte aligned, a K step of 8 floats advances the start address by 32 bytes.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-// kind::tf32, A and B K-major, D f32, M = 128, N = 256
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -172,196 +142,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Split pre-pass: plane position q holds stream sample p0 + q (negative positions = the handle's history,
-// window/mod.rs:63-71; beyond the call's input = 0), de-interleaved and split into hi / lo TF32 planes.
-__global__ void __launch_bounds__(256) fir_tc_split_kernel(const float2 *__restrict__ x, long long n_in,
-                                                           const float2 *__restrict__ hist, int H, long long p0,
-                                                           float *__restrict__ planes, long long plane_len,
-                                                           int vec_ok) {
-    const long long q = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (q >= plane_len) return;
-    const long long p = p0 + q;
-    float2 v[4];
-    if (vec_ok && p >= 0 && p + 3 < n_in) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(x + p));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(x + p + 2));
-        v[0] = make_float2(a.x, a.y);
-        v[1] = make_float2(a.z, a.w);
-        v[2] = make_float2(b.x, b.y);
-        v[3] = make_float2(b.z, b.w);
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const long long i = p + e;
-            if (i >= 0) v[e] = i < n_in ? x[i] : make_float2(0.f, 0.f);
-            else {
-                const long long h = (long long)H + i;
-                v[e] = h >= 0 ? hist[h] : make_float2(0.f, 0.f);
-            }
-        }
-    }
-    float rh[4], ih[4], rl[4], il[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        rh[e] = rn_tf32(v[e].x);
-        ih[e] = rn_tf32(v[e].y);
-        rl[e] = rn_tf32(v[e].x - rh[e]);
-        il[e] = rn_tf32(v[e].y - ih[e]);
-    }
-    *reinterpret_cast<float4 *>(planes + q) = make_float4(rh[0], rh[1], rh[2], rh[3]);
-    *reinterpret_cast<float4 *>(planes + plane_len + q) = make_float4(ih[0], ih[1], ih[2], ih[3]);
-    *reinterpret_cast<float4 *>(planes + 2 * plane_len + q) = make_float4(rl[0], rl[1], rl[2], rl[3]);
-    *reinterpret_cast<float4 *>(planes + 3 * plane_len + q) = make_float4(il[0], il[1], il[2], il[3]);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-fir_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + kStages * kStageBytes;
-    // barrier slots: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base address
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-    auto tfull_bar = [&](int i) { return bars + 8u * (2 * kStages + i); };
-    auto tempty_bar = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
-    const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
-    auto stage_a = [&](int s) { return base + (uint32_t)s * kStageBytes; };
-    auto stage_b = [&](int s) { return base + (uint32_t)s * kStageBytes + kABytes; };
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(tfull_bar(i), 1);
-            mbar_init(tempty_bar(i), 4);  // one arrival per epilogue warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                for (int q = 0; q < a.nchunks; ++q) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), kStageBytes);
-                    tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
-                    tma_load_3d(stage_b(stage), &tmB, full_bar(stage), (q & 3) * kKC, tile * kNB + (q >> 2), 0);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)acc * kBN;
-                for (int q = 0; q < a.nchunks; ++q) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint64_t a_hi = umma_desc(stage_a(stage));
-                    const uint64_t a_lo = umma_desc(stage_a(stage) + kBM * kKC * 4);
-                    const uint64_t b_hi = umma_desc(stage_b(stage));
-                    const uint64_t b_lo = umma_desc(stage_b(stage) + kBN * kKC * 4);
-#pragma unroll
-                    for (int kk = 0; kk < kKC / kUK; ++kk) {
-                        const uint64_t off = (uint64_t)(kk * kUK * 4 >> 4);
-                        umma_tf32(d, a_hi + off, b_hi + off, kIdescTf32, (q | kk) != 0 ? 1u : 0u);
-                        umma_tf32(d, a_lo + off, b_hi + off, kIdescTf32, 1u);
-                        umma_tf32(d, a_hi + off, b_lo + off, kIdescTf32, 1u);
-                    }
-                    umma_commit(empty_bar(stage));  // smem stage free once these MMAs have read it
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-                umma_commit(tfull_bar(acc));  // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
-    } else {  // ===== epilogue: warps 2..5 own TMEM lane quarters 2, 3, 0, 1 =====
-        const int wq = warp & 3;
-        const int m = wq * 32 + lane;  // output offset inside a block = TMEM lane
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * kBN;
-            const long long n0 = (long long)tile * kTileSamples + m;
-#pragma unroll 1
-            for (int cg = 0; cg < kNB / 16; ++cg) {
-                float re[16], im[16];
-                tmem_ld16(taddr + cg * 16, re);
-                tmem_ld16(taddr + kNB + cg * 16, im);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const long long n = n0 + (long long)(cg * 16 + i) * kBM;
-                    if (n < a.n_out) a.out[n] = make_float2(re[i] * a.scale, im[i] * a.scale);  // fir/mod.rs:211
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Fused kernel (the default): no pre-pass launch, no stream-sized scratch, short accumulation chains.
+// Fused kernel: no pre-pass launch, no stream-sized scratch, short accumulation chains.
 //
-//  * The tcgen05 tf32 MMA truncates (round-toward-zero) its f32 accumulator on every instruction (measured,
-//    tools/tc_accum_probe.py: DC input, positive taps, TF32-exact operands: error -0.5 ulp per K step,
+//  * The tcgen05 MMA truncates (round-toward-zero) its f32 accumulator on every instruction (measured,
+//    tools/tc_accum_probe.py: DC input, positive taps, exact operands: error -0.5 ulp per K step,
 //    sign follows the sum, grows linearly with T: 3.1e-6 at 512 taps, 1.5e-5 at 2048).  So a tile's K loop is
 //    cut into chains of `gchunks` chunks; each chain goes to one of the two TMEM accumulators from zero and the
 //    epilogue warps add the finished chain into f32 REGISTERS (round-to-nearest) while the next chain runs in
 //    the other accumulator.  The bias then scales with the chain length, not with T.
-//  * The same eight epilogue warps split the NEXT tile's samples into the four TF32 planes between two chain
+//  * The same eight epilogue warps split the NEXT tile's samples into the 16-bit planes between two chain
 //    flushes (a tile needs Koff + 16384 samples, 132 rows of 128), into a per-CTA ring of two tile buffers in
-//    global memory (148 x 2 x 270 KB = 80 MB: stays in the 126 MB L2).  TMA reads it back as before; HBM sees
+//    global memory (148 x 2 x 135 KB = 40 MB for F16x2: stays in the 126 MB L2).  TMA reads it back; HBM sees
 //    8 bytes in and 8 bytes out per sample.
 constexpr int kEpiWarps = 8;                          // 4 per TMEM lane quarter
 constexpr int kColsW = kNB / (kEpiWarps / 4);          // blocks (accumulator columns per re / im half) per epilogue warp
@@ -370,44 +162,50 @@ constexpr int kOneWarps = 8;                           // one-chain kernel: grou
 constexpr int kOneThreads = 64 + 32 * kOneWarps;
 constexpr int kOneRing = 2 * (kOneWarps / 4);          // ring buffers per CTA of the one-chain kernel: every group splits its next tile ahead
 
-// Operand format of the fused kernel.
-//   TF32x3: hi/lo TF32 planes (4 B), 3 MMAs per K step of 8, SWIZZLE_128B rows of 32 floats, 96 KB per K chunk of 32.
-//   BF16x3: b1/b2/b3 bf16 planes (2 B), 6 MMAs per K step of 16 (b1*b1, b1*b2, b2*b1, b2*b2, b1*b3, b3*b1: every
-//           product down to 2^-24 relative), SWIZZLE_64B rows of 32 bf16, 72 KB per K chunk of 32: the same tensor
-//           time per K (bf16 runs at twice the TF32 rate), 25 % less L2 -> shared-memory traffic, three stages.
-template <bool BF, bool CT = false>
+// Operand format of the fused kernel (both: 2-byte elements, SWIZZLE_64B rows of 32 elements).
+//   F16x2:  f1 / f2 fp16 planes of the block-scaled samples, 3 MMAs per K step of 16, 48 KB per K chunk of 32, 4 stages.
+//   BF16x3: b1 / b2 / b3 bf16 planes, 6 MMAs per K step of 16, 72 KB per K chunk of 32, 3 stages.
+template <bool F16, bool CT = false>
 struct Fmt {
-    static_assert(BF || !CT, "complex taps run in the BF16x3 format only");
-    static constexpr int kParts = BF ? 3 : 2;                       // planes per operand
-    static constexpr int kElem = BF ? 2 : 4;                        // bytes per element
-    static constexpr int kRowBytes = kKC * kElem;                   // 64 / 128: the swizzle span
+    static constexpr int kParts = F16 ? 2 : 3;                      // planes per operand
+    static constexpr int kElem = 2;                                 // bytes per element
+    static constexpr int kRowBytes = kKC * kElem;                   // 64: the swizzle span
     static constexpr int kAPart = kBM * kRowBytes;                  // one A plane of a stage
     static constexpr int kBPart = kBN * kRowBytes;                  // one B plane (re rows then im rows) of a stage
     static constexpr int kAParts = kParts * (CT ? 2 : 1);           // complex taps: Gr parts then Gi parts
     static constexpr int kA = kAParts * kAPart;
-    static constexpr int kStage = kA + kParts * kBPart;             // 73728 (BF16x3) / 98304 (TF32x3, BF16x3 complex taps)
-    static constexpr int kNStages = (BF && !CT) ? 3 : 2;
-    static constexpr int kKSteps = BF ? 2 : 4;                      // UMMAs along K per chunk (32-byte steps)
-    static constexpr size_t kSmem = (size_t)kNStages * kStage + 1024 + 256;
-    static constexpr uint32_t kIdesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24))
-                                          : kIdescTf32;
+    static constexpr int kStage = kA + kParts * kBPart;             // F16x2: 48 KB (complex taps 64 KB); BF16x3: 72 KB (96 KB)
+    static constexpr int kNStages = F16 ? (CT ? 3 : 4) : (CT ? 2 : 3);
+    static constexpr int kKSteps = 2;                               // UMMAs along K per chunk (32-byte steps)
+    static constexpr int kProducts = F16 ? 3 : 6;                   // (A part, B part) products per K step
+    static constexpr size_t kSmemFixed = (size_t)kNStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // kind::f16 instruction descriptor: D f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), K-major both,
+    // N >> 3 at bit 17, M >> 4 at bit 24; bit 13 negates A
+    static constexpr uint32_t kTy = F16 ? 0u : 1u;
+    static constexpr uint32_t kIdesc = (1u << 4) | (kTy << 7) | (kTy << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 };
+// N = 128: the cross terms of complex taps, D[:, re] -= Gi Xim (negate-A bit), D[:, im] += Gi Xre
+template <bool F16>
+constexpr uint32_t kIdescHalf = (1u << 4) | ((F16 ? 0u : 1u) << 7) | ((F16 ? 0u : 1u) << 10) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+template <bool F16>
+constexpr uint32_t kIdescHalfNegA = kIdescHalf<F16> | (1u << 13);
+// (A part, B part) of product t, most significant first
+__device__ __forceinline__ constexpr int prod_a(bool f16, int t) { return f16 ? (t == 2 ? 1 : 0) : (t == 2 || t == 3 ? 1 : (t == 5 ? 2 : 0)); }
+__device__ __forceinline__ constexpr int prod_b(bool f16, int t) { return f16 ? (t == 1 ? 1 : 0) : (t == 1 || t == 3 ? 1 : (t == 4 ? 2 : 0)); }
 
-// bf16 MMA with N = 128: the cross terms of complex taps, D[:, re] -= Gi Xim (negate-A bit), D[:, im] += Gi Xre
-constexpr uint32_t kIdescBf16Half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNB >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-constexpr uint32_t kIdescBf16HalfNegA = kIdescBf16Half | (1u << 13);
-
-// K-major SWIZZLE_64B descriptor: rows of 64 bytes, 8-row groups 512 bytes apart
+// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 bytes, 8-row groups 512 bytes apart; the tile base
+// is 1024-byte aligned, a K step of 16 elements advances the start address by 32 bytes
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
     return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], 16-bit inputs, f32 accumulation, issued by one thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -426,17 +224,20 @@ struct TcFusedArgs {
     const float2 *hist;   // [C][H]: the last H inputs of the previous call per channel, oldest first
     int H;                // T-1 for the FIR, S (the PFB window) for the interpolator
     float2 *out;          // [C][out_stride]
-    void *scratch;        // [gridDim.x * 2][2 * parts][tile_plane] elements
+    void *scratch;        // [gridDim.x * nbuf][2 * parts][tile_plane] elements
+    uint32_t *flags;      // [ntiles]: set when a tile's samples hold an Inf / NaN (fir_tc_post_kernel recomputes it)
     int tile_plane;       // elements per plane of one tile buffer = Koff + 128 R rounded up to R
     int Koff;
     int R, rsh;           // input samples per block row (128 / L); rsh = log2(R / 32)
     int tiles_per_ch;     // tiles per channel (a tile = 128 blocks = 16384 outputs = 128 R inputs)
     int ntiles, nchunks, gchunks, ngroups;
-    int slice;            // plane positions converted per slice (multiple of 8)
+    int slice;            // plane positions converted per slice (multiple of 64)
     int nslices;          // the next tile's split is cut into this many slices (<= ngroups), one before each of the first chain waits
     int nbuf;             // ring buffers per CTA (2..4): the split runs nbuf - 1 tiles ahead of the flush
     int dbg;              // experiments only (SGPU_FIR_TC_DBG): 1 = no MMAs issued, 2 = no TMA loads issued (results are garbage)
     int vec_ok;
+    int sc_len;           // F16x2: floats per slot of the shared-memory scale table (>= groups per tile)
+    int rg;               // F16x2: log2(R / 64): scale group of (block b, chain c) = (b << rg) + c
     float scale, scale_im;  // complex scale only with complex taps (fir/mod.rs:211)
 };
 
@@ -453,7 +254,7 @@ __device__ __forceinline__ uint32_t bf16_pair(float lo, float hi) {  // two bf16
     return r;
 }
 
-// L2 residency hints: the split ring (60-80 MB, rewritten every other tile) should stay in the 126 MB L2 while the
+// L2 residency hints: the split ring (40-60 MB, rewritten every other tile) should stay in the 126 MB L2 while the
 // sample streams pass through once (ncu without hints: 19.5 GB of DRAM writes for 8.6 GB of output at 2^30 samples)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
@@ -480,144 +281,187 @@ __device__ __forceinline__ float4 ld_hint_v4(const void *ptr, uint64_t pol) {
     return v;
 }
 
+// eight consecutive samples from x + p (16-byte aligned), de-interleaved
+__device__ __forceinline__ void ld8(const float2 *__restrict__ xp, float *re, float *im, uint64_t pol) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float4 xv = ld_hint_v4(xp + 2 * e, pol);
+        re[2 * e] = xv.x;
+        im[2 * e] = xv.y;
+        re[2 * e + 1] = xv.z;
+        im[2 * e + 1] = xv.w;
+    }
+}
+
+// ---- BF16x3 split ------------------------------------------------------------------------------------
 // plane positions [q0, q1) of tile `tile` (channel tile / tiles_per_ch, tile tt inside it): position q holds input
-// sample tt * 128 R - Koff + q of that channel
-template <bool BF, int U = 1, int NTHR = 32 * kEpiWarps, bool EXTRA = false>
-__device__ __forceinline__ void tc_split_range(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
-                                               int et, uint64_t pol_ring, uint64_t pol_stream) {
+// sample tt * 128 R - Koff + q of that channel.  Returns true when a sample with an all-ones exponent went through.
+template <int U = 1, int NTHR = 32 * kEpiWarps, bool EXTRA = false>
+__device__ __forceinline__ bool tc_split_bf16(const TcFusedArgs &a, int tile, void *__restrict__ dstv, int q0, int q1,
+                                              int et, uint64_t pol_ring, uint64_t pol_stream) {
     const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ hist = a.hist + (long long)ch * a.H;
     const long long pbase = (long long)tt * (kNB * a.R) - a.Koff;
-    if constexpr (!BF) {
-        float *__restrict__ dst = reinterpret_cast<float *>(dstv);
-        for (int q = q0 + 4 * et; q < q1; q += 4 * NTHR) {
-            const long long p = pbase + q;
-            float2 v[4];
-            if (a.vec_ok && p >= 0 && p + 3 < a.n_in) {
-                const float4 x0 = ld_hint_v4(x + p, pol_stream);
-                const float4 x1 = ld_hint_v4(x + p + 2, pol_stream);
-                v[0] = make_float2(x0.x, x0.y);
-                v[1] = make_float2(x0.z, x0.w);
-                v[2] = make_float2(x1.x, x1.y);
-                v[3] = make_float2(x1.z, x1.w);
-            } else {
+    uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
+    constexpr int kStep = 8 * NTHR;
+    float nf = 0.f;  // becomes NaN when an Inf / NaN sample is seen (0 * Inf = NaN, NaN + anything = NaN)
+    auto convert_store = [&](int qq, float *re, float *im) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = tc_fetch(a, x, hist, p + e);
-            }
-            float rh[4], ih[4], rl[4], il[4];
+        for (int e = 0; e < 8; ++e) nf = fmaf(re[e], 0.f, fmaf(im[e], 0.f, nf));
+        // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+            uint32_t wr[4], wi[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                rh[e] = rn_tf32(v[e].x);
-                ih[e] = rn_tf32(v[e].y);
-                rl[e] = rn_tf32(v[e].x - rh[e]);
-                il[e] = rn_tf32(v[e].y - ih[e]);
+                wr[e] = bf16_pair(re[2 * e], re[2 * e + 1]);
+                wi[e] = bf16_pair(im[2 * e], im[2 * e + 1]);
+                re[2 * e] -= __uint_as_float(wr[e] << 16);
+                re[2 * e + 1] -= __uint_as_float(wr[e] & 0xFFFF0000u);
+                im[2 * e] -= __uint_as_float(wi[e] << 16);
+                im[2 * e + 1] -= __uint_as_float(wi[e] & 0xFFFF0000u);
             }
-#define SGPU_U(x) __float_as_uint(x)
-            st_hint_v4(dst + q, SGPU_U(rh[0]), SGPU_U(rh[1]), SGPU_U(rh[2]), SGPU_U(rh[3]), pol_ring);
-            st_hint_v4(dst + a.tile_plane + q, SGPU_U(ih[0]), SGPU_U(ih[1]), SGPU_U(ih[2]), SGPU_U(ih[3]), pol_ring);
-            st_hint_v4(dst + 2 * a.tile_plane + q, SGPU_U(rl[0]), SGPU_U(rl[1]), SGPU_U(rl[2]), SGPU_U(rl[3]), pol_ring);
-            st_hint_v4(dst + 3 * a.tile_plane + q, SGPU_U(il[0]), SGPU_U(il[1]), SGPU_U(il[2]), SGPU_U(il[3]), pol_ring);
-#undef SGPU_U
+            st_hint_v4(dst + (size_t)(2 * part) * a.tile_plane + qq, wr[0], wr[1], wr[2], wr[3], pol_ring);
+            st_hint_v4(dst + (size_t)(2 * part + 1) * a.tile_plane + qq, wi[0], wi[1], wi[2], wi[3], pol_ring);
         }
-    } else {
-        uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
-        constexpr int kStep = 8 * NTHR;
-        auto convert_store = [&](int qq, float *re, float *im) {
-            // x = b1 + b2 + b3 (+ < 2^-25 |x|): three bf16 terms, each the rounded residual of the previous ones
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                uint32_t wr[4], wi[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    wr[e] = bf16_pair(re[2 * e], re[2 * e + 1]);
-                    wi[e] = bf16_pair(im[2 * e], im[2 * e + 1]);
-                    re[2 * e] -= __uint_as_float(wr[e] << 16);
-                    re[2 * e + 1] -= __uint_as_float(wr[e] & 0xFFFF0000u);
-                    im[2 * e] -= __uint_as_float(wi[e] << 16);
-                    im[2 * e + 1] -= __uint_as_float(wi[e] & 0xFFFF0000u);
-                }
-                st_hint_v4(dst + (size_t)(2 * part) * a.tile_plane + qq, wr[0], wr[1], wr[2], wr[3], pol_ring);
-                st_hint_v4(dst + (size_t)(2 * part + 1) * a.tile_plane + qq, wi[0], wi[1], wi[2], wi[3], pol_ring);
-            }
-        };
-        int q = q0 + 8 * et;
-        if constexpr (U > 1) {
-            // U positions per trip, all loads first: the latency of the sample loads is paid once per trip.  Only
-            // for trips that lie entirely inside the call's input; the rest goes through the guarded loop below.
-            for (; q + (U - 1) * kStep < q1; q += U * kStep) {
-                const long long p = pbase + q;
-                if (!(a.vec_ok && p >= 0 && p + (U - 1) * kStep + 7 < a.n_in)) break;
-                float re[U][8], im[U][8];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 xv = ld_hint_v4(x + p + u * kStep + 2 * e, pol_stream);
-                        re[u][2 * e] = xv.x;
-                        im[u][2 * e] = xv.y;
-                        re[u][2 * e + 1] = xv.z;
-                        im[u][2 * e + 1] = xv.w;
-                    }
-                }
-                // EXTRA: one more position in the same latency window when it is the last one of the range (a tile of
-                // 4096 + Koff positions over 128 threads leaves 4-8 positions after four full rounds)
-                float rx[8], ix[8];
-                bool extra = false;
-                if constexpr (EXTRA) {
-                    const int qe = q + U * kStep;
-                    extra = qe < q1 && qe + kStep >= q1 && p + (long long)U * kStep + 7 < a.n_in;
-                    if (extra) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float4 xv = ld_hint_v4(x + p + U * kStep + 2 * e, pol_stream);
-                            rx[2 * e] = xv.x;
-                            ix[2 * e] = xv.y;
-                            rx[2 * e + 1] = xv.z;
-                            ix[2 * e + 1] = xv.w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) convert_store(q + u * kStep, re[u], im[u]);
-                if constexpr (EXTRA) {
-                    if (extra) {
-                        convert_store(q + U * kStep, rx, ix);
-                        q += kStep;
-                    }
-                }
-            }
-        }
-        for (; q < q1; q += kStep) {
+    };
+    int q = q0 + 8 * et;
+    if constexpr (U > 1) {
+        // U positions per trip, all loads first: the latency of the sample loads is paid once per trip.  Only
+        // for trips that lie entirely inside the call's input; the rest goes through the guarded loop below.
+        for (; q + (U - 1) * kStep < q1; q += U * kStep) {
             const long long p = pbase + q;
-            float re[8], im[8];
-            if (a.vec_ok && p >= 0 && p + 7 < a.n_in) {
+            if (!(a.vec_ok && p >= 0 && p + (U - 1) * kStep + 7 < a.n_in)) break;
+            float re[U][8], im[U][8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 xv = ld_hint_v4(x + p + 2 * e, pol_stream);
-                    re[2 * e] = xv.x;
-                    im[2 * e] = xv.y;
-                    re[2 * e + 1] = xv.z;
-                    im[2 * e + 1] = xv.w;
-                }
-            } else {
+            for (int u = 0; u < U; ++u) ld8(x + p + u * kStep, re[u], im[u], pol_stream);
+            // EXTRA: one more position in the same latency window when it is the last one of the range (a tile of
+            // 4096 + Koff positions over 128 threads leaves 4-8 positions after four full rounds)
+            float rx[8], ix[8];
+            bool extra = false;
+            if constexpr (EXTRA) {
+                const int qe = q + U * kStep;
+                extra = qe < q1 && qe + kStep >= q1 && p + (long long)U * kStep + 7 < a.n_in;
+                if (extra) ld8(x + p + U * kStep, rx, ix, pol_stream);
+            }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float2 v = tc_fetch(a, x, hist, p + e);
-                    re[e] = v.x;
-                    im[e] = v.y;
+            for (int u = 0; u < U; ++u) convert_store(q + u * kStep, re[u], im[u]);
+            if constexpr (EXTRA) {
+                if (extra) {
+                    convert_store(q + U * kStep, rx, ix);
+                    q += kStep;
                 }
             }
-            convert_store(q, re, im);
         }
     }
+    for (; q < q1; q += kStep) {
+        const long long p = pbase + q;
+        float re[8], im[8];
+        if (a.vec_ok && p >= 0 && p + 7 < a.n_in) {
+            ld8(x + p, re, im, pol_stream);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 v = tc_fetch(a, x, hist, p + e);
+                re[e] = v.x;
+                im[e] = v.y;
+            }
+        }
+        convert_store(q, re, im);
+    }
+    return nf != nf;
 }
 
-template <bool BF, bool CT, bool ONE>
+// ---- F16x2 block-floating split ------------------------------------------------------------------------
+// Same positions as above.  Lanes 8j .. 8j+7 of a warp hold one group of 64 consecutive positions (q0 is a multiple of
+// 64): the group's largest |component| is found with three shuffles, its exponent E gives the scale 2^(141 - E)
+// (largest component -> [2^14, 2^15)), the scaled samples are split into f1 = fp16(s), f2 = fp16(s - f1) and the
+// factor that undoes the scale, 2^(E - 141), goes to sc[q / 64] for the epilogue (the taps' own power of two is part
+// of a.scale).
+// The loops are warp-uniform (the shuffles need all 32 lanes); lanes beyond q1 contribute zeros and store nothing.
+template <int U = 1, int NTHR = 32 * kEpiWarps>
+__device__ __forceinline__ bool tc_split_f16(const TcFusedArgs &a, int tile, void *__restrict__ dstv,
+                                             float *__restrict__ sc, int q0, int q1, int et, uint64_t pol_ring,
+                                             uint64_t pol_stream) {
+    const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+    const float2 *__restrict__ hist = a.hist + (long long)ch * a.H;
+    const long long pbase = (long long)tt * (kNB * a.R) - a.Koff;
+    uint16_t *__restrict__ dst = reinterpret_cast<uint16_t *>(dstv);
+    constexpr int kStep = 8 * NTHR;
+    const int lane = et & 31;
+    bool bad = false;
+    auto convert_store = [&](int qq, bool valid, const float *re, const float *im) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            m = max(m, max(__float_as_uint(re[e]) & 0x7FFFFFFFu, __float_as_uint(im[e]) & 0x7FFFFFFFu));
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        uint32_t E = m >> 23;
+        bad |= E == 255u;
+        E = min(max(E, 15u), 254u);
+        const float f = __uint_as_float((268u - E) << 23);  // 2^(141 - E)
+        if (valid && (lane & 7) == 0) sc[qq >> 6] = __uint_as_float((E - 14u) << 23);  // 2^(E - 141): always a normal float
+        uint32_t w1r[4], w1i[4], w2r[4], w2i[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float r0 = re[2 * e] * f, r1 = re[2 * e + 1] * f, i0 = im[2 * e] * f, i1 = im[2 * e + 1] * f;
+            const __half2 hr = __floats2half2_rn(r0, r1), hi = __floats2half2_rn(i0, i1);  // .x = low half = even position
+            const float2 fr = __half22float2(hr), fi = __half22float2(hi);
+            const __half2 lr = __floats2half2_rn(r0 - fr.x, r1 - fr.y), li = __floats2half2_rn(i0 - fi.x, i1 - fi.y);
+            w1r[e] = *reinterpret_cast<const uint32_t *>(&hr);
+            w1i[e] = *reinterpret_cast<const uint32_t *>(&hi);
+            w2r[e] = *reinterpret_cast<const uint32_t *>(&lr);
+            w2i[e] = *reinterpret_cast<const uint32_t *>(&li);
+        }
+        if (valid) {
+            st_hint_v4(dst + qq, w1r[0], w1r[1], w1r[2], w1r[3], pol_ring);
+            st_hint_v4(dst + (size_t)a.tile_plane + qq, w1i[0], w1i[1], w1i[2], w1i[3], pol_ring);
+            st_hint_v4(dst + (size_t)2 * a.tile_plane + qq, w2r[0], w2r[1], w2r[2], w2r[3], pol_ring);
+            st_hint_v4(dst + (size_t)3 * a.tile_plane + qq, w2i[0], w2i[1], w2i[2], w2i[3], pol_ring);
+        }
+    };
+    int qw = q0 + 8 * (et - lane);  // lane 0's position: every condition on qw is warp-uniform
+    if constexpr (U > 1) {
+        for (; qw + (U - 1) * kStep + 256 <= q1; qw += U * kStep) {
+            const long long pw = pbase + qw;
+            if (!(a.vec_ok && pw >= 0 && pw + (U - 1) * kStep + 255 < a.n_in)) break;
+            float re[U][8], im[U][8];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ld8(x + pw + 8 * lane + u * kStep, re[u], im[u], pol_stream);
+#pragma unroll
+            for (int u = 0; u < U; ++u) convert_store(qw + 8 * lane + u * kStep, true, re[u], im[u]);
+        }
+    }
+    for (; qw < q1; qw += kStep) {
+        const int q = qw + 8 * lane;
+        const long long p = pbase + q;
+        const bool valid = q < q1;
+        float re[8], im[8];
+        if (valid && a.vec_ok && p >= 0 && p + 7 < a.n_in) {
+            ld8(x + p, re, im, pol_stream);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 v = valid ? tc_fetch(a, x, hist, p + e) : make_float2(0.f, 0.f);
+                re[e] = v.x;
+                im[e] = v.y;
+            }
+        }
+        convert_store(q, valid, re, im);
+    }
+    return bad;
+}
+
+template <bool F16, bool CT, bool ONE>
 __global__ void __launch_bounds__(ONE ? kOneThreads : kFusedThreads, 1)
 fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcFusedArgs a) {
-    using F = Fmt<BF, CT>;
+    static_assert(!(F16 && ONE), "one-chain tiles run in the BF16x3 format (a chain of 3 chunks is not one scale group)");
+    using F = Fmt<F16, CT>;
     constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -630,6 +474,9 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_slot = bars + 8u * (2 * NS + 14);
     auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
     auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
+    // F16x2: scale table, nbuf + 1 slots of sc_len floats behind the barriers (a warp may start the split of the tile
+    // nbuf - 1 ahead while a slower warp still flushes the previous tile, so the table is one slot deeper than the ring)
+    float *sc_tab = reinterpret_cast<float *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -673,8 +520,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_arrive(full_bar(stage));
                     } else {
                         mbar_expect_tx(full_bar(stage), F::kStage);
-                        if constexpr (BF) tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
-                        else tma_load_2d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0);
+                        tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
                         tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & ((1 << a.rsh) - 1)) * kKC, q >> a.rsh, 0, buf);
                     }
                     if (++stage == NS) {
@@ -698,48 +544,32 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int q = q0; q < q1; ++q) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        if (a.dbg & 1) {
-                        } else if constexpr (BF) {
-                            uint64_t da[3], db[3];
+                        if (!(a.dbg & 1)) {
+                            uint64_t da[F::kParts], db[F::kParts];
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) {
+                            for (int i = 0; i < F::kParts; ++i) {
                                 da[i] = umma_desc_sw64(stage_a(stage) + i * F::kAPart);
                                 db[i] = umma_desc_sw64(stage_b(stage) + i * F::kBPart);
                             }
 #pragma unroll
                             for (int kk = 0; kk < F::kKSteps; ++kk) {
                                 const uint64_t off = (uint64_t)(kk * 32 >> 4);
-                                umma_bf16(d, da[0] + off, db[0] + off, F::kIdesc, (q != q0 || kk != 0) ? 1u : 0u);
-                                umma_bf16(d, da[0] + off, db[1] + off, F::kIdesc, 1u);
-                                umma_bf16(d, da[1] + off, db[0] + off, F::kIdesc, 1u);
-                                umma_bf16(d, da[1] + off, db[1] + off, F::kIdesc, 1u);
-                                umma_bf16(d, da[0] + off, db[2] + off, F::kIdesc, 1u);
-                                umma_bf16(d, da[2] + off, db[0] + off, F::kIdesc, 1u);
+#pragma unroll
+                                for (int t = 0; t < F::kProducts; ++t)
+                                    umma_f16(d, da[prod_a(F16, t)] + off, db[prod_b(F16, t)] + off, F::kIdesc,
+                                             (t != 0 || q != q0 || kk != 0) ? 1u : 0u);
                                 if constexpr (CT) {
                                     // complex taps g = gr + j gi: D_re -= Gi Xim, D_im += Gi Xre (dot_product/mod.rs:167:
                                     // complex x complex), as N = 128 MMAs on the im / re row halves of the B planes
-                                    constexpr int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
 #pragma unroll
-                                    for (int t = 0; t < 6; ++t) {
-                                        const uint64_t gi = umma_desc_sw64(stage_a(stage) + (3 + pa[t]) * F::kAPart) + off;
-                                        const uint64_t xre = db[pb[t]] + off;
+                                    for (int t = 0; t < F::kProducts; ++t) {
+                                        const uint64_t gi = umma_desc_sw64(stage_a(stage) + (F::kParts + prod_a(F16, t)) * F::kAPart) + off;
+                                        const uint64_t xre = db[prod_b(F16, t)] + off;
                                         const uint64_t xim = xre + (uint64_t)((kNB * F::kRowBytes) >> 4);
-                                        umma_bf16(d, gi, xim, kIdescBf16HalfNegA, 1u);
-                                        umma_bf16(d + kNB, gi, xre, kIdescBf16Half, 1u);
+                                        umma_f16(d, gi, xim, kIdescHalfNegA<F16>, 1u);
+                                        umma_f16(d + kNB, gi, xre, kIdescHalf<F16>, 1u);
                                     }
                                 }
-                            }
-                        } else {
-                            const uint64_t a_hi = umma_desc(stage_a(stage));
-                            const uint64_t a_lo = umma_desc(stage_a(stage) + F::kAPart);
-                            const uint64_t b_hi = umma_desc(stage_b(stage));
-                            const uint64_t b_lo = umma_desc(stage_b(stage) + F::kBPart);
-#pragma unroll
-                            for (int kk = 0; kk < F::kKSteps; ++kk) {
-                                const uint64_t off = (uint64_t)(kk * 32 >> 4);
-                                umma_tf32(d, a_hi + off, b_hi + off, F::kIdesc, (q != q0 || kk != 0) ? 1u : 0u);
-                                umma_tf32(d, a_lo + off, b_hi + off, F::kIdesc, 1u);
-                                umma_tf32(d, a_hi + off, b_lo + off, F::kIdesc, 1u);
                             }
                         }
                         umma_commit(empty_bar(stage));
@@ -769,6 +599,9 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(ready_bar(b));
         };
+        auto flag_tile = [&](int tile, bool bad) {  // a sample with an all-ones exponent: fir_tc_post_kernel redoes the tile
+            if (bad) a.flags[tile] = 1u;
+        };
         if constexpr (ONE) {
             // One accumulation chain per tile (short interpolator sub-filters: K = 64 / 96).  Nothing has to be summed
             // in registers, so a warp drains its whole TMEM lane quarter in batches of 16 columns, four warps serve a
@@ -781,15 +614,15 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int it = grp;
             int tile = (int)blockIdx.x + it * (int)gridDim.x;
             if (tile < a.ntiles) {
-                tc_split_range<BF, BF ? 4 : 2, 128, BF>(a, tile, ring + (size_t)(it % kOneRing) * buf_bytes, 0, a.tile_plane,
-                                                     et4, pol_ring, pol_stream);
+                flag_tile(tile, tc_split_bf16<4, 128, true>(a, tile, ring + (size_t)(it % kOneRing) * buf_bytes, 0, a.tile_plane,
+                                                            et4, pol_ring, pol_stream));
                 publish(it % kOneRing);
             }
             for (; tile < a.ntiles; it += NG, tile += NG * (int)gridDim.x) {
                 const int ntile = tile + NG * (int)gridDim.x;
                 if (ntile < a.ntiles) {
-                    tc_split_range<BF, BF ? 4 : 2, 128, BF>(a, ntile, ring + (size_t)((it + NG) % kOneRing) * buf_bytes, 0,
-                                                         a.tile_plane, et4, pol_ring, pol_stream);
+                    flag_tile(ntile, tc_split_bf16<4, 128, true>(a, ntile, ring + (size_t)((it + NG) % kOneRing) * buf_bytes, 0,
+                                                                 a.tile_plane, et4, pol_ring, pol_stream));
                     publish((it + NG) % kOneRing);
                 }
                 const uint32_t acc = (uint32_t)it & 1u;
@@ -833,16 +666,25 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
         } else {
+        const int nsc = a.nbuf + 1;  // slots of the scale table
+        // split of plane positions [q0, q1) of `tile` into ring buffer `nb` / scale slot `ss`
+        auto split = [&](auto u_tag, int tile, uint8_t *nb, int ss, int q0, int q1) {
+            constexpr int UU = decltype(u_tag)::value;
+            if constexpr (F16) flag_tile(tile, tc_split_f16<UU>(a, tile, nb, sc_tab + (size_t)ss * a.sc_len, q0, q1, et, pol_ring, pol_stream));
+            else flag_tile(tile, tc_split_bf16<UU>(a, tile, nb, q0, q1, et, pol_ring, pol_stream));
+        };
         // the first `ahead` tiles of this CTA: split them now
         for (int d = 0; d < ahead; ++d) {
             const int t0 = (int)blockIdx.x + d * (int)gridDim.x;
             if (t0 < a.ntiles) {
-                tc_split_range<BF>(a, t0, ring + (size_t)d * buf_bytes, 0, a.tile_plane, et, pol_ring, pol_stream);
+                split(std::integral_constant<int, 1>{}, t0, ring + (size_t)d * buf_bytes, d, 0, a.tile_plane);
                 publish(d);
             }
         }
         uint32_t use = 0;
-        int wb = ahead;  // ring buffer the tile `ahead` tiles further on goes to: (it + ahead) mod nbuf
+        int wb = ahead;       // ring buffer the tile `ahead` tiles further on goes to: (it + ahead) mod nbuf
+        int ws = ahead % nsc; // ... and its scale slot: (it + ahead) mod (nbuf + 1)
+        int fs = 0;           // scale slot of the tile being flushed: it mod (nbuf + 1)
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int next = tile + ahead * (int)gridDim.x;
             uint8_t *nbuf = ring + (size_t)wb * buf_bytes;
@@ -852,9 +694,10 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // slice is the whole split, and a ring of four buffers keeps the split -> fence -> TMA -> MMA latency
             // chain three tiles deep.
             if (next < a.ntiles) {
-                tc_split_range<BF, BF ? 4 : 2>(a, next, nbuf, 0, min(a.slice, a.tile_plane), et, pol_ring, pol_stream);
+                split(std::integral_constant<int, 4>{}, next, nbuf, ws, 0, min(a.slice, a.tile_plane));
                 if (a.nslices == 1) publish(wb);
             }
+            const float *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + ((half * kColsW) << a.rg);
             float accr[kColsW], acci[kColsW];
             {
                 const uint32_t acc = use & 1u;
@@ -870,12 +713,19 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if constexpr (F16) {
+#pragma unroll
+                    for (int i = 0; i < kColsW; ++i) {
+                        const float mlt = scf[i << a.rg];
+                        accr[i] *= mlt;
+                        acci[i] *= mlt;
+                    }
+                }
                 ++use;
             }
             for (int gi = 1; gi < a.ngroups; ++gi, ++use) {
                 if (next < a.ntiles && gi < a.nslices) {
-                    tc_split_range<BF>(a, next, nbuf, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane), et, pol_ring,
-                                       pol_stream);
+                    split(std::integral_constant<int, 1>{}, next, nbuf, ws, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane));
                     if (gi == a.nslices - 1) publish(wb);
                 }
                 const uint32_t acc = use & 1u;
@@ -890,8 +740,14 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        accr[cg * 16 + i] += re[i];
-                        acci[cg * 16 + i] += im[i];
+                        if constexpr (F16) {
+                            const float mlt = scf[((cg * 16 + i) << a.rg) + gi];
+                            accr[cg * 16 + i] = fmaf(re[i], mlt, accr[cg * 16 + i]);
+                            acci[cg * 16 + i] = fmaf(im[i], mlt, acci[cg * 16 + i]);
+                        } else {
+                            accr[cg * 16 + i] += re[i];
+                            acci[cg * 16 + i] += im[i];
+                        }
                     }
                 }
                 tc_fence_before();
@@ -919,6 +775,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
             }
             if (++wb == a.nbuf) wb = 0;
+            if (++ws == nsc) ws = 0;
+            if (++fs == nsc) fs = 0;
         }
         }  // several chains per tile (!ONE)
     }
@@ -928,6 +786,87 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Behind the tensor kernel, same stream.  Blocks [0, fix_blocks): every block scans its share of the tile flags and
+// recomputes the flagged tiles the way the reference does -- one sequential f32 dot product per output, newest sample
+// first (dot_product/mod.rs:159-170), exactly S taps, so a NaN / Inf sample reaches exactly the outputs whose window
+// holds it (fir/mod.rs:209-212; pfb.rs:85-90 for the interpolator) -- and clears the flags.
+// Blocks [fix_blocks, ...): the handle's new history, the last H of (old history ++ input) (window/mod.rs:63-71).
+struct TcPostArgs {
+    const float2 *in;
+    long long n_in, in_stride, out_stride, n_out;
+    const float2 *hist;    // state entering the call, [C][H]
+    float2 *hist_new;      // state leaving the call (nullptr: the caller updates it)
+    float2 *out;
+    uint32_t *flags;
+    const float *tp;       // [L][S][tw] f32 taps: tp[p][j] multiplies x[n - j] for output L n + p
+    int H, L, S, tw, R;
+    int tiles_per_ch, ntiles, fix_blocks;
+    long long hist_total;  // C * H
+    float scale, scale_im;
+};
+
+__global__ void __launch_bounds__(256) fir_tc_post_kernel(const TcPostArgs a) {
+    if ((int)blockIdx.x >= a.fix_blocks) {
+        const long long i = (long long)(blockIdx.x - a.fix_blocks) * 256 + threadIdx.x;
+        if (i >= a.hist_total) return;
+        const long long ch = i / a.H;
+        const int k = (int)(i - ch * a.H);
+        const long long s = a.n_in - a.H + k;
+        float2 v;
+        if (s >= 0) v = a.in[ch * a.in_stride + s];
+        else {
+            const long long h = (long long)a.H + s;
+            v = h >= 0 ? a.hist[ch * a.H + h] : make_float2(0.f, 0.f);
+        }
+        a.hist_new[i] = v;
+        return;
+    }
+    const int per = (a.ntiles + a.fix_blocks - 1) / a.fix_blocks;
+    const int t_lo = (int)blockIdx.x * per, t_hi = min(t_lo + per, a.ntiles);
+    for (int t0 = t_lo; t0 < t_hi; t0 += 256) {
+        const int t = t0 + (int)threadIdx.x;
+        const bool mine = t < t_hi && a.flags[t] != 0u;
+        if (!__syncthreads_or(mine)) continue;
+        for (int tile = t0; tile < min(t0 + 256, t_hi); ++tile) {
+            if (a.flags[tile] == 0u) continue;  // block-uniform: every thread reads the same word
+            const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+            const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
+            const float2 *__restrict__ hist = a.hist + (long long)ch * a.H;
+            float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
+            for (int k = threadIdx.x; k < kTileSamples; k += 256) {
+                const long long o = (long long)tt * kTileSamples + k;
+                if (o >= a.n_out) break;
+                const long long n = o / a.L;
+                const float *__restrict__ g = a.tp + (size_t)(o - n * a.L) * a.S * a.tw;
+                float yr = 0.f, yi = 0.f;
+                for (int j = 0; j < a.S; ++j) {
+                    const long long i = n - j;
+                    float2 w;
+                    if (i >= 0) w = x[i];
+                    else {
+                        const long long h = (long long)a.H + i;
+                        w = h >= 0 ? hist[h] : make_float2(0.f, 0.f);
+                    }
+                    if (a.tw == 2) {  // complex x complex, no contraction across the two products' sum order
+                        const float gr = g[2 * j], gi = g[2 * j + 1];
+                        yr += gr * w.x - gi * w.y;
+                        yi += gr * w.y + gi * w.x;
+                    } else {
+                        const float gj = g[j];
+                        yr = fmaf(gj, w.x, yr);
+                        yi = fmaf(gj, w.y, yi);
+                    }
+                }
+                if (a.tw == 2) y[o] = make_float2(yr * a.scale - yi * a.scale_im, yr * a.scale_im + yi * a.scale);
+                else y[o] = make_float2(yr * a.scale, yi * a.scale);
+            }
+        }
+        __syncthreads();
+        if (t < t_hi && mine) a.flags[t] = 0u;
     }
 }
 
@@ -960,36 +899,48 @@ float host_bf16_to_f32(uint16_t b) {
     memcpy(&r, &u, 4);
     return r;
 }
-
-float host_rn_tf32(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;  // round to nearest, ties away (cvt.rna.tf32.f32)
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
+uint16_t host_f16_rne(float x) {  // cvt.rn.f16.f32, |x| < 65520 (the band is scaled into [2^14, 2^15))
+    return static_cast<__half_raw>(__float2half_rn(x)).x;
 }
+float host_f16_to_f32(uint16_t b) {
+    __half_raw r;
+    r.x = b;
+    return __half2float(__half(r));
+}
+
+// Persisting-L2 carve-out for the split ring, reference counted PER DEVICE.  The limit that was in force before the
+// first handle asked is restored when the last one goes (a host application's own setting survives us).
+struct PersistDev {
+    int users = 0;
+    size_t saved_limit = 0, ours = 0;
+};
+PersistDev g_persist[64];
+std::atomic_flag g_persist_lock = ATOMIC_FLAG_INIT;
+struct PersistGuard {
+    PersistGuard() { while (g_persist_lock.test_and_set(std::memory_order_acquire)) {} }
+    ~PersistGuard() { g_persist_lock.clear(std::memory_order_release); }
+};
 
 }  // namespace
 
-static std::atomic<int> g_persist_users{0};  // handles that asked for a persisting-L2 carve-out
-
 struct FirTcState {
     int T = 0 /* taps per phase (S) */, L = 1, R = kBM /* input samples per block of 128 outputs */, Koff = 0, K = 0, nchunks = 0;
-    float *d_A = nullptr;        // [256][K]: rows 0..127 = hi, 128..255 = lo
-    float *d_planes = nullptr;   // [4][plane_cap]
-    long long plane_cap = 0;     // floats per plane allocated
-    CUtensorMap tmA;
-    bool smem_set = false;
-    // fused kernel: per-CTA ring of two split tile buffers (format: 0 = TF32x3, 1 = BF16x3)
+    int device = 0;
+    // per-CTA ring of split tile buffers (format: 0 = BF16x3, 1 = F16x2)
     void *d_ring = nullptr;
     int ring_ctas = 0, tile_plane = 0, ring_fmt = -1, ring_nbuf = 0;
     CUtensorMap tmRing;
     bool fused_smem_set[8] = {false, false, false, false, false, false, false, false};
-    bool persist_set = false;    // persisting-L2 carve-out requested (SGPU_FIR_TC_PERSIST)
-    bool ctaps = false;          // complex taps: A16 holds Gr parts then Gi parts (BF16x3 only)
-    uint16_t *d_A16 = nullptr;   // [3][128][K] bf16: b1, b2, b3 of the band
+    bool persist_set = false;    // this handle holds a reference on its device's persisting-L2 carve-out
+    bool ctaps = false;          // complex taps: the bands hold the Gr parts, then the Gi parts
+    uint16_t *d_A16 = nullptr;   // [3 (x2)][128][K] bf16: b1, b2, b3 of the band
     CUtensorMap tmA16;
+    uint16_t *d_Ah = nullptr;    // [2 (x2)][128][K] fp16: f1, f2 of the band times 2^tap_shift
+    CUtensorMap tmAh;
+    int tap_shift = 0;
+    float *d_tp = nullptr;       // [L][S][tw] f32 taps for fir_tc_post_kernel
+    uint32_t *d_flags = nullptr; // [flags_cap] non-finite tile flags, all zero between calls
+    size_t flags_cap = 0;
 };
 
 // Banded matrix of a polyphase filter bank: output o = L n + p of the stream is sum_j tp[p][j] x[n - j]
@@ -1000,8 +951,11 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S, bool comp
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SGPU_OK;
     if (L < 1 || kBM % L != 0 || kBM / L < kKC) return SGPU_OK;  // L = 1, 2, 4: row stride a multiple of the K chunk
+    for (size_t i = 0; i < (size_t)L * S * (complex_taps ? 2 : 1); ++i)
+        if (!std::isfinite(tp[i])) return SGPU_OK;  // NaN / Inf taps: the FP32 kernels propagate them as the reference does
     FirTcState *st = new (std::nothrow) FirTcState();
     if (!st) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    cudaGetDevice(&st->device);
     const int T = S;
     st->T = S;
     st->L = L;
@@ -1017,63 +971,51 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S, bool comp
         g = tp[((size_t)(m % L) * S + jj) * tw + c];
         return true;
     };
-    std::vector<float> A((size_t)2 * kBM * st->K, 0.f);  // TF32x3 band: real taps only (complex taps run as BF16x3)
-    for (int m = 0; m < kBM; ++m)
-        for (int k = 0; k < st->K; ++k) {
-            float g;
-            if (!tap(m, k, g)) continue;
-            const float hi = host_rn_tf32(g);
-            A[(size_t)m * st->K + k] = hi;
-            A[(size_t)(kBM + m) * st->K + k] = host_rn_tf32(g - hi);
-        }
-    if (cudaMalloc(&st->d_A, A.size() * sizeof(float)) != cudaSuccess) {
-        delete st;
-        return fail(SGPU_ERR_CUDA, "cudaMalloc(banded tap matrix) failed");
-    }
-    if (cudaMemcpy(st->d_A, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const size_t ntp = (size_t)L * S * tw;
+    if (cudaMalloc(&st->d_tp, ntp * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(st->d_tp, tp, ntp * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
         fir_tc_destroy(st);
-        return fail(SGPU_ERR_CUDA, "upload of the banded tap matrix failed");
+        return fail(SGPU_ERR_CUDA, "upload of the taps failed");
     }
-    const cuuint64_t gdim[2] = {(cuuint64_t)st->K, (cuuint64_t)(2 * kBM)};
-    const cuuint64_t gstr[1] = {(cuuint64_t)st->K * 4};
-    const cuuint32_t box[2] = {kKC, 2 * kBM};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&st->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, st->d_A, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        fir_tc_destroy(st);
-        return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-    }
-    {   // bf16 x 3 band for the BF16x3 format of the fused kernel; complex taps: the three Gr parts, then the Gi parts
-        std::vector<uint16_t> A16((size_t)3 * tw * kBM * st->K, 0);
+    // one power of two for all taps: the largest |tap| -> [2^14, 2^15)
+    float gmax = 0.f;
+    for (size_t i = 0; i < ntp; ++i)
+        if (std::isfinite(tp[i])) gmax = std::max(gmax, fabsf(tp[i]));
+    int ge = 0;
+    if (gmax > 0.f) frexpf(gmax, &ge);  // gmax = f 2^ge, f in [0.5, 1)
+    st->tap_shift = gmax > 0.f ? std::min(std::max(15 - ge, -100), 100) : 0;
+    auto upload_band = [&](int parts, bool f16, uint16_t **d_dst, CUtensorMap *tm) -> int {
+        std::vector<uint16_t> A16((size_t)parts * tw * kBM * st->K, 0);
         for (int c = 0; c < tw; ++c)
             for (int m = 0; m < kBM; ++m)
                 for (int k = 0; k < st->K; ++k) {
                     float g;
                     if (!tap(m, k, g, c)) continue;
-                    for (int part = 0; part < 3; ++part) {
-                        const uint16_t b = host_bf16_rne(g);
-                        A16[((size_t)(3 * c + part) * kBM + m) * st->K + k] = b;
-                        g -= host_bf16_to_f32(b);
+                    if (f16) g = std::isfinite(g) ? ldexpf(g, st->tap_shift) : 0.f;
+                    for (int part = 0; part < parts; ++part) {
+                        const uint16_t b = f16 ? host_f16_rne(g) : host_bf16_rne(g);
+                        A16[((size_t)(parts * c + part) * kBM + m) * st->K + k] = b;
+                        g -= f16 ? host_f16_to_f32(b) : host_bf16_to_f32(b);
                     }
                 }
-        if (cudaMalloc(&st->d_A16, A16.size() * sizeof(uint16_t)) != cudaSuccess ||
-            cudaMemcpy(st->d_A16, A16.data(), A16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
-            fir_tc_destroy(st);
-            return fail(SGPU_ERR_CUDA, "upload of the bf16 banded tap matrix failed");
-        }
-        const cuuint64_t gdim3[3] = {(cuuint64_t)st->K, (cuuint64_t)kBM, (cuuint64_t)(3 * tw)};
+        if (cudaMalloc(d_dst, A16.size() * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMemcpy(*d_dst, A16.data(), A16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(SGPU_ERR_CUDA, "upload of the banded tap matrix failed");
+        const cuuint64_t gdim3[3] = {(cuuint64_t)st->K, (cuuint64_t)kBM, (cuuint64_t)(parts * tw)};
         const cuuint64_t gstr3[2] = {(cuuint64_t)st->K * 2, (cuuint64_t)st->K * 2 * kBM};
-        const cuuint32_t box3[3] = {kKC, kBM, (cuuint32_t)(3 * tw)};
+        const cuuint32_t box3[3] = {kKC, kBM, (cuuint32_t)(parts * tw)};
         const cuuint32_t estr3[3] = {1, 1, 1};
-        const CUresult r3 = enc(&st->tmA16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, st->d_A16, gdim3, gstr3, box3, estr3,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r3 != CUDA_SUCCESS) {
-            fir_tc_destroy(st);
-            return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A bf16) failed: %d", (int)r3);
-        }
+        const CUresult r3 = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, *d_dst, gdim3,
+                                gstr3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r3 != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r3);
+        return SGPU_OK;
+    };
+    int rc = upload_band(3, false, &st->d_A16, &st->tmA16);
+    if (rc == SGPU_OK) rc = upload_band(2, true, &st->d_Ah, &st->tmAh);
+    if (rc != SGPU_OK) {
+        fir_tc_destroy(st);
+        return rc;
     }
     *out = st;
     return SGPU_OK;
@@ -1089,14 +1031,20 @@ int fir_tc_create(FirTcState **out, const float *taps, int T, bool complex_taps)
 
 void fir_tc_destroy(FirTcState *st) {
     if (!st) return;
-    if (st->persist_set && g_persist_users.fetch_sub(1) == 1) {  // last user: give the L2 carve-out back
-        cudaCtxResetPersistingL2Cache();
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    if (st->persist_set && st->device >= 0 && st->device < 64) {
+        PersistGuard lock;
+        PersistDev &pd = g_persist[st->device];
+        if (--pd.users == 0) {  // last user on this device: put the caller's limit back
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, pd.saved_limit);
+            pd.ours = 0;
+            (void)cudaGetLastError();
+        }
     }
-    if (st->d_A) cudaFree(st->d_A);
-    if (st->d_planes) cudaFree(st->d_planes);
     if (st->d_ring) cudaFree(st->d_ring);
     if (st->d_A16) cudaFree(st->d_A16);
+    if (st->d_Ah) cudaFree(st->d_Ah);
+    if (st->d_tp) cudaFree(st->d_tp);
+    if (st->d_flags) cudaFree(st->d_flags);
     delete st;
 }
 
@@ -1107,35 +1055,52 @@ int env_i(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <bool BF, bool CT, bool ONE>
-int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, cudaStream_t s) {
-    using F = Fmt<BF, CT>;
-    bool &set = st->fused_smem_set[(BF ? 1 : 0) + (CT ? 2 : 0) + (ONE ? 4 : 0)];
+template <bool F16, bool CT, bool ONE>
+int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, size_t smem, const cudaAccessPolicyWindow *win,
+                        cudaStream_t s) {
+    bool &set = st->fused_smem_set[(F16 ? 1 : 0) + (CT ? 2 : 0) + (ONE ? 4 : 0)];
     if (!set) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<BF, CT, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)F::kSmem));
+        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<F16, CT, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
         set = true;
     }
-    fir_tc_fused_kernel<BF, CT, ONE><<<grid, ONE ? kOneThreads : kFusedThreads, F::kSmem, s>>>(BF ? st->tmA16 : st->tmA,
-                                                                                                st->tmRing, a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(ONE ? kOneThreads : kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (win) {  // the persisting-L2 window rides on THIS launch: the caller's stream attributes are never touched
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow = *win;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    SGPU_CUDA(cudaLaunchKernelEx(&cfg, fir_tc_fused_kernel<F16, CT, ONE>, F16 ? st->tmAh : st->tmA16, st->tmRing, a));
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
 }
 
-int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
-                     float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count,
-                     cudaStream_t s) {
+}  // namespace
+
+int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
+               float2 *hist_new, float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count,
+               cudaStream_t s) {
+    if (n_in <= 0) return SGPU_OK;
     EncodeTiledFn enc = encode_fn();
-    const char *fe = getenv("SGPU_FIR_TC_FMT");
-    const int fmt = (fe && fe[0] == 't' && !st->ctaps) ? 0 : 1;  // default BF16x3; SGPU_FIR_TC_FMT=tf32 selects TF32x3
-    const int parts = fmt ? 3 : 2, elem = fmt ? 2 : 4;
     const int R = st->R;
-    const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
     // chunks per accumulation chain: 2 (64 taps); bands of up to 3 chunks run as ONE chain (the alternating-group epilogue)
     const int gchunks = st->nchunks <= 3 ? st->nchunks : std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
     const int nchains = (st->nchunks + gchunks - 1) / gchunks;
-    // one chain per tile: the one-chain kernel (four groups of warps, each four tiles ahead: ring of eight); two chains: measured no gain
+    // F16x2 (block floating point, 3 products) wherever a chain of 2 chunks is one aligned group of 64 samples of every
+    // block row: multi-chain tiles with R = 128 (FIR) or 64 (L = 2); BF16x3 (6 products) for the rest or on request
+    const char *fe = getenv("SGPU_FIR_TC_FMT");
+    // (taps whose largest magnitude is beyond 2^-25 .. 2^55 keep BF16x3: 2^-tap_shift is folded into the output scale)
+    const int fmt = (nchains > 1 && gchunks == 2 && R >= kGroup && std::abs(st->tap_shift) <= 40 && !(fe && fe[0] == 'b')) ? 1 : 0;
+    const int parts = fmt ? 2 : 3, elem = 2;
+    const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
+    // one chain per tile: the one-chain kernel (groups of warps, each NG tiles ahead); two chains: measured no gain
     const int nbuf = nchains == 1 ? kOneRing : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", nchains <= 2 ? 4 : 2)));
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
@@ -1156,15 +1121,29 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
                                     (cuuint64_t)tile_plane * elem * 2 * parts};
         const cuuint32_t box[4] = {kKC, kNB, (cuuint32_t)(2 * parts), 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = enc(&st->tmRing, fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+        const CUresult r = enc(&st->tmRing, fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                st->d_ring, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               fmt ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed: %d", (int)r);
     }
     const long long tile_in = (long long)kNB * R;
     const long long tiles_per_ch = (long long)ceil_div((size_t)n_in, (size_t)tile_in);
     if (tiles_per_ch * (long long)C >= (1ll << 31)) return fail(SGPU_ERR_UNSUPPORTED, "too many tiles for one launch");
+    const size_t ntiles = (size_t)(tiles_per_ch * (long long)C);
+    if (ntiles > st->flags_cap) {
+        if (st->d_flags) {
+            SGPU_CUDA(cudaStreamSynchronize(s));
+            cudaFree(st->d_flags);
+        }
+        st->d_flags = nullptr;
+        st->flags_cap = 0;
+        const size_t cap = round_up(ntiles, 4096);
+        if (cudaMalloc(&st->d_flags, cap * sizeof(uint32_t)) != cudaSuccess)
+            return fail(SGPU_ERR_CUDA, "cudaMalloc(tile flags, %zu bytes) failed", cap * sizeof(uint32_t));
+        SGPU_CUDA(cudaMemsetAsync(st->d_flags, 0, cap * sizeof(uint32_t), s));
+        st->flags_cap = cap;
+    }
     TcFusedArgs a{};
     a.in = in;
     a.n_in = n_in;
@@ -1175,125 +1154,109 @@ int fir_tc_run_fused(FirTcState *st, const float2 *in, long long n_in, long long
     a.H = H;
     a.out = out;
     a.scratch = st->d_ring;
+    a.flags = st->d_flags;
     a.tile_plane = tile_plane;
     a.Koff = st->Koff;
     a.R = R;
     a.rsh = R == 128 ? 2 : (R == 64 ? 1 : 0);
     a.tiles_per_ch = (int)tiles_per_ch;
-    a.ntiles = (int)(tiles_per_ch * (long long)C);
+    a.ntiles = (int)ntiles;
     a.nchunks = st->nchunks;
     a.gchunks = gchunks;
-    a.ngroups = (a.nchunks + a.gchunks - 1) / a.gchunks;
+    a.ngroups = nchains;
     // Slices of the next tile's split, one before each of the first chain waits.  Measured (tools/tc_probe.py, 2^27
     // samples): one slice per chain is best for long bands (512 taps: 80.1 vs 76.3 Gsamp/s, 2048 taps: 28.7 vs 28.0),
     // the whole split in one slice at the top of the tile (no accumulator register live, 4 positions per trip) for
     // short ones (256 taps: 107 vs 104; one-chain interpolator tiles).
     a.nslices = std::max(1, std::min(env_i("SGPU_FIR_TC_SLICES", a.nchunks >= 16 ? a.ngroups : 1), a.ngroups));
-    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.nslices), 8);
+    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.nslices), kGroup);
     a.nbuf = nbuf;
     a.dbg = env_i("SGPU_FIR_TC_DBG", 0);
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
-    a.scale = scale;
-    a.scale_im = scale_im;
+    a.rg = R == 128 ? 1 : 0;
+    a.sc_len = fmt ? (int)round_up(ceil_div((size_t)tile_plane, kGroup) + 2, 4) : 0;
+    // F16x2: the band holds taps * 2^tap_shift; the register accumulators hold outputs * 2^tap_shift
+    a.scale = fmt ? ldexpf(scale, -st->tap_shift) : scale;
+    a.scale_im = fmt ? ldexpf(scale_im, -st->tap_shift) : scale_im;
     const int grid = std::min(a.ntiles, sm_count);
-    // Keep the split ring resident: mark it as a persisting L2 window for this launch.  The per-instruction evict_last
-    // hints alone still let L2 write back about half of the ring lines (ncu, 512 taps x 2^30: 15.3 GB of DRAM writes for
-    // 8.6 GB of output); with the window 8.65 GB.  The carve-out (<= the ring size) is released with the last handle.
-    const bool persist = env_i("SGPU_FIR_TC_PERSIST", 1) != 0;
+    // Keep the split ring resident: a persisting L2 access-policy window attached to this launch (a launch attribute,
+    // the caller's stream attributes are not touched).  The per-instruction evict_last hints alone still let L2 write
+    // back about half of the ring lines (ncu, 512 taps x 2^30: 15.3 GB of DRAM writes for 8.6 GB of output); with the
+    // window 8.65 GB.  The device-wide carve-out it needs is reference counted per device and the limit found before
+    // the first handle asked is put back when the last one goes.  SGPU_FIR_TC_PERSIST=0 switches all of it off.
     const size_t ring_bytes = (size_t)sm_count * nbuf * 2 * parts * tile_plane * elem;
-    if (persist) {
-        int dev = 0, max_persist = 0, max_window = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaAccessPolicyWindow win{};
+    bool window = false;
+    if (env_i("SGPU_FIR_TC_PERSIST", 1) != 0 && st->device >= 0 && st->device < 64) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, st->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, st->device);
         if (max_persist > 0 && max_window > 0) {
+            PersistGuard lock;
+            PersistDev &pd = g_persist[st->device];
+            const size_t want = std::min<size_t>(ring_bytes, (size_t)max_persist);
             if (!st->persist_set) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(ring_bytes, (size_t)max_persist));
+                if (pd.users == 0) {
+                    pd.saved_limit = 0;
+                    cudaDeviceGetLimit(&pd.saved_limit, cudaLimitPersistingL2CacheSize);
+                    pd.ours = 0;
+                }
+                ++pd.users;
                 st->persist_set = true;
-                g_persist_users.fetch_add(1);
             }
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = st->d_ring;
-            av.accessPolicyWindow.num_bytes = std::min<size_t>(ring_bytes, (size_t)max_window);
-            av.accessPolicyWindow.hitRatio = 1.0f;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (want > pd.saved_limit && want > pd.ours) {  // never shrink what the caller (or another handle) set
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) pd.ours = want;
+            }
+            (void)cudaGetLastError();  // best effort: a refused limit must not surface as a launch failure
+            win.base_ptr = st->d_ring;
+            win.num_bytes = std::min<size_t>(ring_bytes, (size_t)max_window);
+            win.hitRatio = 1.0f;
+            win.hitProp = cudaAccessPropertyPersisting;
+            win.missProp = cudaAccessPropertyStreaming;
+            window = true;
         }
     }
-    struct WindowReset {
-        bool on;
-        cudaStream_t s;
-        ~WindowReset() {
-            if (!on) return;
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.num_bytes = 0;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-        }
-    } window_reset{persist, s};
+    const cudaAccessPolicyWindow *wp = window ? &win : nullptr;
+    int rc;
     if (a.ngroups == 1) {
-        if (st->ctaps) return fir_tc_launch_fused<true, true, true>(st, a, grid, s);
-        return fmt ? fir_tc_launch_fused<true, false, true>(st, a, grid, s) : fir_tc_launch_fused<false, false, true>(st, a, grid, s);
+        rc = st->ctaps ? fir_tc_launch_fused<false, true, true>(st, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
+                       : fir_tc_launch_fused<false, false, true>(st, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
+    } else if (fmt) {
+        const size_t tab = (size_t)(nbuf + 1) * a.sc_len * sizeof(float);
+        rc = st->ctaps ? fir_tc_launch_fused<true, true, false>(st, a, grid, Fmt<true, true>::kSmemFixed + tab, wp, s)
+                       : fir_tc_launch_fused<true, false, false>(st, a, grid, Fmt<true, false>::kSmemFixed + tab, wp, s);
+    } else {
+        rc = st->ctaps ? fir_tc_launch_fused<false, true, false>(st, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
+                       : fir_tc_launch_fused<false, false, false>(st, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
     }
-    if (st->ctaps) return fir_tc_launch_fused<true, true, false>(st, a, grid, s);
-    return fmt ? fir_tc_launch_fused<true, false, false>(st, a, grid, s) : fir_tc_launch_fused<false, false, false>(st, a, grid, s);
-}
-
-}  // namespace
-
-int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
-               float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count, cudaStream_t s) {
-    if (n_in <= 0) return SGPU_OK;
-    if (env_i("SGPU_FIR_TC", 1) != 2 || C != 1 || st->L != 1 || st->ctaps)
-        return fir_tc_run_fused(st, in, n_in, in_stride, hist, H, out, out_stride, C, scale, scale_im, sm_count, s);
-    // SGPU_FIR_TC=2: first generation (split pre-pass launch + one accumulation chain per tile), kept for comparison
-    EncodeTiledFn enc = encode_fn();
-    if (!st->smem_set) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        st->smem_set = true;
-    }
-    const long long seg_max = std::min<long long>(kSegSamples, (long long)round_up((size_t)n_in, kTileSamples));
-    const long long need = (long long)round_up((size_t)(st->Koff + seg_max), kBM);
-    if (need > st->plane_cap) {
-        if (st->d_planes) cudaFree(st->d_planes);
-        st->d_planes = nullptr;
-        st->plane_cap = 0;
-        if (cudaMalloc(&st->d_planes, (size_t)need * 4 * sizeof(float)) != cudaSuccess)
-            return fail(SGPU_ERR_CUDA, "cudaMalloc(split planes, %lld bytes) failed", need * 16);
-        st->plane_cap = need;
-    }
-    const int vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    for (long long s0 = 0; s0 < n_in; s0 += seg_max) {
-        const long long n_seg = std::min<long long>(seg_max, n_in - s0);
-        const long long plane_len = (long long)round_up((size_t)(st->Koff + n_seg), kBM);
-        const long long rows = plane_len / kBM;
-        CUtensorMap tmB;
-        const cuuint64_t gdim[3] = {(cuuint64_t)kBM, (cuuint64_t)rows, 4};
-        const cuuint64_t gstr[2] = {(cuuint64_t)kBM * 4, (cuuint64_t)plane_len * 4};
-        const cuuint32_t box[3] = {kKC, kNB, 4};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, st->d_planes, gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-
-        const long long nthreads = plane_len / 4;
-        fir_tc_split_kernel<<<(unsigned)ceil_div((size_t)nthreads, 256), 256, 0, s>>>(
-            in, n_in, hist, st->T - 1, s0 - st->Koff, st->d_planes, plane_len, vec_ok);
-        SGPU_LAUNCH_CHECK();
-        count_launch();
-
-        TcArgs a{};
-        a.out = out + s0;
-        a.n_out = n_seg;
-        a.ntiles = (int)ceil_div((size_t)n_seg, kTileSamples);
-        a.nchunks = st->nchunks;
-        a.scale = scale;
-        const int grid = std::min(a.ntiles, sm_count);
-        fir_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(st->tmA, tmB, a);
-        SGPU_LAUNCH_CHECK();
-        count_launch();
-    }
+    if (rc) return rc;
+    // fix-up of tiles that saw a non-finite sample + the new history tail, one launch
+    TcPostArgs p{};
+    p.in = in;
+    p.n_in = n_in;
+    p.in_stride = in_stride;
+    p.out_stride = out_stride;
+    p.n_out = a.n_out;
+    p.hist = hist;
+    p.hist_new = hist_new;
+    p.out = out;
+    p.flags = st->d_flags;
+    p.tp = st->d_tp;
+    p.H = H;
+    p.L = st->L;
+    p.S = st->T;
+    p.tw = st->ctaps ? 2 : 1;
+    p.R = R;
+    p.tiles_per_ch = a.tiles_per_ch;
+    p.ntiles = a.ntiles;
+    p.fix_blocks = std::min(a.ntiles, 4 * sm_count);
+    p.hist_total = hist_new ? (long long)C * H : 0;
+    p.scale = scale;
+    p.scale_im = scale_im;
+    const long long hist_blocks = (p.hist_total + 255) / 256;
+    fir_tc_post_kernel<<<(unsigned)(p.fix_blocks + hist_blocks), 256, 0, s>>>(p);
+    SGPU_LAUNCH_CHECK();
+    count_launch();
     return SGPU_OK;
 }
 

@@ -17,8 +17,11 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S, bool comp
 void fir_tc_destroy(FirTcState *st);
 
 // C channels, one call: out[c][L n + p] = scale * sum_j tp[p][j] * x[c][n-j], x[c][<0] from hist[c] (the last H
-// inputs, oldest first).  `in` and `out` must not overlap.  One persistent tcgen05 kernel launch on `s`.
+// inputs, oldest first).  `in` and `out` must not overlap.  Two launches on `s`: the persistent tcgen05 kernel and
+// fir_tc_post_kernel, which recomputes tiles that saw an Inf / NaN sample in the reference's order and, when hist_new
+// is not NULL, writes the new history (the last H of old history ++ input, [C][H]) there.
 int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_stride, const float2 *hist, int H,
-               float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count, cudaStream_t s);
+               float2 *hist_new, float2 *out, long long out_stride, size_t C, float scale, float scale_im, int sm_count,
+               cudaStream_t s);
 
 }  // namespace sgpu

@@ -12,7 +12,7 @@
 // Shared-memory plane layout and fir_chunk are those of fir_core.cuh.  Groups of a warp sit K rows
 // apart, so K is odd to keep the lanes' LDS.128 conflict free.
 //
-// Included by fir.cu inside namespace sgpu::<anonymous>, after FirArgs / fetch_sample / cp_async*.
+// Included by fir.cu inside namespace sgpu::<anonymous>, after FirArgs / fetch_sample / cp_async* / hist_tail_update.
 #pragma once
 
 // one run of R outputs over a 2R-tap sub-filter.  PAR = 0: the run's newest row sits in W[0, R) and
@@ -47,14 +47,15 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs
     constexpr int RS = ROWS | 1, STAGE_F4 = (R / 2) * RS + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *taps_s = reinterpret_cast<float *>(smem + NW * 2 * STAGE_F4);
+    const int ch = blockIdx.y;
+    hist_tail_update(a, ch, tid, NT);
     {
         const int n4 = L * (QP + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NT) dst[i] = src[i];
     }
     __syncthreads();
-    const int ch = blockIdx.y;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     float4 *stage0 = smem + warp * 2 * STAGE_F4;
     auto issue = [&](const long long n_base, float4 *plane) {
@@ -143,14 +144,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
     const int Qpad = a.Qpad, HR = Qpad / R, rows = HR + G, RS = a.RS;
     const int plane_f4 = (R / 2) * RS + 1, stage_f4 = max(M * plane_f4, 32 * (R / 2 + 1));  // room for the reduction
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * stage_f4);
+    const int ch = blockIdx.y;
+    hist_tail_update(a, ch, tid, NW * 32);
     {
         const int n4 = M * (Qpad + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
     }
     __syncthreads();
-    const int ch = blockIdx.y;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     float4 *stage = smem + (size_t)warp * stage_f4;
     // loader role: element e = k*32 + lane of a row-of-all-planes (RM consecutive input samples)
@@ -270,14 +272,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
     const int Qpad = a.Qpad, HR = Qpad / R, rows = HR + 32, RS = a.RS;
     const int stage_f4 = max((R / 2) * RS + 1, 32 * (R / 2 + 1));  // room for the output transpose
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * NS * stage_f4);
+    const int ch = blockIdx.y;
+    hist_tail_update(a, ch, tid, NW * 32);
     {
         const int n4 = (Qpad + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
+        const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
     }
     __syncthreads();
-    const int ch = blockIdx.y;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     float4 *stage0 = smem + (size_t)warp * NS * stage_f4;
     const int total_pairs = rows * (R / 2);
@@ -351,129 +354,5 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
             __syncwarp();  // the stage is free again
             if (t + 1 < TPW && m_base + STEP < a.n_out) issue(m_base + STEP, stage0);
         }
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// Walking decimator: M in {2, 4, 8} with sub-filters of <= 2R = 32 taps, ONE PHASE PER LANE (M lanes
-// share a run of R outputs).  An FFMA2 holds the dispatch port for two cycles, so every other
-// instruction costs half an FFMA2 slot; fir_decim_warp_kernel still issues 0.42 of them per FFMA2.
-// Here a lane walks K consecutive runs of its phase plane backwards in time, so a run costs one row
-// load (as in the interpolator) and the tile's loads and address math are spread over K runs; the M
-// partial sums of a run meet in a warp-private scratch (R/2 STS.128, M LDS.128, 2(M-1) FADD2) and
-// lane p stores the p-th 16-byte piece of the run: the M lanes of a group write R*8 contiguous bytes.
-template <int R, int M, int K, int NW, int MINB, int TPW>
-__global__ void __launch_bounds__(NW * 32, MINB) fir_decim_walk_kernel(const FirArgs a) {
-    extern __shared__ float4 smem[];
-    static_assert(K % 2 == 1, "K must be odd (parity of the last run)");
-    static_assert(M * 2 == R || M * 4 == R || M * 8 == R, "lane p stores R/M consecutive outputs in 16-byte pieces");
-    constexpr int G = 32 / M, HR = 2, QP = 2 * R, ROWS = HR + G * K, RS = ROWS | 1, RM = R * M, LPRW = RM / 32;
-    constexpr int PLANE_F4 = (R / 2) * RS + 1, STAGE_F4 = M * PLANE_F4, RED = R / 2 + 1, SCR_F4 = 32 * RED;
-    constexpr int NPC = R / 2 / M;  // 16-byte pieces per lane
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * (STAGE_F4 + SCR_F4));
-    {
-        const int n4 = M * (QP + kTapSkew) / 4;
-        const float4 *src = reinterpret_cast<const float4 *>(a.taps);
-        float4 *dst = reinterpret_cast<float4 *>(taps_s);
-        for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int ch = blockIdx.y;
-    const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
-    float4 *stage = smem + (size_t)warp * (STAGE_F4 + SCR_F4);
-    float4 *scr = stage + STAGE_F4;
-    unsigned sdst[LPRW];
-    int eoff[LPRW];
-#pragma unroll
-    for (int k = 0; k < LPRW; ++k) {
-        const int e = k * 32 + lane, rem = e % M, j = e / M, p = M - 1 - rem;
-        eoff[k] = ((p * PLANE_F4 + (j >> 1) * RS) << 1) + (j & 1);
-        sdst[k] = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float2 *>(stage) + eoff[k]);
-    }
-    auto issue = [&](const long long m_base) {
-        const long long i_lo = (m_base - QP) * M - a.c0;
-        if (i_lo >= 0 && i_lo + (long long)ROWS * RM <= a.n_in) {
-            const float2 *src = x + i_lo + lane;
-#pragma unroll 2
-            for (int rho = 0; rho < ROWS; ++rho) {
-#pragma unroll
-                for (int k = 0; k < LPRW; ++k)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst[k] + 16u * rho), "l"(src + k * 32)
-                                 : "memory");
-                src += RM;
-            }
-        } else {
-            const float2 *__restrict__ hist = a.hist + (long long)ch * (a.T - 1);
-            float2 *base = reinterpret_cast<float2 *>(stage);
-            long long i = i_lo + lane;
-            for (int rho = 0; rho < ROWS; ++rho) {
-#pragma unroll
-                for (int k = 0; k < LPRW; ++k) {
-                    const long long ii = i + k * 32;
-                    if (ii >= 0 && ii < a.n_in) cp_async8(base + eoff[k] + 2 * rho, x + ii);
-                    else base[eoff[k] + 2 * rho] = fetch_sample(x, hist, ii, a.n_in, a.T);
-                }
-                i += RM;
-            }
-        }
-    };
-    const int g = lane / M, p = lane % M;
-    const float *tp = taps_s + p * (QP + kTapSkew);
-    const float4 *plane = stage + (size_t)p * PLANE_F4;
-    const float sc = a.scale_re;
-    constexpr int TILE = G * K * R;                   // outputs per warp tile
-    constexpr long long STEP = (long long)NW * TILE;  // warps take the block's tiles round-robin
-    long long m_base = ((long long)blockIdx.x * NW * TPW + warp) * (long long)TILE;
-    if (m_base >= a.n_out) return;
-    issue(m_base);
-#pragma unroll 1
-    for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += STEP) {
-        cp_async_wait_all();
-        __syncwarp();
-        int row = HR + g * K + (K - 1);
-        long long o0 = m_base + (long long)(g * K + (K - 1)) * R;  // first output of the group's newest run
-        float2 W[2 * R], acc[R];
-        load_row<R, 0>(W, plane, RS, row);
-        load_row<R, R>(W, plane, RS, row - 1);
-        auto finish = [&]() {  // partial sums of the M lanes -> lane p's pieces -> global
-#pragma unroll
-            for (int q = 0; q < R / 2; ++q)
-                scr[lane * RED + q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
-            __syncwarp();
-            float2 *__restrict__ y = a.out + (long long)ch * a.out_stride + o0;
-#pragma unroll
-            for (int k = 0; k < NPC; ++k) {
-                const int piece = k * M + p;
-                float2 lo = make_float2(0.f, 0.f), hi = lo;
-#pragma unroll
-                for (int sl = 0; sl < M; ++sl) {
-                    const float4 v = scr[(g * M + sl) * RED + piece];
-                    lo = __fadd2_rn(lo, make_float2(v.x, v.y));
-                    hi = __fadd2_rn(hi, make_float2(v.z, v.w));
-                }
-                const int q = 2 * piece;
-                if (a.vec_out && o0 + R <= a.n_out) {
-                    *reinterpret_cast<float4 *>(y + q) = make_float4(lo.x * sc, lo.y * sc, hi.x * sc, hi.y * sc);
-                } else {
-                    if (o0 + q < a.n_out) y[q] = make_float2(lo.x * sc, lo.y * sc);
-                    if (o0 + q + 1 < a.n_out) y[q + 1] = make_float2(hi.x * sc, hi.y * sc);
-                }
-            }
-            __syncwarp();  // scratch free for the next run
-            o0 -= R;
-        };
-#pragma unroll 1
-        for (int it = 0; it < (K - 1) / 2; ++it) {
-            walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);
-            finish();
-            walk_run<R, 1>(acc, W, plane, RS, row - 3, tp);
-            finish();
-            row -= 2;
-        }
-        walk_run<R, 0>(acc, W, plane, RS, row - 2, tp);
-        finish();
-        // every lane has finished reading the planes (the syncwarp in finish): refill the stage
-        if (t + 1 < TPW && m_base + STEP < a.n_out) issue(m_base + STEP);
     }
 }

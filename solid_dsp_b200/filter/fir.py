@@ -97,12 +97,16 @@ class FIRFilter(_FirHandle):
     """FIRFilter<Coef, In> -- fir/mod.rs:58-316.  y[n] = scale * sum_i h[T-1-i] x[n-i]."""
 
     def __init__(self, coefficents, scale=1.0, n_channels: int = 1):
+        """coefficents: [T] taps shared by all channels, or [C, T]: one tap set per channel (C reference objects)."""
         super().__init__()
         cv, kind, n, self._coefs_in = as_doubles(coefficents)
+        per_channel = self._coefs_in.ndim == 2
+        if per_channel:
+            n_channels = self._coefs_in.shape[0]
         self._C = n_channels
         self._complex = kind == _ffi.TAPS_COMPLEX
-        _check_ctor(lib.sgpu_fir_create(dptr(cv), n, kind, n_channels, *_scale_parts(scale), 0, 0,
-                                        C.byref(self._h)))
+        create = lib.sgpu_fir_create_per_channel if per_channel else lib.sgpu_fir_create
+        _check_ctor(create(dptr(cv), n, kind, n_channels, *_scale_parts(scale), 0, 0, C.byref(self._h)))
 
     def set_scale(self, scale):  # fir/mod.rs:106
         check(lib.sgpu_fir_set_scale(self._h, *_scale_parts(scale)))
@@ -118,10 +122,10 @@ class FIRFilter(_FirHandle):
     def is_empty(self) -> bool:  # fir/mod.rs:158
         return self.len() == 0
 
-    def coefficients(self):  # fir/mod.rs:176 -- stored (reversed) order
+    def coefficients(self, channel: int = 0):  # fir/mod.rs:176 -- stored (reversed) order
         n = self.len()
         out = np.zeros(n * (2 if self._complex else 1))
-        check(lib.sgpu_fir_coefficients(self._h, dptr(out)))
+        check(lib.sgpu_fir_channel_coefficients(self._h, channel, dptr(out)))
         return out.view(np.complex128) if self._complex else out
 
     def execute_block(self, samples):  # fir/mod.rs:235
@@ -170,12 +174,15 @@ class DecimatingFIRFilter(FIRFilter):
     def __init__(self, coefficents, scale, decimation: int, n_channels: int = 1):
         _FirHandle.__init__(self)
         cv, kind, n, self._coefs_in = as_doubles(coefficents)
+        per_channel = self._coefs_in.ndim == 2
+        if per_channel:
+            n_channels = self._coefs_in.shape[0]
         self._C = n_channels
         self._complex = kind == _ffi.TAPS_COMPLEX
         if n > 0 and decimation < 1:  # decim.rs:30 (usize cannot be negative; mirror the check)
             raise FIRError(FIRErrorCode.DecimationLessThanOne)
-        _check_ctor(lib.sgpu_fir_create(dptr(cv), n, kind, n_channels, *_scale_parts(scale), 1,
-                                        max(decimation, 0), C.byref(self._h)))
+        create = lib.sgpu_fir_create_per_channel if per_channel else lib.sgpu_fir_create
+        _check_ctor(create(dptr(cv), n, kind, n_channels, *_scale_parts(scale), 1, max(decimation, 0), C.byref(self._h)))
 
     def get_decimation(self) -> int:  # decim.rs:96
         return lib.sgpu_fir_decimation(self._h)
@@ -269,11 +276,14 @@ class InterpolatingFIRFilter(_InterpHandle):
 
     def __init__(self, coefficents, interpolation: int, n_channels: int = 1):
         _FirHandle.__init__(self)
-        cv, kind, n, _ = as_doubles(coefficents)
+        cv, kind, n, orig = as_doubles(coefficents)
+        per_channel = orig.ndim == 2
+        if per_channel:
+            n_channels = orig.shape[0]
         self._C = n_channels
         self._complex = kind == _ffi.TAPS_COMPLEX
-        _check_ctor(lib.sgpu_interp_create(dptr(cv), n, kind, n_channels, max(interpolation, 0),
-                                           C.byref(self._h)))
+        create = lib.sgpu_interp_create_per_channel if per_channel else lib.sgpu_interp_create
+        _check_ctor(create(dptr(cv), n, kind, n_channels, max(interpolation, 0), C.byref(self._h)))
 
     def interpolation(self) -> int:  # interp.rs:82
         return lib.sgpu_interp_interpolation(self._h)

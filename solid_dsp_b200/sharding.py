@@ -35,9 +35,12 @@ def exchange_halo(x_local, halo_out, rank: int, world: int, dist):
     """Send the last len(halo_out) samples of this rank's segment to rank+1 and receive the
     previous rank's tail into halo_out (rank 0 keeps halo_out as is: the filter's own history).
     x_local / halo_out are 1-D complex64 torch tensors on the communicator's device."""
-    if world == 1:
-        return halo_out
     h = halo_out.shape[0]
+    if world == 1 or h == 0:  # a 1-tap filter has no history: nothing to exchange (x_local[-0:] would be the whole segment)
+        return halo_out
+    if rank + 1 < world and x_local.shape[0] < h:
+        raise ValueError(f"rank {rank}: segment of {x_local.shape[0]} samples is shorter than the halo ({h}): the next "
+                         "rank would need samples of the rank before this one; use fewer ranks for this stream")
     ops = []
     if rank + 1 < world:
         tail = x_local[-h:].contiguous()

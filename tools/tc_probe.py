@@ -12,8 +12,7 @@ from solid_dsp_b200.filter.fir import FIRFilter  # noqa: E402
 from tests._util import f32_taps, nerr  # noqa: E402
 
 
-MODES = {"ffma": ("0", "2", "tf32"), "tc-tf32-c2": ("1", "2", "tf32"), "tc-bf16-c2": ("1", "2", "bf16"),
-         "tc-bf16-c4": ("1", "4", "bf16"), "tc-bf16-c1": ("1", "1", "bf16")}
+MODES = {"ffma": ("0", "2", "f16"), "tc-f16x2": ("1", "2", "f16"), "tc-bf16x3": ("1", "2", "bf16")}
 
 
 def run(h, x, tc, reps=3):
