@@ -234,6 +234,13 @@ int sgpu_iir_set_mode(sgpu_iir *f, int mode);
  * preceded by that many samples of the previous segment: reset, execute_block(halo) with the output
  * discarded, then execute_block(segment).  No counterpart in the reference (it is single-threaded). */
 int sgpu_iir_decay_length(sgpu_iir *f, size_t *n);
+/* A^n: how the state of a second-order cascade evolves over n samples of ZERO input, as a D x D matrix of doubles
+ * (row-major, D = *dim = 2 * sections, state order and scaling of sgpu_iir_get_state), built in f64 from the f32
+ * coefficients the kernels use.  With the end state z of a segment run from zero state, the state after the segment
+ * from any start state s is A^n s + z (iir/mod.rs:281-287 and sos.rs:92-114 are linear): that is all the ranks of a
+ * stream cut into time segments have to exchange to make the cut exact for ANY filter (SURVEY 8e row 3;
+ * solid_dsp_b200/sharding.py: iir_segment_exact).  A == NULL: only *dim is written. */
+int sgpu_iir_transition(sgpu_iir *f, uint64_t n, double *A, size_t *dim);
 
 /* ---- AutoCorrelator ------------------------------------------------------------------
  * filter/auto_correlator/mod.rs: new(window_size, delay) :51-62, push :99-111, write :130-141,

@@ -123,6 +123,7 @@ extern "C" {
     pub fn sgpu_iir_state_len(f: *const sgpu_iir) -> size_t;
     pub fn sgpu_iir_set_mode(f: *mut sgpu_iir, mode: c_int) -> c_int;
     pub fn sgpu_iir_decay_length(f: *mut sgpu_iir, n: *mut usize) -> c_int;
+    pub fn sgpu_iir_transition(f: *mut sgpu_iir, n: u64, a: *mut c_double, dim: *mut size_t) -> c_int;
 
     pub fn sgpu_autocorr_create(window_size: size_t, delay: size_t, n_channels: size_t,
                                 out: *mut *mut sgpu_autocorr) -> c_int;

@@ -110,6 +110,7 @@ PROTOTYPES = {
     "sgpu_iir_state_len": (c_size, [vp]),
     "sgpu_iir_set_mode": (C.c_int, [vp, C.c_int]),
     "sgpu_iir_decay_length": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    "sgpu_iir_transition": (C.c_int, [vp, C.c_uint64, c_dp, c_sizep]),
     "sgpu_autocorr_create": (C.c_int, [c_size, c_size, c_size, vpp]),
     "sgpu_autocorr_destroy": (C.c_int, [vp]),
     "sgpu_autocorr_clone": (C.c_int, [vp, vpp]),

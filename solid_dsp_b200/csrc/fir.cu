@@ -32,7 +32,19 @@ struct FirArgs {
     int RS;                 // row stride of a plane in float4, odd
     int vec_in, vec_out;    // 16-byte vector access allowed
     float scale_re, scale_im;
+    // NCO mix-down fused in front of the filter (DDC, nco/mod.rs:141-172): sample i of this call is multiplied by
+    // conj(phasor(nco_theta + i * nco_delta)) before the filter sees it; lut = 1024 x (cos, sin), NULL = no mixing
+    unsigned nco_theta, nco_delta;
+    const float2 *lut;
 };
+
+// NCO phasor of a 32-bit phase (nco/mod.rs:98-114): table index = ((theta + 2^21) >> 22) & 1023, sin = table[index],
+// cos = table[(index + 256) & 1023]; the table here holds the (cos, sin) pair per index
+__device__ __forceinline__ float2 nco_mix_down(const float2 x, const unsigned theta, const float2 *__restrict__ lut) {
+    const float2 cs = lut[(theta + (1u << 21)) >> 22];
+    // conj(cos + j sin) * x  (nco/mod.rs:147-151)
+    return make_float2(fmaf(cs.x, x.x, cs.y * x.y), fmaf(cs.x, x.y, -cs.y * x.x));
+}
 
 // sample `i` of this call's logical input: i < 0 reads the history, beyond either end is 0
 __device__ __forceinline__ float2 fetch_sample(const float2 *__restrict__ x,
@@ -65,8 +77,10 @@ __device__ __forceinline__ void hist_tail_update(const FirArgs &a, const int ch,
     for (int i = tid; i < H; i += nthr) {
         const long long s = a.n_in - H + i;
         float2 v;
-        if (s >= 0) v = x[s];
-        else {
+        if (s >= 0) {
+            v = x[s];
+            if (a.lut) v = nco_mix_down(v, a.nco_theta + (unsigned)s * a.nco_delta, a.lut);  // the history holds MIXED samples
+        } else {
             const long long h = (long long)H + s;
             v = h >= 0 ? ho[h] : make_float2(0.f, 0.f);
         }
@@ -401,6 +415,11 @@ __global__ void __launch_bounds__(128) fir_direct_kernel(const FirArgs a) {
     const float *__restrict__ img = a.taps + (long long)ch * a.tap_stride;
     const int rs = a.Qpad * TW + kTapSkew;
     float yr = 0.f, yi = 0.f;
+    auto fetch = [&](const long long i) {
+        float2 w = fetch_sample(x, hist, i, a.n_in, a.T);
+        if (a.lut && i >= 0 && i < a.n_in) w = nco_mix_down(w, a.nco_theta + (unsigned)i * a.nco_delta, a.lut);
+        return w;
+    };
     auto mac = [&](const float *g, const float2 w) {
         if constexpr (CT) {  // (gr + j gi)(wx + j wy)
             yr += g[0] * w.x - g[1] * w.y;
@@ -414,13 +433,13 @@ __global__ void __launch_bounds__(128) fir_direct_kernel(const FirArgs a) {
         const long long n = o / a.M;
         const float *g = img + (size_t)(o - n * a.M) * rs;
         const int S = a.T - 1;
-        for (int j = 0; j < S; ++j) mac(g + (size_t)j * TW, fetch_sample(x, hist, n - j, a.n_in, a.T));
+        for (int j = 0; j < S; ++j) mac(g + (size_t)j * TW, fetch(n - j));
         a.out[(long long)ch * a.out_stride + o] = make_float2(yr, yi);  // no scale: pfb.rs:85-90
     } else {
         const long long n = o * a.M + (a.M - 1 - a.c0);
         int p = 0, q = 0;
         for (int k = 0; k < a.T; ++k) {
-            mac(img + (size_t)p * rs + (size_t)q * TW, fetch_sample(x, hist, n - k, a.n_in, a.T));
+            mac(img + (size_t)p * rs + (size_t)q * TW, fetch(n - k));
             if (++p == a.M) { p = 0; ++q; }
         }
         float2 y;

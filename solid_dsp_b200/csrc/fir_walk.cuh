@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(NT, MINB) fir_interp_walk_kernel(const FirArgs
 // free by then): a lane writes its R sums as R/2 float4, then reads and adds the PS partials of
 // the pieces it stores -- every PS-th 16-byte piece of the run, so each store instruction writes
 // whole 32-byte sectors.  8 STS + 8 LDS + 12 FADD2 instead of the 128 SHFL/FADD of a butterfly.
-template <int R, int M, int PS, int NW, int MINB, int TPW, bool ONE = false>
+// MIX: the NCO mix-down of a digital down-converter (nco/mod.rs:141-172) is applied to the tile IN shared memory, by
+// the lane that loaded the element, right after the asynchronous copies have landed: the mixed stream never exists in
+// HBM and the loads stay asynchronous.  History samples (in front of the call) are already mixed.
+template <int R, int M, int PS, int NW, int MINB, int TPW, bool ONE = false, bool MIX = false>
 __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const FirArgs a) {
     extern __shared__ float4 smem[];
     constexpr int G = 32 / PS, MP = M / PS, RM = R * M, LPRW = RM / 32;  // LPRW: loader steps per row of all planes
@@ -146,11 +149,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * stage_f4);
     const int ch = blockIdx.y;
     hist_tail_update(a, ch, tid, NW * 32);
+    const int n4 = M * (Qpad + kTapSkew) / 4;
     {
-        const int n4 = M * (Qpad + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
+    }
+    const float2 *lut_s = reinterpret_cast<const float2 *>(reinterpret_cast<float4 *>(taps_s) + n4);  // MIX: 1024 x (cos, sin)
+    if constexpr (MIX) {
+        float4 *dst = reinterpret_cast<float4 *>(taps_s) + n4;
+        const float4 *src = reinterpret_cast<const float4 *>(a.lut);
+        for (int i = tid; i < 512; i += NW * 32) dst[i] = src[i];
     }
     __syncthreads();
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
@@ -192,6 +201,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
             }
         }
     };
+    // MIX: every element of the tile this lane loaded that belongs to this call's input gets its phasor
+    auto mix_tile = [&](const long long m_base) {
+        const long long i_lo = (m_base - Qpad) * M - a.c0;
+        float2 *base = reinterpret_cast<float2 *>(stage);
+        const unsigned d_row = (unsigned)RM * a.nco_delta, d_k = 32u * a.nco_delta;
+        unsigned th_row = a.nco_theta + (unsigned)(i_lo + lane) * a.nco_delta + (1u << 21);  // rounding folded in
+        long long i = i_lo + lane;
+        for (int rho = 0; rho < rows; ++rho) {
+            unsigned th = th_row;
+#pragma unroll
+            for (int k = 0; k < LPRW; ++k) {
+                const long long ii = i + k * 32;
+                if (ii >= 0 && ii < a.n_in) {
+                    float2 *p = base + eoff[k] + 2 * rho;
+                    const float2 x = *p, cs = lut_s[th >> 22];
+                    *p = make_float2(fmaf(cs.x, x.x, cs.y * x.y), fmaf(cs.x, x.y, -cs.y * x.x));
+                }
+                th += d_k;
+            }
+            th_row += d_row;
+            i += RM;
+        }
+    };
     const int g = lane / PS, part = lane % PS;
     const int nchunks = Qpad / R;
     constexpr int TILE = G * R;  // outputs per warp tile
@@ -203,6 +235,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
 #pragma unroll 1
     for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += STEP) {
         cp_async_wait_all();
+        if constexpr (MIX) mix_tile(m_base);  // each lane touches only what it loaded itself: no barrier in front
         __syncwarp();
         float2 acc[R];
 #pragma unroll

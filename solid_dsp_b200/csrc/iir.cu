@@ -1190,6 +1190,22 @@ SGPU_EXPORT int sgpu_iir_decay_length(sgpu_iir *f, size_t *n) {
     return SGPU_OK;
 }
 
+SGPU_EXPORT int sgpu_iir_transition(sgpu_iir *f, uint64_t n, double *A, size_t *dim) {
+    if (!f || !dim) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    if (f->type != SGPU_IIR_SECOND_ORDER) return fail(SGPU_ERR_UNSUPPORTED, "transition matrix: second-order cascades only");
+    const int D = 2 * f->nsec_pad, Da = 2 * f->nsec;
+    *dim = (size_t)Da;
+    if (!A) return SGPU_OK;
+    std::vector<double> A1, An;
+    build_transition(f, A1);  // over the kernel's (folded) coefficients, i.e. on device-scaled states v / gpre[s]
+    mat_pow(A1, (long long)n, An, D);
+    // get_state / set_state speak the reference's scaling: A_ref = G A_dev G^-1, G = diag(gpre); the identity padding
+    // sections sit behind the real ones and the cascade is block lower triangular, so the leading Da x Da block is closed
+    for (int i = 0; i < Da; ++i)
+        for (int j = 0; j < Da; ++j) A[(size_t)i * Da + j] = An[(size_t)i * D + j] * f->gpre[i / 2] / f->gpre[j / 2];
+    return SGPU_OK;
+}
+
 SGPU_EXPORT int sgpu_iir_numerator_coefs(const sgpu_iir *f, double *out, size_t *n) {
     if (!f || !n) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
     const std::vector<double> &v = f->type == SGPU_IIR_SECOND_ORDER ? f->ff_raw : f->num_norm;

@@ -118,6 +118,15 @@ class IIRFilter(Filter):
         check(lib.sgpu_iir_decay_length(self._h, C.byref(n)))
         return n.value
 
+    def transition(self, n: int):
+        """A^n [D, D] float64: evolution of the cascade's state (get_state order and scaling) over n samples of zero
+        input.  state_after = A^n @ state_before + (end state of the same samples run from zero state)."""
+        d = _ffi.c_size()
+        check(lib.sgpu_iir_transition(self._h, n, None, C.byref(d)))
+        A = np.zeros((d.value, d.value))
+        check(lib.sgpu_iir_transition(self._h, n, A.ctypes.data_as(_ffi.c_dp), C.byref(d)))
+        return A
+
     def execute_block(self, samples):  # iir/mod.rs:310
         ib = InBuf(samples, self._C)
         n_out = lib.sgpu_iir_out_len(self._h, ib.n)

@@ -80,6 +80,46 @@ def _worker(rank, world, port, case, ret):
             lens = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(lens, torch.tensor([len(y)]))
             assert sum(int(v) for v in lens) == n
+        elif case == "iir_exact":
+            # any cascade, also one that does not decay: zero-state segments + one all_gather of the end states +
+            # s_{r+1} = A^n s_r + z_r (the oracle stands in for the kernels; A^n from the oracle's own recurrence)
+            ff = np.array([0.2, 0.4, 0.2, 1.0, -1.0, 0.0])
+            fb = np.array([1.0, -1.9999984, 0.9999984, 1.0, -0.5, 0.25])  # section 0: the reference's active_lag poles (z ~ 1)
+            n = 9_001
+            x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+            whole, _ = O.sos_cascade_fast(ff, fb, x)
+            first, count = sharding.shard_stream(n, 1, world, rank)
+
+            class _OracleIIR:
+                def __init__(self):
+                    self.state = np.zeros((1, 4), dtype=np.complex128)
+
+                def reset(self):
+                    self.state = np.zeros((1, 4), dtype=np.complex128)
+
+                def execute_block(self, v):
+                    y, st = O.sos_cascade_fast(ff, fb, np.asarray(v).ravel(), state=self.state[0])
+                    self.state = np.asarray(st).reshape(1, 4)
+                    return y
+
+                def get_state(self):
+                    return self.state.copy(), 0
+
+                def set_state(self, st):
+                    self.state = np.asarray(st, dtype=np.complex128).reshape(1, 4)
+
+                def transition(self, k):  # columns = zero-input evolution of the unit states
+                    A = np.zeros((4, 4))
+                    for j in range(4):
+                        e = np.zeros(4, dtype=np.complex128)
+                        e[j] = 1.0
+                        _, st = O.sos_cascade_fast(ff, fb, np.zeros(k, dtype=np.complex128), state=e)
+                        A[:, j] = np.asarray(st).reshape(4).real
+                    return A
+
+            y = sharding.iir_segment_exact(_OracleIIR(), torch.from_numpy(x[first:first + count].copy()), rank, world, dist)
+            ref = whole[first:first + count]
+            assert np.max(np.abs(np.asarray(y) - ref)) <= 1e-5 * np.max(np.abs(whole))  # states cross as complex64
         else:
             Cn, n = 11, 500
             ff = [0.2, 0.4, 0.2, 0.5, 0.0, -0.5]
@@ -104,7 +144,7 @@ def _worker(rank, world, port, case, ret):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("case", ["stream", "channels", "iir_stream"])
+@pytest.mark.parametrize("case", ["stream", "channels", "iir_stream", "iir_exact"])
 def test_partitioned_equals_unpartitioned(world, case):
     port = _free_port()
     mgr = mp.Manager()
