@@ -61,7 +61,6 @@ constexpr int kBN = 2 * kNB;             // UMMA N: re columns then im columns
 constexpr int kKC = 32;                  // elements per K chunk = one 64-byte swizzle row of 16-bit operands
 constexpr int kTileSamples = kBM * kNB;  // 16384 outputs per tile
 constexpr int kTmemCols = 512;
-constexpr int kGroup = 64;               // plane positions that share one block-floating scale = one chain of 2 K-chunks
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -157,7 +156,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //    8 bytes in and 8 bytes out per sample.
 constexpr int kEpiWarps = 8;                          // 4 per TMEM lane quarter
 constexpr int kColsW = kNB / (kEpiWarps / 4);          // blocks (accumulator columns per re / im half) per epilogue warp
-constexpr int kFusedThreads = 64 + 32 * kEpiWarps;
 constexpr int kOneWarps = 8;                           // one-chain kernel: groups of four epilogue warps (measured at L=4, S=32: 2 groups 418-422, 3 groups 372, 4 groups 373 G out-samp/s)
 constexpr int kOneThreads = 64 + 32 * kOneWarps;
 constexpr int kOneRing = 2 * (kOneWarps / 4);          // ring buffers per CTA of the one-chain kernel: every group splits its next tile ahead
@@ -237,7 +235,8 @@ struct TcFusedArgs {
     int dbg;              // experiments only (SGPU_FIR_TC_DBG): 1 = no MMAs issued, 2 = no TMA loads issued (results are garbage)
     int vec_ok;
     int sc_len;           // F16x2: floats per slot of the shared-memory scale table (>= groups per tile)
-    int rg;               // F16x2: log2(R / 64): scale group of (block b, chain c) = (b << rg) + c
+    int gsh;              // F16x2: log2(group size): 5 + log2(chunks per chain)
+    int rg;               // F16x2: log2(R / group size): scale group of (block b, chain c) = (b << rg) + c
     float scale, scale_im;  // complex scale only with complex taps (fir/mod.rs:211)
 };
 
@@ -374,8 +373,8 @@ __device__ __forceinline__ bool tc_split_bf16(const TcFusedArgs &a, int tile, vo
 }
 
 // ---- F16x2 block-floating split ------------------------------------------------------------------------
-// Same positions as above.  Lanes 8j .. 8j+7 of a warp hold one group of 64 consecutive positions (q0 is a multiple of
-// 64): the group's largest |component| is found with three shuffles, its exponent E gives the scale 2^(141 - E)
+// Same positions as above.  A group of 2^gsh (64 or 128) consecutive positions sits in 8 or 16 adjacent lanes of a
+// warp (q0 is a multiple of the group): the group's largest |component| is found with shuffles, its exponent E gives the scale 2^(141 - E)
 // (largest component -> [2^14, 2^15)), the scaled samples are split into f1 = fp16(s), f2 = fp16(s - f1) and the
 // factor that undoes the scale, 2^(E - 141), goes to sc[q / 64] for the epilogue (the taps' own power of two is part
 // of a.scale).
@@ -399,12 +398,13 @@ __device__ __forceinline__ bool tc_split_f16(const TcFusedArgs &a, int tile, voi
             m = max(m, max(__float_as_uint(re[e]) & 0x7FFFFFFFu, __float_as_uint(im[e]) & 0x7FFFFFFFu));
         m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
         m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        if (a.gsh >= 6) m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        if (a.gsh >= 7) m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
         uint32_t E = m >> 23;
         bad |= E == 255u;
         E = min(max(E, 15u), 254u);
         const float f = __uint_as_float((268u - E) << 23);  // 2^(141 - E)
-        if (valid && (lane & 7) == 0) sc[qq >> 6] = __uint_as_float((E - 14u) << 23);  // 2^(E - 141): always a normal float
+        if (valid && (lane & ((1 << (a.gsh - 3)) - 1)) == 0) sc[qq >> a.gsh] = __uint_as_float((E - 14u) << 23);  // 2^(E - 141): always a normal float
         uint32_t w1r[4], w1i[4], w2r[4], w2i[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -456,11 +456,43 @@ __device__ __forceinline__ bool tc_split_f16(const TcFusedArgs &a, int tile, voi
     return bad;
 }
 
-template <bool F16, bool CT, bool ONE>
-__global__ void __launch_bounds__(ONE ? kOneThreads : kFusedThreads, 1)
-fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const TcFusedArgs a) {
-    static_assert(!(F16 && ONE), "one-chain tiles run in the BF16x3 format (a chain of 3 chunks is not one scale group)");
+// all MMAs of one K chunk (32 elements = two K steps of 16) of one accumulation chain; `first`: the chain starts here
+template <bool F16, bool CT>
+__device__ __forceinline__ void tc_issue_chunk(const uint32_t d, const uint32_t sa, const uint32_t sb, const bool first) {
+    using F = Fmt<F16, CT>;
+    uint64_t da[F::kParts], db[F::kParts];
+#pragma unroll
+    for (int i = 0; i < F::kParts; ++i) {
+        da[i] = umma_desc_sw64(sa + i * F::kAPart);
+        db[i] = umma_desc_sw64(sb + i * F::kBPart);
+    }
+#pragma unroll
+    for (int kk = 0; kk < F::kKSteps; ++kk) {
+        const uint64_t off = (uint64_t)(kk * 32 >> 4);
+#pragma unroll
+        for (int t = 0; t < F::kProducts; ++t)
+            umma_f16(d, da[prod_a(F16, t)] + off, db[prod_b(F16, t)] + off, F::kIdesc, (t != 0 || !first || kk != 0) ? 1u : 0u);
+        if constexpr (CT) {
+            // complex taps g = gr + j gi: D_re -= Gi Xim, D_im += Gi Xre (dot_product/mod.rs:167: complex x complex), as
+            // N = 128 MMAs on the im / re row halves of the B planes
+#pragma unroll
+            for (int t = 0; t < F::kProducts; ++t) {
+                const uint64_t gi = umma_desc_sw64(sa + (F::kParts + prod_a(F16, t)) * F::kAPart) + off;
+                const uint64_t xre = db[prod_b(F16, t)] + off;
+                const uint64_t xim = xre + (uint64_t)((kNB * F::kRowBytes) >> 4);
+                umma_f16(d, gi, xim, kIdescHalfNegA<F16>, 1u);
+                umma_f16(d + kNB, gi, xre, kIdescHalf<F16>, 1u);
+            }
+        }
+    }
+}
+
+// ---- one-chain tiles (bands of <= 3 K-chunks: short interpolator sub-filters), BF16x3 ----------------------------
+template <bool CT>
+__global__ void __launch_bounds__(kOneThreads, 1)
+fir_tc_one_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const TcFusedArgs a) {
+    constexpr bool F16 = false;  // a chain of 3 chunks is not one aligned scale group: BF16x3
     using F = Fmt<F16, CT>;
     constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
@@ -474,10 +506,6 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_slot = bars + 8u * (2 * NS + 14);
     auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
     auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
-    // F16x2: scale table, nbuf + 1 slots of sc_len floats behind the barriers (a warp may start the split of the tile
-    // nbuf - 1 ahead while a slower warp still flushes the previous tile, so the table is one slot deeper than the ring)
-    float *sc_tab = reinterpret_cast<float *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -486,8 +514,8 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(empty_bar(s), 1);
         }
         for (int i = 0; i < 4; ++i) mbar_init(tfull_bar(i), 1);
-        for (int i = 0; i < 2; ++i) mbar_init(tempty_bar(i), ONE ? 4 : kEpiWarps);  // one-chain tiles: four warps per tile
-        for (int i = 0; i < 8; ++i) mbar_init(ready_bar(i), ONE ? 4 : kEpiWarps);
+        for (int i = 0; i < 2; ++i) mbar_init(tempty_bar(i), 4);  // four warps per tile
+        for (int i = 0; i < 8; ++i) mbar_init(ready_bar(i), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -544,34 +572,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int q = q0; q < q1; ++q) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        if (!(a.dbg & 1)) {
-                            uint64_t da[F::kParts], db[F::kParts];
-#pragma unroll
-                            for (int i = 0; i < F::kParts; ++i) {
-                                da[i] = umma_desc_sw64(stage_a(stage) + i * F::kAPart);
-                                db[i] = umma_desc_sw64(stage_b(stage) + i * F::kBPart);
-                            }
-#pragma unroll
-                            for (int kk = 0; kk < F::kKSteps; ++kk) {
-                                const uint64_t off = (uint64_t)(kk * 32 >> 4);
-#pragma unroll
-                                for (int t = 0; t < F::kProducts; ++t)
-                                    umma_f16(d, da[prod_a(F16, t)] + off, db[prod_b(F16, t)] + off, F::kIdesc,
-                                             (t != 0 || q != q0 || kk != 0) ? 1u : 0u);
-                                if constexpr (CT) {
-                                    // complex taps g = gr + j gi: D_re -= Gi Xim, D_im += Gi Xre (dot_product/mod.rs:167:
-                                    // complex x complex), as N = 128 MMAs on the im / re row halves of the B planes
-#pragma unroll
-                                    for (int t = 0; t < F::kProducts; ++t) {
-                                        const uint64_t gi = umma_desc_sw64(stage_a(stage) + (F::kParts + prod_a(F16, t)) * F::kAPart) + off;
-                                        const uint64_t xre = db[prod_b(F16, t)] + off;
-                                        const uint64_t xim = xre + (uint64_t)((kNB * F::kRowBytes) >> 4);
-                                        umma_f16(d, gi, xim, kIdescHalfNegA<F16>, 1u);
-                                        umma_f16(d + kNB, gi, xre, kIdescHalf<F16>, 1u);
-                                    }
-                                }
-                            }
-                        }
+                        if (!(a.dbg & 1)) tc_issue_chunk<F16, CT>(d, stage_a(stage), stage_b(stage), q == q0);
                         umma_commit(empty_bar(stage));
                         if (++stage == NS) {
                             stage = 0;
@@ -580,20 +581,17 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     // ONE: a *full* barrier per warp group (tile mod 4): a parity wait is only safe for a waiter that is at
                     // most one phase behind, and two groups share each accumulator
-                    umma_commit(tfull_bar(ONE ? (use % (kOneWarps / 4)) : acc));
+                    umma_commit(tfull_bar(use % (kOneWarps / 4)));
                 }
             }
         }
-    } else {  // ===== 8 epilogue warps: chain flush into registers, split of the next tile, output =====
-        const int ew = warp - 2;        // 0..kEpiWarps-1
+    } else {  // ===== 8 epilogue warps in two groups: split of the group's next tile, drain, output =====
+        const int ew = warp - 2;        // 0..kOneWarps-1
         const int wq = warp & 3;        // TMEM lane quarter this warp may read
-        const int half = ew >> 2;       // blocks [kColsW half, kColsW half + kColsW) of the tile
-        const int et = ew * 32 + lane;  // 0..32 kEpiWarps - 1
         const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
         const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
         uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(a.nbuf * blockIdx.x) * buf_bytes;
         const uint64_t pol_ring = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-        const int ahead = a.nbuf - 1;  // the split runs this many tiles ahead of the flush
         auto publish = [&](int b) {    // a tile's planes are complete: let the producer's TMA read them
             fence_proxy_async();
             __syncwarp();
@@ -602,7 +600,7 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         auto flag_tile = [&](int tile, bool bad) {  // a sample with an all-ones exponent: fir_tc_post_kernel redoes the tile
             if (bad) a.flags[tile] = 1u;
         };
-        if constexpr (ONE) {
+        {
             // One accumulation chain per tile (short interpolator sub-filters: K = 64 / 96).  Nothing has to be summed
             // in registers, so a warp drains its whole TMEM lane quarter in batches of 16 columns, four warps serve a
             // tile, and the groups of four warps take the tiles in turn: while one group waits for its sample loads
@@ -665,94 +663,205 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-        } else {
-        const int nsc = a.nbuf + 1;  // slots of the scale table
-        // split of plane positions [q0, q1) of `tile` into ring buffer `nb` / scale slot `ss`
-        auto split = [&](auto u_tag, int tile, uint8_t *nb, int ss, int q0, int q1) {
-            constexpr int UU = decltype(u_tag)::value;
-            if constexpr (F16) flag_tile(tile, tc_split_f16<UU>(a, tile, nb, sc_tab + (size_t)ss * a.sc_len, q0, q1, et, pol_ring, pol_stream));
-            else flag_tile(tile, tc_split_bf16<UU>(a, tile, nb, q0, q1, et, pol_ring, pol_stream));
-        };
-        // the first `ahead` tiles of this CTA: split them now
-        for (int d = 0; d < ahead; ++d) {
-            const int t0 = (int)blockIdx.x + d * (int)gridDim.x;
-            if (t0 < a.ntiles) {
-                split(std::integral_constant<int, 1>{}, t0, ring + (size_t)d * buf_bytes, d, 0, a.tile_plane);
-                publish(d);
-            }
         }
-        uint32_t use = 0;
-        int wb = ahead;       // ring buffer the tile `ahead` tiles further on goes to: (it + ahead) mod nbuf
-        int ws = ahead % nsc; // ... and its scale slot: (it + ahead) mod (nbuf + 1)
-        int fs = 0;           // scale slot of the tile being flushed: it mod (nbuf + 1)
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            const int next = tile + ahead * (int)gridDim.x;
-            uint8_t *nbuf = ring + (size_t)wb * buf_bytes;
-            // Slice gi of that tile's split runs BEFORE the wait for chain gi: its ring buffer, (it - 1) mod nbuf, was
-            // last read by tile it-1, all of whose loads completed before that tile's last chain (flushed in the
-            // previous iteration) could finish.  With one chain per tile (short interpolator sub-filters) the first
-            // slice is the whole split, and a ring of four buffers keeps the split -> fence -> TMA -> MMA latency
-            // chain three tiles deep.
-            if (next < a.ntiles) {
-                split(std::integral_constant<int, 4>{}, next, nbuf, ws, 0, min(a.slice, a.tile_plane));
-                if (a.nslices == 1) publish(wb);
-            }
-            const float *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + ((half * kColsW) << a.rg);
-            float accr[kColsW], acci[kColsW];
-            {
-                const uint32_t acc = use & 1u;
-                mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * kColsW;
-#pragma unroll
-                for (int cg = 0; cg < kColsW / 16; ++cg) {
-                    tmem_ld16(taddr + cg * 16, accr + cg * 16);
-                    tmem_ld16(taddr + kNB + cg * 16, acci + cg * 16);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+
+// ---- several accumulation chains per tile (every FIR, long interpolator sub-filters): warp-specialised roles --------
+// 16 warps in four warpgroups with their own register budgets (setmaxnreg):
+//   warpgroup 0: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread), warps 2-3 idle        24 registers
+//   warpgroups 1-2 (warps 4-11): FLUSH.  Warp w reads TMEM lane quarter w % 4, columns half (w - 4) / 4 of every
+//       finished chain and adds it into 128 f32 register accumulators (F16x2: times the chain's block-floating scale),
+//       then frees the TMEM accumulator; after the tile's last chain the outputs leave from the registers.  192 registers
+//   warpgroup 3 (warps 12-15): CONVERT.  Splits the tile nbuf - 1 ahead of the one in flight into the 16-bit planes of
+//       the per-CTA ring (four positions per trip in flight, the sample loads never wait on a chain), waits only for the
+//       ring buffer to be free (rfree barrier: tcgen05.commit behind the last MMA of the tile that used it).  104 registers
+// The r1 kernel had the eight epilogue warps do both jobs in turn, so every chain flush sat behind a global-memory load
+// and the tensor pipe idled: 80 (BF16x3) and 88 (F16x2) Gsamp/s at 512 taps.
+constexpr int kChainThreads = 512;
+constexpr int kRegProducer = 24, kRegFlush = 192, kRegConvert = 104;
+static_assert(4 * kRegProducer + 8 * kRegFlush + 4 * kRegConvert <= 2048, "register file: 64 K registers per SM");
+
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <bool F16, bool CT>
+__global__ void __launch_bounds__(kChainThreads, 1)
+fir_tc_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const TcFusedArgs a) {
+    using F = Fmt<F16, CT>;
+    constexpr int NS = F::kNStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + NS * F::kStage;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (NS + s); };
+    auto tfull_bar = [&](int i) { return bars + 8u * (2 * NS + i); };       // 2 slots
+    auto tempty_bar = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };  // 2 slots
+    auto ready_bar = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };   // 4 slots: a tile's planes are in ring buffer i
+    auto rfree_bar = [&](int i) { return bars + 8u * (2 * NS + 8 + i); };   // 4 slots: every MMA that read ring buffer i is done
+    const uint32_t tmem_slot = bars + 8u * (2 * NS + 12);
+    auto stage_a = [&](int s) { return base + (uint32_t)s * F::kStage; };
+    auto stage_b = [&](int s) { return base + (uint32_t)s * F::kStage + F::kA; };
+    // F16x2: scale table, nbuf + 2 slots of sc_len floats behind the barriers.  The converter may be nbuf tiles ahead
+    // of the MMA and the flush of a tile's last chains (which reads the scales after it has handed the accumulator
+    // back) trails the MMA by up to a tile, so the table is two slots deeper than the ring.
+    float *sc_tab = reinterpret_cast<float *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar(i), 1);
+            mbar_init(tempty_bar(i), 8);  // the eight flush warps
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(ready_bar(i), 4);   // the four converter warps
+            mbar_init(rfree_bar(i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp < 4) {
+        reg_dec<kRegProducer>();
+        if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+            int stage = 0, rb = 0;
+            uint32_t phase = 0, rphase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                mbar_wait(ready_bar(rb), rphase);  // this tile's planes are in the ring
+                const int buf = a.nbuf * (int)blockIdx.x + rb;
+                if (++rb == a.nbuf) {
+                    rb = 0;
+                    rphase ^= 1u;
                 }
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
-                if constexpr (F16) {
-#pragma unroll
-                    for (int i = 0; i < kColsW; ++i) {
-                        const float mlt = scf[i << a.rg];
-                        accr[i] *= mlt;
-                        acci[i] *= mlt;
+                for (int q = 0; q < a.nchunks; ++q) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (a.dbg & 2) {
+                        mbar_arrive(full_bar(stage));
+                    } else {
+                        mbar_expect_tx(full_bar(stage), F::kStage);
+                        tma_load_3d(stage_a(stage), &tmA, full_bar(stage), q * kKC, 0, 0);
+                        tma_load_4d(stage_b(stage), &tmB, full_bar(stage), (q & ((1 << a.rsh) - 1)) * kKC, q >> a.rsh, 0, buf);
+                    }
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
-                ++use;
             }
-            for (int gi = 1; gi < a.ngroups; ++gi, ++use) {
-                if (next < a.ntiles && gi < a.nslices) {
-                    split(std::integral_constant<int, 1>{}, next, nbuf, ws, gi * a.slice, min((gi + 1) * a.slice, a.tile_plane));
-                    if (gi == a.nslices - 1) publish(wb);
+        } else if (warp == 1 && lane == 0) {  // ===== MMA issuer: one accumulation chain per TMEM accumulator use =====
+            int stage = 0, rb = 0;
+            uint32_t phase = 0, use = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int q0 = 0; q0 < a.nchunks; q0 += a.gchunks, ++use) {
+                    const uint32_t acc = use & 1u;
+                    mbar_wait(tempty_bar(acc), ((use >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * kBN;
+                    const int q1 = min(q0 + a.gchunks, a.nchunks);
+                    for (int q = q0; q < q1; ++q) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        if (!(a.dbg & 1)) tc_issue_chunk<F16, CT>(d, stage_a(stage), stage_b(stage), q == q0);
+                        umma_commit(empty_bar(stage));
+                        if (++stage == NS) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(tfull_bar(acc));
                 }
+                umma_commit(rfree_bar(rb));  // every read of this tile's ring buffer has completed by then
+                if (++rb == a.nbuf) rb = 0;
+            }
+        }
+    } else if (warp < 12) {  // ===== FLUSH: chains -> register accumulators -> outputs =====
+        reg_inc<kRegFlush>();
+        const int ew = warp - 4;        // 0..7
+        const int wq = warp & 3;        // TMEM lane quarter this warp may read
+        const int half = ew >> 2;       // blocks [kColsW half, kColsW half + kColsW) of the tile
+        const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
+        const uint64_t pol_stream = l2_policy_evict_first();
+        const int nsc = a.nbuf + 2;
+        uint32_t use = 0;
+        int fs = 0;  // scale slot of the tile being flushed: it mod (nbuf + 2)
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const float *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + ((half * kColsW) << a.rg);
+            float accr[kColsW], acci[kColsW];
+            for (int gi = 0; gi < a.ngroups; ++gi, ++use) {
                 const uint32_t acc = use & 1u;
                 mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * kColsW;
+                if (gi == 0) {
 #pragma unroll
-                for (int cg = 0; cg < kColsW / 16; ++cg) {
-                    float re[16], im[16];
-                    tmem_ld16(taddr + cg * 16, re);
-                    tmem_ld16(taddr + kNB + cg * 16, im);
+                    for (int cg = 0; cg < kColsW / 16; ++cg) {
+                        tmem_ld16(taddr + cg * 16, accr + cg * 16);
+                        tmem_ld16(taddr + kNB + cg * 16, acci + cg * 16);
+                    }
                     tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if constexpr (F16) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if constexpr (F16) {
-                            const float mlt = scf[((cg * 16 + i) << a.rg) + gi];
-                            accr[cg * 16 + i] = fmaf(re[i], mlt, accr[cg * 16 + i]);
-                            acci[cg * 16 + i] = fmaf(im[i], mlt, acci[cg * 16 + i]);
-                        } else {
-                            accr[cg * 16 + i] += re[i];
-                            acci[cg * 16 + i] += im[i];
+                        for (int i = 0; i < kColsW; ++i) {
+                            const float mlt = scf[i << a.rg];
+                            accr[i] *= mlt;
+                            acci[i] *= mlt;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int cg = 0; cg < kColsW / 16; ++cg) {
+                        float re[16], im[16];
+                        tmem_ld16(taddr + cg * 16, re);
+                        tmem_ld16(taddr + kNB + cg * 16, im);
+                        tmem_ld_wait();
+                        if (cg + 1 == kColsW / 16) {  // the accumulator is in registers: hand it back before the arithmetic
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if constexpr (F16) {
+                                const float mlt = scf[((cg * 16 + i) << a.rg) + gi];
+                                accr[cg * 16 + i] = fmaf(re[i], mlt, accr[cg * 16 + i]);
+                                acci[cg * 16 + i] = fmaf(im[i], mlt, acci[cg * 16 + i]);
+                            } else {
+                                accr[cg * 16 + i] += re[i];
+                                acci[cg * 16 + i] += im[i];
+                            }
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
             const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
             float2 *__restrict__ y = a.out + (long long)ch * a.out_stride;
@@ -774,11 +883,34 @@ fir_tc_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         else st_hint_v2(yp + i * kBM, accr[i] * a.scale, acci[i] * a.scale, pol_stream);
                     }
             }
-            if (++wb == a.nbuf) wb = 0;
-            if (++ws == nsc) ws = 0;
             if (++fs == nsc) fs = 0;
         }
-        }  // several chains per tile (!ONE)
+    } else {  // ===== CONVERT: cf32 samples -> 16-bit planes of the ring, nbuf - 1 tiles ahead =====
+        reg_dec<kRegConvert>();
+        const int et = (warp - 12) * 32 + lane;  // 0..127
+        const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
+        uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(a.nbuf * blockIdx.x) * buf_bytes;
+        const uint64_t pol_ring = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const int nsc = a.nbuf + 2;
+        int wb = 0, ws = 0;
+        uint32_t fphase = 0;  // parity of the rfree completion this buffer's next reuse waits for
+        bool wrapped = false;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            if (wrapped) mbar_wait(rfree_bar(wb), fphase);  // the tile that used this buffer nbuf tiles ago has been read
+            bool bad;
+            if constexpr (F16) bad = tc_split_f16<2, 128>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0, a.tile_plane, et, pol_ring, pol_stream);
+            else bad = tc_split_bf16<4, 128>(a, tile, ring + (size_t)wb * buf_bytes, 0, a.tile_plane, et, pol_ring, pol_stream);
+            if (bad) a.flags[tile] = 1u;  // a sample with an all-ones exponent: fir_tc_post_kernel redoes the tile
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready_bar(wb));
+            if (++wb == a.nbuf) {
+                wb = 0;
+                if (wrapped) fphase ^= 1u;
+                wrapped = true;
+            }
+            if (++ws == nsc) ws = 0;
+        }
     }
 
     tc_fence_before();
@@ -1055,18 +1187,16 @@ int env_i(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <bool F16, bool CT, bool ONE>
-int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, size_t smem, const cudaAccessPolicyWindow *win,
-                        cudaStream_t s) {
-    bool &set = st->fused_smem_set[(F16 ? 1 : 0) + (CT ? 2 : 0) + (ONE ? 4 : 0)];
+template <typename Kern>
+int fir_tc_launch(Kern kern, bool &set, int threads, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcFusedArgs &a,
+                  int grid, size_t smem, const cudaAccessPolicyWindow *win, cudaStream_t s) {
     if (!set) {
-        SGPU_CUDA(cudaFuncSetAttribute(fir_tc_fused_kernel<F16, CT, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
+        SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(ONE ? kOneThreads : kFusedThreads);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -1076,7 +1206,7 @@ int fir_tc_launch_fused(FirTcState *st, const TcFusedArgs &a, int grid, size_t s
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    SGPU_CUDA(cudaLaunchKernelEx(&cfg, fir_tc_fused_kernel<F16, CT, ONE>, F16 ? st->tmAh : st->tmA16, st->tmRing, a));
+    SGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
@@ -1090,18 +1220,25 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     if (n_in <= 0) return SGPU_OK;
     EncodeTiledFn enc = encode_fn();
     const int R = st->R;
-    // chunks per accumulation chain: 2 (64 taps); bands of up to 3 chunks run as ONE chain (the alternating-group epilogue)
-    const int gchunks = st->nchunks <= 3 ? st->nchunks : std::max(1, std::min(env_i("SGPU_FIR_TC_CHAIN", 2), st->nchunks));
-    const int nchains = (st->nchunks + gchunks - 1) / gchunks;
-    // F16x2 (block floating point, 3 products) wherever a chain of 2 chunks is one aligned group of 64 samples of every
-    // block row: multi-chain tiles with R = 128 (FIR) or 64 (L = 2); BF16x3 (6 products) for the rest or on request
+    // F16x2 (block floating point, 3 products) wherever a chain is one aligned scale group of every block row: R = 128
+    // (FIR) or 64 (L = 2), more than 3 chunks; BF16x3 (6 products) for the rest or on request (SGPU_FIR_TC_FMT=bf16).
+    // Taps whose largest magnitude is beyond 2^-25 .. 2^55 keep BF16x3 (2^-tap_shift is folded into the output scale).
     const char *fe = getenv("SGPU_FIR_TC_FMT");
-    // (taps whose largest magnitude is beyond 2^-25 .. 2^55 keep BF16x3: 2^-tap_shift is folded into the output scale)
-    const int fmt = (nchains > 1 && gchunks == 2 && R >= kGroup && std::abs(st->tap_shift) <= 40 && !(fe && fe[0] == 'b')) ? 1 : 0;
+    const bool want_f16 = st->nchunks > 3 && R >= 64 && std::abs(st->tap_shift) <= 40 && !(fe && fe[0] == 'b');
+    // Chunks per accumulation chain.  The accumulator's truncation bias grows with the MMAs per chain (24 = 2 chunks of
+    // BF16x3 = 4 chunks of F16x2: 8e-7) and every chain costs a 128 KB TMEM drain, so F16x2 runs chains of 4 chunks
+    // where the scale group of 128 samples stays aligned (R = 128), else 2.  Bands of up to 3 chunks: ONE chain.
+    int gchunks = st->nchunks <= 3 ? st->nchunks : env_i("SGPU_FIR_TC_CHAIN", want_f16 && R == 128 ? 4 : 2);
+    gchunks = std::max(1, std::min(gchunks, st->nchunks));
+    if (st->nchunks > 3 && want_f16 && gchunks != 1 && gchunks != 2 && !(gchunks == 4 && R == 128)) gchunks = 2;
+    if (st->nchunks > 3 && st->nchunks <= gchunks) gchunks = (st->nchunks + 1) / 2;  // the chain kernel wants >= 2 chains
+    const int nchains = (st->nchunks + gchunks - 1) / gchunks;
+    const int fmt = (want_f16 && nchains > 1 && (gchunks == 1 || gchunks == 2 || gchunks == 4)) ? 1 : 0;
     const int parts = fmt ? 2 : 3, elem = 2;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
-    // one chain per tile: the one-chain kernel (groups of warps, each NG tiles ahead); two chains: measured no gain
-    const int nbuf = nchains == 1 ? kOneRing : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", nchains <= 2 ? 4 : 2)));
+    // ring buffers per CTA: the one-chain kernel's groups of warps split NG tiles ahead; the chain kernel's converter
+    // warps run one tile ahead of the MMAs
+    const int nbuf = nchains == 1 ? kOneRing : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", 2)));
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
@@ -1164,17 +1301,15 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     a.nchunks = st->nchunks;
     a.gchunks = gchunks;
     a.ngroups = nchains;
-    // Slices of the next tile's split, one before each of the first chain waits.  Measured (tools/tc_probe.py, 2^27
-    // samples): one slice per chain is best for long bands (512 taps: 80.1 vs 76.3 Gsamp/s, 2048 taps: 28.7 vs 28.0),
-    // the whole split in one slice at the top of the tile (no accumulator register live, 4 positions per trip) for
-    // short ones (256 taps: 107 vs 104; one-chain interpolator tiles).
-    a.nslices = std::max(1, std::min(env_i("SGPU_FIR_TC_SLICES", a.nchunks >= 16 ? a.ngroups : 1), a.ngroups));
-    a.slice = (int)round_up(ceil_div((size_t)tile_plane, (size_t)a.nslices), kGroup);
+    a.nslices = 1;
+    a.slice = tile_plane;
     a.nbuf = nbuf;
     a.dbg = env_i("SGPU_FIR_TC_DBG", 0);
     a.vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (C == 1 || in_stride % 2 == 0);
-    a.rg = R == 128 ? 1 : 0;
-    a.sc_len = fmt ? (int)round_up(ceil_div((size_t)tile_plane, kGroup) + 2, 4) : 0;
+    const int group = kKC * gchunks;  // positions per block-floating scale group = the K extent of a chain
+    a.gsh = group == 128 ? 7 : (group == 64 ? 6 : 5);
+    a.rg = R == 128 ? 7 - a.gsh : 6 - a.gsh;  // log2(R / group)
+    a.sc_len = fmt ? (int)round_up(ceil_div((size_t)tile_plane, (size_t)group) + 2, 4) : 0;
     // F16x2: the band holds taps * 2^tap_shift; the register accumulators hold outputs * 2^tap_shift
     a.scale = fmt ? ldexpf(scale, -st->tap_shift) : scale;
     a.scale_im = fmt ? ldexpf(scale_im, -st->tap_shift) : scale_im;
@@ -1219,15 +1354,15 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     const cudaAccessPolicyWindow *wp = window ? &win : nullptr;
     int rc;
     if (a.ngroups == 1) {
-        rc = st->ctaps ? fir_tc_launch_fused<false, true, true>(st, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
-                       : fir_tc_launch_fused<false, false, true>(st, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
+        rc = st->ctaps ? fir_tc_launch(fir_tc_one_kernel<true>, st->fused_smem_set[0], kOneThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
+                       : fir_tc_launch(fir_tc_one_kernel<false>, st->fused_smem_set[1], kOneThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
     } else if (fmt) {
-        const size_t tab = (size_t)(nbuf + 1) * a.sc_len * sizeof(float);
-        rc = st->ctaps ? fir_tc_launch_fused<true, true, false>(st, a, grid, Fmt<true, true>::kSmemFixed + tab, wp, s)
-                       : fir_tc_launch_fused<true, false, false>(st, a, grid, Fmt<true, false>::kSmemFixed + tab, wp, s);
+        const size_t tab = (size_t)(nbuf + 2) * a.sc_len * sizeof(float);
+        rc = st->ctaps ? fir_tc_launch(fir_tc_chain_kernel<true, true>, st->fused_smem_set[2], kChainThreads, st->tmAh, st->tmRing, a, grid, Fmt<true, true>::kSmemFixed + tab, wp, s)
+                       : fir_tc_launch(fir_tc_chain_kernel<true, false>, st->fused_smem_set[3], kChainThreads, st->tmAh, st->tmRing, a, grid, Fmt<true, false>::kSmemFixed + tab, wp, s);
     } else {
-        rc = st->ctaps ? fir_tc_launch_fused<false, true, false>(st, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
-                       : fir_tc_launch_fused<false, false, false>(st, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
+        rc = st->ctaps ? fir_tc_launch(fir_tc_chain_kernel<false, true>, st->fused_smem_set[4], kChainThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
+                       : fir_tc_launch(fir_tc_chain_kernel<false, false>, st->fused_smem_set[5], kChainThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
     }
     if (rc) return rc;
     // fix-up of tiles that saw a non-finite sample + the new history tail, one launch
