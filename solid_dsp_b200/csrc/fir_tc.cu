@@ -921,6 +921,271 @@ fir_tc_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+
+// ---- FIR with the split samples RESIDENT in shared memory (real taps, F16x2, up to ~2000 taps) ------------------------
+// The chain kernel streams 32 KB of B per K chunk although chunk q + 4 of a tile is chunk q shifted by ONE block row:
+// 58 B of L2 -> shared-memory traffic per sample, and ncu shows the kernel pinned at the L2's 7.1 TB/s with the tensor
+// pipe 52 % busy.  Here the tile's samples are loaded ONCE, as four "strips" (one per residue class c = q mod 4 of the
+// K chunks): strip c = [128 + S rows][32 positions] of the tile's plane viewed as [rows][128], rows holding re and im
+// interleaved (row 2 r = re, 2 r + 1 = im of block row r; one 5-D TMA box per strip and part).  The B operand of chunk
+// q = 4 s + c is strip c from row 2 s on: the shared-memory descriptor's start address moves by s x 128 bytes (the
+// swizzle pattern is anchored to the 1024-byte aligned strip, base offset 0).  Only the 16 KB of A per chunk still
+// stream.  L2 -> shared memory: 135 KB + 320 KB per tile at 512 taps instead of 960 KB.
+//   Chains are two chunks of the same class pair, (4 s, 4 s + 1) for all s, then (4 s + 2, 4 s + 3) for all s, so that the
+// strips of classes 0 / 1 are free half a tile before those of 2 / 3 and the next tile's loads hide behind the MMAs.
+//   Accumulator column n = 2 b + z (z = 0 re, 1 im): a flush thread holds (re, im) of 64 blocks in adjacent registers.
+// Roles: warp 0 = A producer, warp 1 = MMA issuer, warp 2 = strip producer (warpgroup 0, 24 registers); warps 4-11 flush
+// (192); warps 12-15 convert (104), exactly as in the chain kernel.
+struct StripGeom {
+    int nrows;        // block rows per strip = 128 + ceil(Koff / 128)
+    int strip_bytes;  // 2 * nrows * 64, rounded up to 1024
+    int nsa;          // A stages
+    int nch0, nch1;   // chains of class pair 0 (chunks 4 s, 4 s + 1) and 1 (4 s + 2, 4 s + 3)
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kChainThreads, 1)
+fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
+                    const TcFusedArgs a, const StripGeom g) {
+    using F = Fmt<true, false>;
+    constexpr int kAStage = F::kA;  // 16 KB: f1 and f2 of 128 x 32 taps
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto strip = [&](int c, int part) { return base + (uint32_t)(2 * c + part) * (uint32_t)g.strip_bytes; };
+    const uint32_t abase = base + 8u * (uint32_t)g.strip_bytes;
+    auto stage_a = [&](int s) { return abase + (uint32_t)s * kAStage; };
+    const uint32_t bars = abase + (uint32_t)g.nsa * kAStage;
+    auto afull_bar = [&](int s) { return bars + 8u * s; };              // 4 slots
+    auto aempty_bar = [&](int s) { return bars + 8u * (4 + s); };       // 4 slots
+    auto tfull_bar = [&](int i) { return bars + 8u * (8 + i); };        // 2 slots
+    auto tempty_bar = [&](int i) { return bars + 8u * (10 + i); };      // 2 slots
+    auto ready_bar = [&](int i) { return bars + 8u * (12 + i); };       // 4 slots: a tile's planes are in ring buffer i
+    auto rfree_bar = [&](int i) { return bars + 8u * (16 + i); };       // 4 slots: ring buffer i has been read
+    auto sfull_bar = [&](int p) { return bars + 8u * (20 + p); };       // 2 slots: the strips of class pair p have landed
+    auto sfree_bar = [&](int p) { return bars + 8u * (22 + p); };       // 2 slots: every MMA that reads them is done
+    const uint32_t tmem_slot = bars + 8u * 24;
+    float *sc_tab = reinterpret_cast<float *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);  // nbuf + 2 slots, as in the chain kernel
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(afull_bar(s), 1);
+            mbar_init(aempty_bar(s), 1);
+            mbar_init(ready_bar(s), 4);  // the four converter warps
+            mbar_init(rfree_bar(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar(i), 1);
+            mbar_init(tempty_bar(i), 8);  // the eight flush warps
+            mbar_init(sfull_bar(i), 1);
+            mbar_init(sfree_bar(i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp < 4) {
+        reg_dec<kRegProducer>();
+        if (warp == 0 && lane == 0) {  // ===== A producer: the band's K chunks in the order the chains consume them =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int p = 0; p < 2; ++p) {
+                    const int nch = p ? g.nch1 : g.nch0;
+                    for (int sft = 0; sft < nch; ++sft) {
+                        const int q0 = 4 * sft + 2 * p, q1 = min(q0 + 2, a.nchunks);
+                        for (int q = q0; q < q1; ++q) {
+                            mbar_wait(aempty_bar(stage), phase ^ 1u);
+                            mbar_expect_tx(afull_bar(stage), kAStage);
+                            tma_load_3d(stage_a(stage), &tmA, afull_bar(stage), q * kKC, 0, 0);
+                            if (++stage == g.nsa) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (warp == 2 && lane == 0) {  // ===== strip producer: a tile's samples, once =====
+            int rb = 0;
+            uint32_t rphase = 0, fphase = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                mbar_wait(ready_bar(rb), rphase);  // this tile's planes are in the ring
+                const int buf = a.nbuf * (int)blockIdx.x + rb;
+                if (++rb == a.nbuf) {
+                    rb = 0;
+                    rphase ^= 1u;
+                }
+                for (int p = 0; p < 2; ++p) {
+                    if (!first) mbar_wait(sfree_bar(p), fphase);  // the previous tile's MMAs on these strips are done
+                    mbar_expect_tx(sfull_bar(p), 4u * (uint32_t)(2 * g.nrows * 64));
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                        for (int part = 0; part < 2; ++part)
+                            tma_load_5d(strip(2 * p + cc, part), &tmS, sfull_bar(p), (2 * p + cc) * kKC, 0, 0, part, buf);
+                }
+                if (!first) fphase ^= 1u;
+                first = false;
+            }
+        } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+            int stage = 0, rb = 0;
+            uint32_t phase = 0, use = 0, sphase = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int p = 0; p < 2; ++p) {
+                    mbar_wait(sfull_bar(p), sphase);
+                    if (p == 1) {  // both pairs have landed: the ring buffer may be rewritten
+                        mbar_arrive(rfree_bar(rb));
+                        if (++rb == a.nbuf) rb = 0;
+                    }
+                    const int nch = p ? g.nch1 : g.nch0;
+                    for (int sft = 0; sft < nch; ++sft, ++use) {
+                        const uint32_t acc = use & 1u;
+                        mbar_wait(tempty_bar(acc), ((use >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + acc * kBN;
+                        const int q0 = 4 * sft + 2 * p, q1 = min(q0 + 2, a.nchunks);
+                        for (int q = q0; q < q1; ++q) {
+                            mbar_wait(afull_bar(stage), phase);
+                            tc_fence_after();
+                            if (!(a.dbg & 1)) {
+                                const uint32_t sa = stage_a(stage);
+                                const uint32_t sb0 = strip(q & 3, 0) + (uint32_t)sft * 128u, sb1 = strip(q & 3, 1) + (uint32_t)sft * 128u;
+                                const uint64_t da0 = umma_desc_sw64(sa), da1 = umma_desc_sw64(sa + F::kAPart);
+                                const uint64_t db0 = umma_desc_sw64(sb0), db1 = umma_desc_sw64(sb1);
+#pragma unroll
+                                for (int kk = 0; kk < F::kKSteps; ++kk) {
+                                    const uint64_t off = (uint64_t)(kk * 32 >> 4);
+                                    umma_f16(d, da0 + off, db0 + off, F::kIdesc, (q != q0 || kk != 0) ? 1u : 0u);  // f1 h1
+                                    umma_f16(d, da0 + off, db1 + off, F::kIdesc, 1u);                              // f2 h1
+                                    umma_f16(d, da1 + off, db0 + off, F::kIdesc, 1u);                              // f1 h2
+                                }
+                            }
+                            umma_commit(aempty_bar(stage));
+                            if (++stage == g.nsa) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                        umma_commit(tfull_bar(acc));
+                    }
+                    umma_commit(sfree_bar(p));
+                }
+                sphase ^= 1u;
+            }
+        }
+    } else if (warp < 12) {  // ===== FLUSH =====
+        reg_inc<kRegFlush>();
+        const int ew = warp - 4;
+        const int wq = warp & 3;        // TMEM lane quarter this warp may read
+        const int half = ew >> 2;       // blocks [64 half, 64 half + 64) of the tile = accumulator columns [128 half, 128 half + 128)
+        const int m = wq * 32 + lane;   // output offset inside a block = TMEM lane
+        const uint64_t pol_stream = l2_policy_evict_first();
+        const int nsc = a.nbuf + 2;
+        uint32_t use = 0;
+        int fs = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            // scale group of (block b, class pair p, shift s): positions 128 (b + s) + 64 p + [0, 64) -> 2 (b + s) + p
+            const float *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + 2 * (64 * half);
+            float acc_[128];  // (re, im) of block 64 half + j at [2 j], [2 j + 1]
+#pragma unroll
+            for (int j = 0; j < 128; ++j) acc_[j] = 0.f;
+            for (int p = 0; p < 2; ++p) {
+                const int nch = p ? g.nch1 : g.nch0;
+                for (int sft = 0; sft < nch; ++sft, ++use) {
+                    const uint32_t acc = use & 1u;
+                    mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * 128;
+                    const float *__restrict__ scj = scf + 2 * sft + p;
+#pragma unroll
+                    for (int cg = 0; cg < 4; ++cg) {
+                        float v[32];
+                        tmem_ld16(taddr + cg * 32, v);
+                        tmem_ld16(taddr + cg * 32 + 16, v + 16);
+                        tmem_ld_wait();
+                        if (cg == 3) {  // the accumulator is in registers: hand it back before the arithmetic
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float mlt = scj[2 * (cg * 16 + j)];
+                            acc_[cg * 32 + 2 * j] = fmaf(v[2 * j], mlt, acc_[cg * 32 + 2 * j]);
+                            acc_[cg * 32 + 2 * j + 1] = fmaf(v[2 * j + 1], mlt, acc_[cg * 32 + 2 * j + 1]);
+                        }
+                    }
+                }
+            }
+            const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
+            const long long n0 = (long long)tt * kTileSamples + (long long)(half * 64) * kBM + m;
+            float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0;
+            if ((long long)(tt + 1) * kTileSamples <= a.n_out) {  // interior tile: constant offsets, no guards
+#pragma unroll
+                for (int j = 0; j < 64; ++j) st_hint_v2(yp + j * kBM, acc_[2 * j] * a.scale, acc_[2 * j + 1] * a.scale, pol_stream);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j)
+                    if (n0 + (long long)j * kBM < a.n_out)  // fir/mod.rs:211
+                        st_hint_v2(yp + j * kBM, acc_[2 * j] * a.scale, acc_[2 * j + 1] * a.scale, pol_stream);
+            }
+            if (++fs == nsc) fs = 0;
+        }
+    } else {  // ===== CONVERT: as in the chain kernel =====
+        reg_dec<kRegConvert>();
+        const int et = (warp - 12) * 32 + lane;
+        const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
+        uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(a.nbuf * blockIdx.x) * buf_bytes;
+        const uint64_t pol_ring = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const int nsc = a.nbuf + 2;
+        int wb = 0, ws = 0;
+        uint32_t fphase = 0;
+        bool wrapped = false;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            if (wrapped) mbar_wait(rfree_bar(wb), fphase);
+            const bool bad = tc_split_f16<2, 128>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0,
+                                                  a.tile_plane, et, pol_ring, pol_stream);
+            if (bad) a.flags[tile] = 1u;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready_bar(wb));
+            if (++wb == a.nbuf) {
+                wb = 0;
+                if (wrapped) fphase ^= 1u;
+                wrapped = true;
+            }
+            if (++ws == nsc) ws = 0;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Behind the tensor kernel, same stream.  Blocks [0, fix_blocks): every block scans its share of the tile flags and
 // recomputes the flagged tiles the way the reference does -- one sequential f32 dot product per output, newest sample
@@ -1062,6 +1327,8 @@ struct FirTcState {
     void *d_ring = nullptr;
     int ring_ctas = 0, tile_plane = 0, ring_fmt = -1, ring_nbuf = 0;
     CUtensorMap tmRing;
+    CUtensorMap tmStrip;         // the same ring as 5-D boxes {32 positions, re / im, block rows, part, buffer} for the strip kernel
+    int strip_rows = 0;
     bool fused_smem_set[8] = {false, false, false, false, false, false, false, false};
     bool persist_set = false;    // this handle holds a reference on its device's persisting-L2 carve-out
     bool ctaps = false;          // complex taps: the bands hold the Gr parts, then the Gi parts
@@ -1232,13 +1499,24 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     gchunks = std::max(1, std::min(gchunks, st->nchunks));
     if (st->nchunks > 3 && want_f16 && gchunks != 1 && gchunks != 2 && !(gchunks == 4 && R == 128)) gchunks = 2;
     if (st->nchunks > 3 && st->nchunks <= gchunks) gchunks = (st->nchunks + 1) / 2;  // the chain kernel wants >= 2 chains
-    const int nchains = (st->nchunks + gchunks - 1) / gchunks;
+    // Strip kernel (real-tap FIR, samples resident in shared memory): chains of two chunks in class-pair order
+    StripGeom sg{};
+    sg.nrows = 128 + (int)ceil_div((size_t)st->Koff, 128);
+    sg.strip_bytes = (int)round_up((size_t)2 * sg.nrows * 64, 1024);
+    sg.nch0 = (st->nchunks + 3) / 4;
+    sg.nch1 = (st->nchunks - 2 + 3) / 4;
+    const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
+    const size_t strip_tab = (size_t)(2 + 2) * round_up(ceil_div((size_t)tile_plane, 64) + 2, 4) * sizeof(float);
+    for (sg.nsa = 4; sg.nsa >= 2; --sg.nsa)
+        if ((size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 1024 + 256 + strip_tab <= (size_t)227 * 1024) break;
+    const bool use_strip = want_f16 && !st->ctaps && R == 128 && sg.nsa >= 2 && sg.nrows <= 256 && env_i("SGPU_FIR_TC_STRIP", 1) != 0;
+    if (use_strip) gchunks = 2;
+    const int nchains = use_strip ? sg.nch0 + sg.nch1 : (st->nchunks + gchunks - 1) / gchunks;
     const int fmt = (want_f16 && nchains > 1 && (gchunks == 1 || gchunks == 2 || gchunks == 4)) ? 1 : 0;
     const int parts = fmt ? 2 : 3, elem = 2;
-    const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
     // ring buffers per CTA: the one-chain kernel's groups of warps split NG tiles ahead; the chain kernel's converter
     // warps run one tile ahead of the MMAs
-    const int nbuf = nchains == 1 ? kOneRing : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", 2)));
+    const int nbuf = nchains == 1 ? kOneRing : (use_strip ? 2 : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", 2))));
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
@@ -1263,6 +1541,21 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed: %d", (int)r);
+        st->strip_rows = 0;
+    }
+    if (use_strip && st->strip_rows != sg.nrows) {
+        // the same ring seen as {position in row, re / im, block row, part, buffer}: one box = one strip of one part with re
+        // and im interleaved row by row
+        const cuuint64_t gdim[5] = {(cuuint64_t)R, 2, (cuuint64_t)(tile_plane / R), (cuuint64_t)parts, (cuuint64_t)(nbuf * sm_count)};
+        const cuuint64_t gstr[4] = {(cuuint64_t)tile_plane * elem, (cuuint64_t)R * elem, (cuuint64_t)tile_plane * elem * 2,
+                                    (cuuint64_t)tile_plane * elem * 2 * parts};
+        const cuuint32_t box[5] = {kKC, 2, (cuuint32_t)sg.nrows, 1, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = enc(&st->tmStrip, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, st->d_ring, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(strips) failed: %d", (int)r);
+        st->strip_rows = sg.nrows;
     }
     const long long tile_in = (long long)kNB * R;
     const long long tiles_per_ch = (long long)ceil_div((size_t)n_in, (size_t)tile_in);
@@ -1353,7 +1646,29 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     }
     const cudaAccessPolicyWindow *wp = window ? &win : nullptr;
     int rc;
-    if (a.ngroups == 1) {
+    if (use_strip) {
+        bool &set = st->fused_smem_set[6];
+        if (!set) {
+            SGPU_CUDA(cudaFuncSetAttribute(fir_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            set = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)kChainThreads);
+        cfg.dynamicSmemBytes = (size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 1024 + 256 + (size_t)(nbuf + 2) * a.sc_len * sizeof(float);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        if (wp) {
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow = *wp;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
+        SGPU_CUDA(cudaLaunchKernelEx(&cfg, fir_tc_strip_kernel, st->tmAh, st->tmStrip, a, sg));
+        SGPU_LAUNCH_CHECK();
+        count_launch();
+        rc = SGPU_OK;
+    } else if (a.ngroups == 1) {
         rc = st->ctaps ? fir_tc_launch(fir_tc_one_kernel<true>, st->fused_smem_set[0], kOneThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, true>::kSmemFixed, wp, s)
                        : fir_tc_launch(fir_tc_one_kernel<false>, st->fused_smem_set[1], kOneThreads, st->tmA16, st->tmRing, a, grid, Fmt<false, false>::kSmemFixed, wp, s);
     } else if (fmt) {
