@@ -82,6 +82,10 @@ typedef struct sgpu_interp sgpu_interp; /* InterpolatingFIRFilter (+ its PolyPha
 typedef struct sgpu_iir sgpu_iir;       /* IIRFilter / Decimating- / InterpolatingIIRFilter   */
 typedef struct sgpu_dot sgpu_dot;       /* DotProduct                              */
 typedef struct sgpu_autocorr sgpu_autocorr; /* AutoCorrelator                      */
+typedef struct sgpu_nco sgpu_nco;       /* NCO (one phase accumulator per channel) */
+typedef struct sgpu_ddc sgpu_ddc;       /* NCO mix-down -> DecimatingFIRFilter      */
+
+#define SGPU_ALL_CHANNELS ((size_t)-1)
 
 /* ---- library ------------------------------------------------------------------------ */
 int sgpu_abi_version(void);
@@ -282,6 +286,47 @@ int sgpu_dot_coefficients(const sgpu_dot *d, double *out); /* dot_product/mod.rs
  * length n_x each (vector v at x + v*x_stride); result[v] cf32. */
 int sgpu_dot_execute(sgpu_dot *d, const float *x, size_t n_x, size_t x_stride, size_t n_vec,
                      float *result, sgpu_mem mem, void *stream);
+
+/* ---- NCO (nco/mod.rs) and the digital down-converter ----------------------------------
+ * the per-sample step next to the decimator.  An sgpu_nco is C reference NCO
+ * objects (nco/mod.rs:26-33): a 32-bit phase `theta`, a 32-bit step `delta_theta`, the
+ * 1024-entry sine table (:36-41; rounded to f32 on the device).  `channel` is an index or
+ * SGPU_ALL_CHANNELS.  The reference's mix_up_block / mix_down_block (:153-172) index an empty
+ * Vec and panic; sgpu_nco_mix_block is the loop they were written to be: y[i] = mix(x[i]); step().
+ * An sgpu_ddc is that loop (mix_down) feeding a DecimatingFIRFilter (fir/decim.rs:221-256), one
+ * pair per channel; on the hot shapes (M in {2, 4, 8}, real taps) the mixing happens inside the
+ * decimator's tile loader and the mixed stream never reaches HBM (sgpu_ddc_last_fused). */
+int sgpu_nco_create(size_t n_channels, sgpu_nco **out);                           /* NCO::new, :36-50 */
+int sgpu_nco_destroy(sgpu_nco *n);
+int sgpu_nco_clone(const sgpu_nco *n, sgpu_nco **out);
+size_t sgpu_nco_channels(const sgpu_nco *n);
+int sgpu_nco_reset(sgpu_nco *n);                                                  /* :53-56 */
+int sgpu_nco_set_frequency(sgpu_nco *n, size_t channel, double delta_theta);      /* :59-61 */
+int sgpu_nco_adjust_frequency(sgpu_nco *n, size_t channel, double dt);            /* :64-66 */
+int sgpu_nco_set_phase(sgpu_nco *n, size_t channel, double phi);                  /* :79-81 */
+int sgpu_nco_adjust_phase(sgpu_nco *n, size_t channel, double delta_phi);         /* :84-86 */
+int sgpu_nco_step(sgpu_nco *n, uint64_t count);                                   /* :93-96, `count` times */
+/* raw accumulator words (theta as of the next sample) */
+int sgpu_nco_get(const sgpu_nco *n, size_t channel, uint32_t *theta, uint32_t *delta_theta);
+int sgpu_nco_set(sgpu_nco *n, size_t channel, uint32_t theta, uint32_t delta_theta);
+uint32_t sgpu_nco_constrain(double theta);                                        /* :176-188 */
+/* up != 0: mix_up (:141-145), else mix_down (:147-151); every channel's NCO steps n_in times */
+int sgpu_nco_mix_block(sgpu_nco *n, int up, const float *in, size_t n_in, size_t in_stride,
+                       float *out, size_t out_stride, sgpu_mem mem, void *stream);
+
+int sgpu_ddc_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels,
+                    double scale_re, double scale_im, size_t decimation, sgpu_ddc **out);
+int sgpu_ddc_destroy(sgpu_ddc *d);
+int sgpu_ddc_clone(const sgpu_ddc *d, sgpu_ddc **out);
+sgpu_fir *sgpu_ddc_filter(sgpu_ddc *d); /* the decimator: scale, taps, state through sgpu_fir_* (its history holds MIXED samples) */
+sgpu_nco *sgpu_ddc_nco(sgpu_ddc *d);    /* the oscillators: frequency / phase through sgpu_nco_* */
+size_t sgpu_ddc_out_len(const sgpu_ddc *d, size_t n_in);
+int sgpu_ddc_execute_block(sgpu_ddc *d, const float *in, size_t n_in, size_t in_stride, float *out,
+                           size_t out_stride, size_t *n_out, sgpu_mem mem, void *stream);
+int sgpu_ddc_write(sgpu_ddc *d, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem,
+                   void *stream);        /* mixed, pushed, no output (decim.rs:136-139) */
+int sgpu_ddc_reset(sgpu_ddc *d);         /* NCO::reset + the decimator's window and counter */
+int sgpu_ddc_last_fused(const sgpu_ddc *d); /* 1: the last call mixed inside the decimator kernel */
 
 /* ---- sharding helpers (pure host arithmetic; no collective) --------------------------
  * Channels: contiguous ranges, remainder spread over the first ranks.

@@ -121,6 +121,20 @@ def lib(native: bool = False):
     sig("so_filter_autocorrelation", C.c_double, c_dp, c_size, C.c_ssize_t)
     sig("so_filter_crosscorrelation", C.c_double, c_dp, c_size, c_dp, c_size, C.c_ssize_t)
     sig("so_pll_active_lag", C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp)
+    sig("so_nco_constrain", C.c_uint32, C.c_double)
+    sig("so_nco_new", vp)
+    sig("so_nco_free", None, vp)
+    sig("so_nco_reset", None, vp)
+    for nm in ("set_frequency", "adjust_frequency", "set_phase", "adjust_phase"):
+        sig("so_nco_" + nm, None, vp, C.c_double)
+    sig("so_nco_step", None, vp)
+    sig("so_nco_set_raw", None, vp, C.c_uint32, C.c_uint32)
+    sig("so_nco_theta", C.c_uint32, vp)
+    sig("so_nco_delta_theta", C.c_uint32, vp)
+    sig("so_nco_sin", C.c_double, vp)
+    sig("so_nco_cos", C.c_double, vp)
+    sig("so_nco_mix", None, vp, C.c_int, C.c_double, C.c_double, c_dp)
+    sig("so_nco_mix_block", None, vp, C.c_int, c_dp, c_size, c_dp)
     sig("so_run_units", c_size, C.c_int, c_dp, c_size, C.c_int, C.c_double, C.c_double, C.c_int,
         c_size, c_dp, c_dp, c_size, c_dp, c_size, c_size, c_size, c_dp, c_size, c_size, C.c_int)
     _libs[native] = L
@@ -465,6 +479,116 @@ class AutoCorrelator:
 
 
 # ----------------------------------------------------------------------------- closed forms
+class NCO:
+    """solid::nco::NCO (nco/mod.rs), structural restatement.  Parity unpinned: the reference has no NCO golden."""
+
+    def __init__(self, native=False):
+        self._L = lib(native)
+        self._h = self._L.so_nco_new()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.so_nco_free(self._h)
+            self._h = None
+
+    def reset(self):
+        self._L.so_nco_reset(self._h)
+
+    def set_frequency(self, dt):
+        self._L.so_nco_set_frequency(self._h, float(dt))
+
+    def adjust_frequency(self, dt):
+        self._L.so_nco_adjust_frequency(self._h, float(dt))
+
+    def set_phase(self, phi):
+        self._L.so_nco_set_phase(self._h, float(phi))
+
+    def adjust_phase(self, dphi):
+        self._L.so_nco_adjust_phase(self._h, float(dphi))
+
+    def set_raw(self, theta, delta_theta):
+        self._L.so_nco_set_raw(self._h, theta & 0xFFFFFFFF, delta_theta & 0xFFFFFFFF)
+
+    def raw(self):
+        return int(self._L.so_nco_theta(self._h)), int(self._L.so_nco_delta_theta(self._h))
+
+    def step(self):
+        self._L.so_nco_step(self._h)
+
+    def sin(self):
+        return float(self._L.so_nco_sin(self._h))
+
+    def cos(self):
+        return float(self._L.so_nco_cos(self._h))
+
+    def sincos(self):
+        return self.sin(), self.cos()
+
+    def complex_exponential(self):
+        return complex(self.cos(), self.sin())
+
+    def _mix(self, up, sample):
+        out = np.zeros(2)
+        z = complex(sample)
+        self._L.so_nco_mix(self._h, up, z.real, z.imag, _p(out))
+        return complex(out[0], out[1])
+
+    def mix_up(self, sample):
+        return self._mix(1, sample)
+
+    def mix_down(self, sample):
+        return self._mix(0, sample)
+
+    def _mix_block(self, up, samples):
+        x, xv = _cx(samples)
+        out = np.zeros_like(x)
+        self._L.so_nco_mix_block(self._h, up, _p(xv), x.size, _p(out.view(np.float64)))
+        return out
+
+    def mix_up_block(self, samples):
+        """y[i] = mix_up(x[i]); step() -- the loop nco/mod.rs:153-161 was written to be."""
+        return self._mix_block(1, samples)
+
+    def mix_down_block(self, samples):
+        return self._mix_block(0, samples)
+
+
+def nco_constrain(theta):
+    return int(lib().so_nco_constrain(float(theta)))
+
+
+def nco_mix_down_block(x, frequency=0.0, phase=0.0, n_threads=1, raw=None, up=False):
+    """Rows of x through independent NCOs (all set to `frequency` / `phase`, or to raw = (theta, delta) words per row),
+    mix_down (or mix_up) + step per sample.  Returns complex128 of x's shape."""
+    x2 = np.atleast_2d(_cx(x)[0])
+    out = np.zeros_like(x2)
+
+    def one(i):
+        n = NCO()
+        if raw is not None:
+            th, dl = raw[i] if np.ndim(raw) == 2 else raw
+            n.set_raw(int(th), int(dl))
+        else:
+            n.set_frequency(frequency)
+            n.set_phase(phase)
+        out[i] = n._mix_block(1 if up else 0, x2[i])
+
+    if n_threads > 1 and x2.shape[0] > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(n_threads) as ex:
+            list(ex.map(one, range(x2.shape[0])))
+    else:
+        for i in range(x2.shape[0]):
+            one(i)
+    return out.reshape(np.shape(x)) if np.ndim(x) == 1 else out
+
+
+def ddc_fast(coefs, x, scale, decimation, frequency=0.0, phase=0.0, count0=0, hist=None, raw=None):
+    """NCO mix-down (structural) feeding the closed-form decimator: the checker for the fused DDC kernel."""
+    mixed = nco_mix_down_block(x, frequency, phase, raw=raw)
+    return fir_fast(coefs, mixed, scale, decimation, count0, hist)
+
+
 def autocorr_fast(window_size, delay, x, hist=None):
     """out[n] = sum_{i < W-d} x[n-i] conj(x[n-d-i]); hist = samples preceding x[0], oldest first"""
     x, xv = _cx(x)

@@ -827,6 +827,63 @@ SO_API int so_pll_active_lag(double w, double zeta, double k, double *num, doubl
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* NCO -- nco/mod.rs.  PARITY UNPINNED: the reference holds no doc-test or golden for the   */
+/* NCO (nco/mod.rs has none; main.rs:29-36 only drives sincos/step), so this follows the    */
+/* source literally.  mix_up_block / mix_down_block (:153-172) index an empty Vec and panic  */
+/* in the reference; so_nco_mix_block is the loop they were written to be.                   */
+typedef struct {
+    double table[1024];
+    uint32_t theta, delta_theta;
+} so_nco;
+
+/* nco/mod.rs:176-188 */
+SO_API uint32_t so_nco_constrain(double theta) {
+    double t = theta / (2.0 * 3.14159265358979323846264338327950288);
+    double ip;
+    double frac = modf(t, &ip);                 /* f64::fract */
+    if (frac < 0.0) frac += 1.0;
+    double v = frac * (double)0xffffffffu;      /* `0xffffffffu32 as f64` binds tighter than `*` */
+    if (!(v > 0.0)) return 0;                   /* Rust `as u32` saturates; NaN -> 0 */
+    if (v >= 4294967295.0) return 0xffffffffu;
+    return (uint32_t)v;
+}
+SO_API so_nco *so_nco_new(void) {              /* :36-50 */
+    so_nco *n = (so_nco *)calloc(1, sizeof(so_nco));
+    if (!n) return NULL;
+    for (int i = 0; i < 1024; i++)
+        n->table[i] = sin(2.0 * 3.14159265358979323846264338327950288 * (double)i / 1024.0);
+    return n;
+}
+SO_API void so_nco_free(so_nco *n) { free(n); }
+SO_API void so_nco_reset(so_nco *n) { n->theta = 0; n->delta_theta = 0; }                                  /* :53-56 */
+SO_API void so_nco_set_frequency(so_nco *n, double dt) { n->delta_theta = so_nco_constrain(dt); }         /* :59-61 */
+SO_API void so_nco_adjust_frequency(so_nco *n, double dt) { n->delta_theta += so_nco_constrain(dt); }     /* :64-66 */
+SO_API void so_nco_set_phase(so_nco *n, double phi) { n->theta = so_nco_constrain(phi); }                 /* :79-81 */
+SO_API void so_nco_adjust_phase(so_nco *n, double dphi) { n->theta += so_nco_constrain(dphi); }           /* :84-86 */
+SO_API void so_nco_step(so_nco *n) { n->theta += n->delta_theta; }                                        /* :93-96 wrapping_add */
+SO_API void so_nco_set_raw(so_nco *n, uint32_t theta, uint32_t delta) { n->theta = theta; n->delta_theta = delta; }
+SO_API uint32_t so_nco_theta(const so_nco *n) { return n->theta; }
+SO_API uint32_t so_nco_delta_theta(const so_nco *n) { return n->delta_theta; }
+static inline size_t nco_index(const so_nco *n) {                                                          /* :98-101 */
+    return (size_t)(((uint32_t)(n->theta + (1u << 21)) >> 22) & 0x3ff);
+}
+SO_API double so_nco_sin(const so_nco *n) { return n->table[nco_index(n)]; }                               /* :103-106 */
+SO_API double so_nco_cos(const so_nco *n) { return n->table[(nco_index(n) + 256) & 0x3ff]; }               /* :108-112 */
+SO_API void so_nco_mix(const so_nco *n, int up, double re, double im, double *out2) {                      /* :141-151 */
+    cplx ph = { so_nco_cos(n), so_nco_sin(n) };   /* complex_exponential, :119-121 */
+    if (!up) ph.im = -ph.im;                      /* .conj() */
+    cplx x = { re, im };
+    cplx y = c_mul(ph, x);
+    out2[0] = y.re; out2[1] = y.im;
+}
+SO_API void so_nco_mix_block(so_nco *n, int up, const double *x, size_t len, double *out) {
+    for (size_t i = 0; i < len; i++) {
+        so_nco_mix(n, up, x[2 * i], x[2 * i + 1], out + 2 * i);
+        so_nco_step(n);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Threaded drivers for the timed baseline: one independent filter OBJECT per channel (or
  * per stream segment), one pthread per worker -- what a user of the (single-threaded,
  * !Send) reference could do with its public API by giving every thread its own object.  */

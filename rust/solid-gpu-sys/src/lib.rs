@@ -41,6 +41,9 @@ pub const SGPU_IIR_INTERPOLATING: c_int = 2;
 #[repr(C)] pub struct sgpu_iir { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_dot { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_autocorr { _private: [u8; 0] }
+#[repr(C)] pub struct sgpu_nco { _private: [u8; 0] }
+#[repr(C)] pub struct sgpu_ddc { _private: [u8; 0] }
+pub const SGPU_ALL_CHANNELS: size_t = usize::MAX;
 
 extern "C" {
     pub fn sgpu_abi_version() -> c_int;
@@ -150,6 +153,38 @@ extern "C" {
     pub fn sgpu_dot_coefficients(d: *const sgpu_dot, out: *mut c_double) -> c_int;
     pub fn sgpu_dot_execute(d: *mut sgpu_dot, x: *const c_float, n_x: size_t, x_stride: size_t, n_vec: size_t,
                             result: *mut c_float, mem: c_int, stream: *mut c_void) -> c_int;
+
+    pub fn sgpu_nco_create(n_channels: size_t, out: *mut *mut sgpu_nco) -> c_int;
+    pub fn sgpu_nco_destroy(n: *mut sgpu_nco) -> c_int;
+    pub fn sgpu_nco_clone(n: *const sgpu_nco, out: *mut *mut sgpu_nco) -> c_int;
+    pub fn sgpu_nco_channels(n: *const sgpu_nco) -> size_t;
+    pub fn sgpu_nco_reset(n: *mut sgpu_nco) -> c_int;
+    pub fn sgpu_nco_set_frequency(n: *mut sgpu_nco, channel: size_t, delta_theta: c_double) -> c_int;
+    pub fn sgpu_nco_adjust_frequency(n: *mut sgpu_nco, channel: size_t, dt: c_double) -> c_int;
+    pub fn sgpu_nco_set_phase(n: *mut sgpu_nco, channel: size_t, phi: c_double) -> c_int;
+    pub fn sgpu_nco_adjust_phase(n: *mut sgpu_nco, channel: size_t, delta_phi: c_double) -> c_int;
+    pub fn sgpu_nco_step(n: *mut sgpu_nco, count: u64) -> c_int;
+    pub fn sgpu_nco_get(n: *const sgpu_nco, channel: size_t, theta: *mut u32, delta_theta: *mut u32) -> c_int;
+    pub fn sgpu_nco_set(n: *mut sgpu_nco, channel: size_t, theta: u32, delta_theta: u32) -> c_int;
+    pub fn sgpu_nco_constrain(theta: c_double) -> u32;
+    pub fn sgpu_nco_mix_block(n: *mut sgpu_nco, up: c_int, input: *const c_float, n_in: size_t, in_stride: size_t,
+                              out: *mut c_float, out_stride: size_t, mem: c_int, stream: *mut c_void) -> c_int;
+
+    pub fn sgpu_ddc_create(taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
+                           scale_re: c_double, scale_im: c_double, decimation: size_t,
+                           out: *mut *mut sgpu_ddc) -> c_int;
+    pub fn sgpu_ddc_destroy(d: *mut sgpu_ddc) -> c_int;
+    pub fn sgpu_ddc_clone(d: *const sgpu_ddc, out: *mut *mut sgpu_ddc) -> c_int;
+    pub fn sgpu_ddc_filter(d: *mut sgpu_ddc) -> *mut sgpu_fir;
+    pub fn sgpu_ddc_nco(d: *mut sgpu_ddc) -> *mut sgpu_nco;
+    pub fn sgpu_ddc_out_len(d: *const sgpu_ddc, n_in: size_t) -> size_t;
+    pub fn sgpu_ddc_execute_block(d: *mut sgpu_ddc, input: *const c_float, n_in: size_t, in_stride: size_t,
+                                  out: *mut c_float, out_stride: size_t, n_out: *mut size_t,
+                                  mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn sgpu_ddc_write(d: *mut sgpu_ddc, input: *const c_float, n_in: size_t, in_stride: size_t,
+                          mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn sgpu_ddc_reset(d: *mut sgpu_ddc) -> c_int;
+    pub fn sgpu_ddc_last_fused(d: *const sgpu_ddc) -> c_int;
 
     pub fn sgpu_shard_channels(n_channels: size_t, world: c_int, rank: c_int, first: *mut size_t,
                                count: *mut size_t) -> c_int;

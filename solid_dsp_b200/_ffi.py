@@ -49,6 +49,7 @@ TAPS_REAL, TAPS_COMPLEX = 0, 1
 FORWARD, REVERSE = 0, 1
 IIR_NORMAL, IIR_SECOND_ORDER = 0, 1
 IIR_PLAIN, IIR_DECIMATING, IIR_INTERPOLATING = 0, 1, 2
+ALL_CHANNELS = (1 << (8 * C.sizeof(C.c_size_t))) - 1
 
 # name -> (restype, argtypes); must cover every prototype in the header (tests check this)
 PROTOTYPES = {
@@ -129,6 +130,30 @@ PROTOTYPES = {
     "sgpu_dot_len": (c_size, [vp]),
     "sgpu_dot_coefficients": (C.c_int, [vp, c_dp]),
     "sgpu_dot_execute": (C.c_int, [vp, vp, c_size, c_size, c_size, vp, C.c_int, vp]),
+    "sgpu_nco_create": (C.c_int, [c_size, vpp]),
+    "sgpu_nco_destroy": (C.c_int, [vp]),
+    "sgpu_nco_clone": (C.c_int, [vp, vpp]),
+    "sgpu_nco_channels": (c_size, [vp]),
+    "sgpu_nco_reset": (C.c_int, [vp]),
+    "sgpu_nco_set_frequency": (C.c_int, [vp, c_size, C.c_double]),
+    "sgpu_nco_adjust_frequency": (C.c_int, [vp, c_size, C.c_double]),
+    "sgpu_nco_set_phase": (C.c_int, [vp, c_size, C.c_double]),
+    "sgpu_nco_adjust_phase": (C.c_int, [vp, c_size, C.c_double]),
+    "sgpu_nco_step": (C.c_int, [vp, C.c_uint64]),
+    "sgpu_nco_get": (C.c_int, [vp, c_size, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "sgpu_nco_set": (C.c_int, [vp, c_size, C.c_uint32, C.c_uint32]),
+    "sgpu_nco_constrain": (C.c_uint32, [C.c_double]),
+    "sgpu_nco_mix_block": (C.c_int, [vp, C.c_int, vp, c_size, c_size, vp, c_size, C.c_int, vp]),
+    "sgpu_ddc_create": (C.c_int, [c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, c_size, vpp]),
+    "sgpu_ddc_destroy": (C.c_int, [vp]),
+    "sgpu_ddc_clone": (C.c_int, [vp, vpp]),
+    "sgpu_ddc_filter": (vp, [vp]),
+    "sgpu_ddc_nco": (vp, [vp]),
+    "sgpu_ddc_out_len": (c_size, [vp, c_size]),
+    "sgpu_ddc_execute_block": (C.c_int, [vp, vp, c_size, c_size, vp, c_size, c_sizep, C.c_int, vp]),
+    "sgpu_ddc_write": (C.c_int, [vp, vp, c_size, c_size, C.c_int, vp]),
+    "sgpu_ddc_reset": (C.c_int, [vp]),
+    "sgpu_ddc_last_fused": (C.c_int, [vp]),
     "sgpu_shard_channels": (C.c_int, [c_size, C.c_int, C.c_int, c_sizep, c_sizep]),
     "sgpu_shard_stream": (C.c_int, [c_size, c_size, C.c_int, C.c_int, c_sizep, c_sizep]),
 }

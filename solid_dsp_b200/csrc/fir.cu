@@ -8,6 +8,7 @@
 //   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
 #include "fir_core.cuh"
 #include "fir_tc.cuh"
+#include "nco.cuh"
 #include "sgpu_common.cuh"
 
 namespace sgpu {
@@ -32,11 +33,19 @@ struct FirArgs {
     int RS;                 // row stride of a plane in float4, odd
     int vec_in, vec_out;    // 16-byte vector access allowed
     float scale_re, scale_im;
-    // NCO mix-down fused in front of the filter (DDC, nco/mod.rs:141-172): sample i of this call is multiplied by
-    // conj(phasor(nco_theta + i * nco_delta)) before the filter sees it; lut = 1024 x (cos, sin), NULL = no mixing
-    unsigned nco_theta, nco_delta;
+    // NCO mix-down fused in front of the filter (DDC, nco/mod.rs:141-172): sample i of this call on channel c is
+    // multiplied by conj(phasor(theta0[c] + (nco_pos + i) * delta[c])) before the filter sees it (32-bit wrapping phase,
+    // nco/mod.rs:93-96).  nco = [C][2] words (theta0, delta_theta); lut = 1024 x (cos, sin); NULL = no mixing
+    const unsigned *nco;
+    unsigned nco_pos;
     const float2 *lut;
 };
+
+// phase of sample 0 of this call and the phase step, channel ch
+__device__ __forceinline__ void nco_channel(const FirArgs &a, const int ch, unsigned &theta, unsigned &delta) {
+    delta = a.nco[2 * ch + 1];
+    theta = a.nco[2 * ch] + a.nco_pos * delta;
+}
 
 // NCO phasor of a 32-bit phase (nco/mod.rs:98-114): table index = ((theta + 2^21) >> 22) & 1023, sin = table[index],
 // cos = table[(index + 256) & 1023]; the table here holds the (cos, sin) pair per index
@@ -74,12 +83,14 @@ __device__ __forceinline__ void hist_tail_update(const FirArgs &a, const int ch,
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     const float2 *__restrict__ ho = a.hist + (long long)ch * H;
     float2 *__restrict__ hn = a.hist_new + (long long)ch * H;
+    unsigned nco_theta = 0, nco_delta = 0;
+    if (a.lut) nco_channel(a, ch, nco_theta, nco_delta);
     for (int i = tid; i < H; i += nthr) {
         const long long s = a.n_in - H + i;
         float2 v;
         if (s >= 0) {
             v = x[s];
-            if (a.lut) v = nco_mix_down(v, a.nco_theta + (unsigned)s * a.nco_delta, a.lut);  // the history holds MIXED samples
+            if (a.lut) v = nco_mix_down(v, nco_theta + (unsigned)s * nco_delta, a.lut);  // the history holds MIXED samples
         } else {
             const long long h = (long long)H + s;
             v = h >= 0 ? ho[h] : make_float2(0.f, 0.f);
@@ -415,11 +426,7 @@ __global__ void __launch_bounds__(128) fir_direct_kernel(const FirArgs a) {
     const float *__restrict__ img = a.taps + (long long)ch * a.tap_stride;
     const int rs = a.Qpad * TW + kTapSkew;
     float yr = 0.f, yi = 0.f;
-    auto fetch = [&](const long long i) {
-        float2 w = fetch_sample(x, hist, i, a.n_in, a.T);
-        if (a.lut && i >= 0 && i < a.n_in) w = nco_mix_down(w, a.nco_theta + (unsigned)i * a.nco_delta, a.lut);
-        return w;
-    };
+    auto fetch = [&](const long long i) { return fetch_sample(x, hist, i, a.n_in, a.T); };
     auto mac = [&](const float *g, const float2 w) {
         if constexpr (CT) {  // (gr + j gi)(wx + j wy)
             yr += g[0] * w.x - g[1] * w.y;
@@ -511,6 +518,14 @@ struct sgpu_fir {
     FirTcState *tc = nullptr;     // tensor-core path for long filters (fir_tc.cu), built on first use
     bool tc_tried = false;
     int last_path = 0;            // 0 = FFMA2 kernels, 1 = tensor cores
+    // NCO mix-down in front of the filter (set by an sgpu_ddc around its calls): [C][2] device words (theta0, delta),
+    // the 1024 x (cos, sin) table and the stream position of the call's first sample
+    const unsigned *nco_tab = nullptr;
+    const float2 *nco_lut = nullptr;
+    unsigned nco_pos = 0;
+    float2 *d_mix = nullptr;      // pre-mixed input of the shapes without a fused kernel
+    size_t mix_cap = 0;           // samples
+    int last_mix_fused = 0;
 };
 
 static int fir_R(const sgpu_fir *f) { return f->complex_taps ? 8 : kR; }
@@ -605,6 +620,7 @@ SGPU_EXPORT int sgpu_fir_destroy(sgpu_fir *f) {
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     fir_tc_destroy(f->tc);
+    if (f->d_mix) cudaFree(f->d_mix);
     f->stage.release();
     f->pipe.release();
     delete f;
@@ -676,6 +692,39 @@ int enqueue_hist_update(const float2 *d_in, long long in_stride, long long n_in,
 int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
                      long long out_stride, long long n_out, cudaStream_t s);
 
+constexpr size_t kNcoLutBytes = 1024 * sizeof(float2);
+
+// Launch geometry of the warp-private decimator (fir_walk.cuh) for this handle; false when that kernel does not serve it.
+struct DwarpGeom {
+    int PS, NW, RS;
+    bool one;
+    size_t stage_b, taps_b;
+};
+bool dwarp_geometry(const sgpu_fir *f, DwarpGeom &g) {
+    if (!((f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32) && f->packed && !f->complex_taps &&
+          env_int("SGPU_DEC_WARP", 1)))
+        return false;
+    int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
+    if (PS != 1 && PS != 2 && PS != 4) PS = 4;
+    if (PS > (int)f->M) PS = (int)f->M;
+    g.one = f->Qpad == kR;  // sub-filters of <= 16 taps: single tap chunk
+    if (g.one) PS = f->M >= 4 ? 4 : 2;
+    g.PS = PS;
+    g.NW = g.one ? 4 : (PS == 1 ? 1 : (PS == 2 ? 2 : 4));
+    const int G = 32 / PS;
+    const int rows = f->Qpad / kR + G;
+    g.RS = rows | 1;
+    g.stage_b = std::max<size_t>((size_t)f->M * ((size_t)(kR / 2) * g.RS + 1), 32 * (kR / 2 + 1)) * sizeof(float4);
+    g.taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * sizeof(float);
+    return true;
+}
+// The decimator kernel that serves this handle has a variant with the NCO mix-down fused into its tile loader
+bool fir_mix_fusable(const sgpu_fir *f) {
+    DwarpGeom g;
+    if (!(f->M == 2 || f->M == 4 || f->M == 8) || !dwarp_geometry(f, g)) return false;
+    return (size_t)g.NW * g.stage_b + g.taps_b + kNcoLutBytes <= (size_t)kMaxSmem && env_int("SGPU_DDC_FUSED", 1);
+}
+
 // Channels ride in grid.y (<= 65535): larger handles are launched in channel blocks.
 int fir_launch(sgpu_fir *f, const float2 *d_in, long long n_in, long long in_stride, float2 *d_out,
                long long out_stride, long long n_out, cudaStream_t s) {
@@ -713,6 +762,9 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     a.vec_out = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) && (out_stride % 2 == 0);
     a.scale_re = (float)f->scale_re;
     a.scale_im = (float)f->scale_im;
+    a.nco = f->nco_tab ? f->nco_tab + 2 * f->ch_off : nullptr;
+    a.lut = f->nco_tab ? f->nco_lut : nullptr;
+    a.nco_pos = f->nco_pos;
     f->last_path = 0;
     if (n_out <= 0) return SGPU_OK;  // a decimator call shorter than one period: the caller enqueues the history update
     if (f->M == 1 && !f->per_channel && (f->complex_taps || f->scale_im == 0.0) &&
@@ -776,27 +828,21 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             return SGPU_OK;
         }
     }
-    if ((f->M == 2 || f->M == 4 || f->M == 8 || f->M == 16 || f->M == 32) && f->packed && !f->complex_taps &&
-        env_int("SGPU_DEC_WARP", 1)) {
+    DwarpGeom dg;
+    if (dwarp_geometry(f, dg)) {
         // warp-private tiles (fir_walk.cuh)
-        int PS = env_int("SGPU_DEC_PS", f->M >= 4 ? 4 : 2);
-        if (PS != 1 && PS != 2 && PS != 4) PS = 4;
-        if (PS > (int)f->M) PS = (int)f->M;
-        const bool one = f->Qpad == kR;  // sub-filters of <= 16 taps: single tap chunk
-        if (one) PS = f->M >= 4 ? 4 : 2;
-        const int G = 32 / PS;
-        const int rows = f->Qpad / kR + G;
-        a.RS = rows | 1;
-        const size_t stage_b = std::max<size_t>((size_t)f->M * ((size_t)(kR / 2) * a.RS + 1), 32 * (kR / 2 + 1)) * sizeof(float4);
-        const size_t taps_b = (size_t)f->M * (f->Qpad + kTapSkew) * sizeof(float);
+        const int PS = dg.PS;
+        const bool one = dg.one;
+        a.RS = dg.RS;
+        const size_t stage_b = dg.stage_b, taps_b = dg.taps_b;
         constexpr int TPW = 8;
         int st = SGPU_OK;
         bool done = false;
-#define LAUNCH_DWARP(MV, PSV, NWV, MB, ONEV)                                                  \
+#define LAUNCH_DWARP_X(MV, PSV, NWV, MB, ONEV, MIXV)                                          \
     do {                                                                                      \
-        const size_t smem = (size_t)NWV * stage_b + taps_b;                                   \
+        const size_t smem = (size_t)NWV * stage_b + taps_b + (MIXV ? kNcoLutBytes : 0);       \
         if (smem <= (size_t)kMaxSmem) {                                                       \
-            auto kern = fir_decim_warp_kernel<kR, MV, PSV, NWV, MB, TPW, ONEV>;               \
+            auto kern = fir_decim_warp_kernel<kR, MV, PSV, NWV, MB, TPW, ONEV, MIXV>;         \
             st = set_smem(kern, smem);                                                        \
             if (st) return st;                                                                \
             const long long per_block = (long long)(32 / PSV) * kR * TPW * NWV;               \
@@ -805,16 +851,24 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             done = true;                                                                      \
         }                                                                                     \
     } while (0)
+#define LAUNCH_DWARP(MV, PSV, NWV, MB, ONEV) LAUNCH_DWARP_X(MV, PSV, NWV, MB, ONEV, false)
+    // M = 2, 4, 8 also exist with the NCO mix-down fused into the tile loader (DDC)
+#define LAUNCH_DWARP_MIX(MV, PSV, NWV, MB, ONEV)                                              \
+    do {                                                                                      \
+        if (a.lut) LAUNCH_DWARP_X(MV, PSV, NWV, MB, ONEV, true);                              \
+        else LAUNCH_DWARP_X(MV, PSV, NWV, MB, ONEV, false);                                   \
+    } while (0)
 #define LAUNCH_DWARP_M(MV)                                                                    \
     do {                                                                                      \
-        if (one) LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4, true);                             \
-        else if (PS == 1) LAUNCH_DWARP(MV, 1, 1, 4, false);                                   \
-        else if (PS == 2) LAUNCH_DWARP(MV, 2, 2, 4, false);                                   \
-        else LAUNCH_DWARP(MV, (MV >= 4 ? 4 : 2), 4, 4, false);                                \
+        if (one) LAUNCH_DWARP_MIX(MV, (MV >= 4 ? 4 : 2), 4, 4, true);                         \
+        else if (PS == 1) LAUNCH_DWARP_MIX(MV, 1, 1, 4, false);                               \
+        else if (PS == 2) LAUNCH_DWARP_MIX(MV, 2, 2, 4, false);                               \
+        else LAUNCH_DWARP_MIX(MV, (MV >= 4 ? 4 : 2), 4, 4, false);                            \
     } while (0)
         if (f->M == 8) LAUNCH_DWARP_M(8);
         else if (f->M == 4) LAUNCH_DWARP_M(4);
         else if (f->M == 2) LAUNCH_DWARP_M(2);
+        else if (a.lut) return fail(SGPU_ERR_UNSUPPORTED, "NCO mix requested on a kernel without a fused variant");
         else if (f->M == 16) {  // 16 / 32 phase planes per stage: fewer warps per block as the tile grows
             if (one) LAUNCH_DWARP(16, 4, 4, 2, true);
             else {
@@ -830,7 +884,9 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             }
         }
 #undef LAUNCH_DWARP_M
+#undef LAUNCH_DWARP_MIX
 #undef LAUNCH_DWARP
+#undef LAUNCH_DWARP_X
         if (done) {
             SGPU_LAUNCH_CHECK();
             count_launch();
@@ -838,6 +894,7 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             return SGPU_OK;
         }
     }
+    if (a.lut) return fail(SGPU_ERR_UNSUPPORTED, "NCO mix requested on a kernel without a fused variant");
     {
         const bool m1 = f->M == 1;
         const int R = fir_R(f);
@@ -900,6 +957,49 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
 
 }  // namespace
 
+// One pass over device-resident samples: ONE kernel computes the outputs and writes the new history tail (the tensor
+// path: two launches, fir_tc.cuh); only the phase counter lives on the host.  With an NCO attached (sgpu_ddc) the
+// mix-down runs inside the decimator's tile loader where a fused variant exists, else as a kernel of its own in front.
+static int fir_run_device(sgpu_fir *f, const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr,
+                          size_t nout, cudaStream_t st_) {
+    const unsigned *tab = f->nco_tab;
+    if (tab) {
+        const bool fused = nout > 0 && fir_mix_fusable(f);
+        f->last_mix_fused = fused ? 1 : 0;
+        if (!fused) {
+            const size_t need = f->C * nc;
+            if (need > f->mix_cap) {
+                if (f->d_mix) {
+                    SGPU_CUDA(cudaStreamSynchronize(st_));
+                    cudaFree(f->d_mix);
+                }
+                f->d_mix = nullptr;
+                f->mix_cap = 0;
+                if (cudaMalloc(&f->d_mix, need * sizeof(float2)) != cudaSuccess)
+                    return fail(SGPU_ERR_ALLOC, "cudaMalloc(mixed samples, %zu bytes) failed", need * sizeof(float2));
+                f->mix_cap = need;
+            }
+            int st = nco_mix_launch(false, d_in, istr, f->d_mix, (long long)nc, (long long)nc, f->C, tab, f->nco_pos, f->nco_lut, st_);
+            if (st) return st;
+            d_in = f->d_mix;
+            istr = (long long)nc;
+            f->nco_tab = nullptr;  // the kernels below see mixed samples
+        }
+    }
+    f->hist_written = false;
+    int st = fir_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
+    if (st == SGPU_OK) {
+        if (f->hist_written) f->cur ^= 1;
+        else if (f->nco_tab) st = fail(SGPU_ERR_UNSUPPORTED, "fused mix without a history update");
+        else st = enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->T - 1, st_);
+    }
+    f->nco_tab = tab;
+    if (st) return st;
+    if (tab) f->nco_pos += (unsigned)nc;                                // one NCO::step per sample (nco/mod.rs:93-96)
+    if (f->is_decim) f->current_item = (f->current_item + nc) % f->M;  // decim.rs:116
+    return SGPU_OK;
+}
+
 SGPU_EXPORT int sgpu_fir_execute_block(sgpu_fir *f, const float *in, size_t n_in, size_t in_stride,
                                        float *out, size_t out_stride, size_t *n_out_p, sgpu_mem mem,
                                        void *stream) {
@@ -915,19 +1015,8 @@ SGPU_EXPORT int sgpu_fir_execute_block(sgpu_fir *f, const float *in, size_t n_in
         return fail(SGPU_ERR_INVALID_ARGUMENT, "in and out overlap: execute_block is not an in-place operation");
     DeviceGuard g(f->device);
     cudaStream_t s = (cudaStream_t)stream;
-    // one pass over device-resident samples: ONE kernel computes the outputs and writes the new history tail (the
-    // tensor path: two launches, fir_tc.cuh); only the phase counter lives on the host
     auto run = [f](const float2 *d_in, size_t nc, long long istr, float2 *d_out, long long ostr, size_t nout,
-                   cudaStream_t st_) -> int {
-        f->hist_written = false;
-        int st = fir_launch(f, d_in, (long long)nc, istr, d_out, ostr, (long long)nout, st_);
-        if (st) return st;
-        if (f->hist_written) f->cur ^= 1;
-        else st = enqueue_hist_update(d_in, istr, (long long)nc, f->d_hist, f->cur, f->C, f->T - 1, st_);
-        if (st) return st;
-        if (f->is_decim) f->current_item = (f->current_item + nc) % f->M;  // decim.rs:116
-        return SGPU_OK;
-    };
+                   cudaStream_t st_) -> int { return fir_run_device(f, d_in, nc, istr, d_out, ostr, nout, st_); };
     if (mem == SGPU_DEVICE)
         return run(reinterpret_cast<const float2 *>(in), n_in, (long long)in_stride, reinterpret_cast<float2 *>(out),
                    (long long)out_stride, n_out, s);
@@ -1008,6 +1097,124 @@ SGPU_EXPORT int sgpu_fir_clone(const sgpu_fir *f, sgpu_fir **out) {
     }
     c->current_item = f->current_item;
     *out = c;
+    return SGPU_OK;
+}
+
+// =============================================================================================
+// Digital down-converter: NCO::mix_down + step per sample (nco/mod.rs:93-96,147-151) feeding a DecimatingFIRFilter
+// (fir/decim.rs:221-256) -- SURVEY 8f rank 3.  One NCO and one decimator per channel, the mixed stream never reaches HBM
+// where the decimator kernel has a fused variant (fir_walk.cuh, MIX).
+// =============================================================================================
+struct sgpu_ddc {
+    sgpu_fir *fir = nullptr;
+    sgpu_nco *nco = nullptr;
+};
+
+SGPU_EXPORT int sgpu_ddc_create(const double *taps, size_t n_taps, sgpu_tapkind kind, size_t n_channels, double scale_re,
+                                double scale_im, size_t decimation, sgpu_ddc **out) {
+    if (!out) return fail(SGPU_ERR_INVALID_ARGUMENT, "ddc_create: out is NULL");
+    *out = nullptr;
+    sgpu_ddc *d = new (std::nothrow) sgpu_ddc();
+    if (!d) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    int st = sgpu_fir_create(taps, n_taps, kind, n_channels, scale_re, scale_im, 1, decimation, &d->fir);
+    if (st == SGPU_OK) st = sgpu_nco_create(n_channels, &d->nco);
+    if (st) {
+        sgpu_ddc_destroy(d);
+        return st;
+    }
+    *out = d;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_ddc_destroy(sgpu_ddc *d) {
+    if (!d) return SGPU_OK;
+    sgpu_fir_destroy(d->fir);
+    sgpu_nco_destroy(d->nco);
+    delete d;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_ddc_clone(const sgpu_ddc *d, sgpu_ddc **out) {
+    if (!d || !out) return fail(SGPU_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    sgpu_ddc *c = new (std::nothrow) sgpu_ddc();
+    if (!c) return fail(SGPU_ERR_ALLOC, "out of host memory");
+    int st = sgpu_fir_clone(d->fir, &c->fir);
+    if (st == SGPU_OK) st = sgpu_nco_clone(d->nco, &c->nco);
+    if (st) {
+        sgpu_ddc_destroy(c);
+        return st;
+    }
+    *out = c;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT sgpu_fir *sgpu_ddc_filter(sgpu_ddc *d) { return d ? d->fir : nullptr; }
+SGPU_EXPORT sgpu_nco *sgpu_ddc_nco(sgpu_ddc *d) { return d ? d->nco : nullptr; }
+SGPU_EXPORT size_t sgpu_ddc_out_len(const sgpu_ddc *d, size_t n_in) { return d ? sgpu_fir_out_len(d->fir, n_in) : 0; }
+SGPU_EXPORT int sgpu_ddc_last_fused(const sgpu_ddc *d) { return d && d->fir ? d->fir->last_mix_fused : 0; }
+
+SGPU_EXPORT int sgpu_ddc_reset(sgpu_ddc *d) {  // NCO::reset (nco/mod.rs:53-56) + the decimator's window and counter
+    if (!d) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    int st = sgpu_nco_reset(d->nco);
+    return st ? st : sgpu_fir_reset(d->fir);
+}
+
+namespace {
+// the decimator sees the NCO for the duration of one call
+struct NcoAttach {
+    sgpu_fir *f;
+    sgpu_nco *n;
+    NcoAttach(sgpu_fir *f_, sgpu_nco *n_) : f(f_), n(n_) {
+        f->nco_tab = n->d_tab;
+        f->nco_lut = n->d_lut;
+        f->nco_pos = n->pos;
+    }
+    ~NcoAttach() {
+        n->pos = f->nco_pos;
+        f->nco_tab = nullptr;
+    }
+};
+}  // namespace
+
+SGPU_EXPORT int sgpu_ddc_execute_block(sgpu_ddc *d, const float *in, size_t n_in, size_t in_stride, float *out,
+                                       size_t out_stride, size_t *n_out_p, sgpu_mem mem, void *stream) {
+    if (!d) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_in) {
+        DeviceGuard g(d->fir->device);
+        int st = nco_sync_table(d->nco, (cudaStream_t)stream);
+        if (st) return st;
+    }
+    NcoAttach attach(d->fir, d->nco);
+    return sgpu_fir_execute_block(d->fir, in, n_in, in_stride, out, out_stride, n_out_p, mem, stream);
+}
+
+// DecimatingFIRFilter::write behind the mixer: the samples are mixed and pushed, no output (fir/decim.rs:136-139)
+SGPU_EXPORT int sgpu_ddc_write(sgpu_ddc *d, const float *in, size_t n_in, size_t in_stride, sgpu_mem mem, void *stream) {
+    if (!d) return fail(SGPU_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_in == 0) return SGPU_OK;
+    if (!in) return fail(SGPU_ERR_INVALID_ARGUMENT, "null buffer");
+    sgpu_fir *f = d->fir;
+    DeviceGuard g(f->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = nco_sync_table(d->nco, s);
+    if (st) return st;
+    const float2 *d_in = reinterpret_cast<const float2 *>(in);
+    long long istr = (long long)in_stride;
+    if (mem == SGPU_HOST) {
+        st = f->stage.ensure(f->C * n_in * sizeof(float2), 0);
+        if (st) return st;
+        SGPU_CUDA(cudaMemcpy2DAsync(f->stage.in, n_in * sizeof(float2), in, in_stride * sizeof(float2), n_in * sizeof(float2), f->C,
+                                    cudaMemcpyHostToDevice, s));
+        d_in = (const float2 *)f->stage.in;
+        istr = (long long)n_in;
+    }
+    {
+        NcoAttach attach(f, d->nco);
+        st = fir_run_device(f, d_in, n_in, istr, nullptr, 1, 0, s);  // no outputs: mix into scratch + history update
+    }
+    if (st) return st;
+    if (mem == SGPU_HOST) SGPU_CUDA(cudaStreamSynchronize(s));
     return SGPU_OK;
 }
 

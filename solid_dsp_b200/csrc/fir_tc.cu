@@ -951,9 +951,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
+template <int CU, int RF, int RC>  // converter positions in flight per trip, register budgets of the flush / converter warps
 __global__ void __launch_bounds__(kChainThreads, 1)
 fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
                     const TcFusedArgs a, const StripGeom g) {
+    static_assert(4 * kRegProducer + 8 * RF + 4 * RC <= 2048, "register file: 64 K registers per SM");
     using F = Fmt<true, false>;
     constexpr int kAStage = F::kA;  // 16 KB: f1 and f2 of 128 x 32 taps
     extern __shared__ uint8_t smem_raw[];
@@ -1037,6 +1039,10 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 for (int p = 0; p < 2; ++p) {
                     if (!first) mbar_wait(sfree_bar(p), fphase);  // the previous tile's MMAs on these strips are done
+                    if (a.dbg & 2) {  // experiments: no strip loads
+                        mbar_arrive(sfull_bar(p));
+                        continue;
+                    }
                     mbar_expect_tx(sfull_bar(p), 4u * (uint32_t)(2 * g.nrows * 64));
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc)
@@ -1094,7 +1100,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp < 12) {  // ===== FLUSH =====
-        reg_inc<kRegFlush>();
+        reg_inc<RF>();
         const int ew = warp - 4;
         const int wq = warp & 3;        // TMEM lane quarter this warp may read
         const int half = ew >> 2;       // blocks [64 half, 64 half + 64) of the tile = accumulator columns [128 half, 128 half + 128)
@@ -1117,6 +1123,12 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * 128;
                     const float *__restrict__ scj = scf + 2 * sft + p;
+                    if (a.dbg & 16) {  // experiments: the chain is not read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        continue;
+                    }
 #pragma unroll
                     for (int cg = 0; cg < 4; ++cg) {
                         float v[32];
@@ -1140,7 +1152,12 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
             const long long n0 = (long long)tt * kTileSamples + (long long)(half * 64) * kBM + m;
             float2 *__restrict__ yp = a.out + (long long)ch * a.out_stride + n0;
-            if ((long long)(tt + 1) * kTileSamples <= a.n_out) {  // interior tile: constant offsets, no guards
+            if (a.dbg & 8) {  // experiments: no output stores (one store keeps the accumulators alive)
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 128; ++j) sum += acc_[j];
+                if (sum == 123.456f) st_hint_v2(yp, sum, sum, pol_stream);
+            } else if ((long long)(tt + 1) * kTileSamples <= a.n_out) {  // interior tile: constant offsets, no guards
 #pragma unroll
                 for (int j = 0; j < 64; ++j) st_hint_v2(yp + j * kBM, acc_[2 * j] * a.scale, acc_[2 * j + 1] * a.scale, pol_stream);
             } else {
@@ -1152,7 +1169,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++fs == nsc) fs = 0;
         }
     } else {  // ===== CONVERT: as in the chain kernel =====
-        reg_dec<kRegConvert>();
+        reg_dec<RC>();
         const int et = (warp - 12) * 32 + lane;
         const size_t buf_bytes = (size_t)2 * F::kParts * a.tile_plane * F::kElem;
         uint8_t *ring = reinterpret_cast<uint8_t *>(a.scratch) + (size_t)(a.nbuf * blockIdx.x) * buf_bytes;
@@ -1163,8 +1180,9 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bool wrapped = false;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             if (wrapped) mbar_wait(rfree_bar(wb), fphase);
-            const bool bad = tc_split_f16<2, 128>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0,
-                                                  a.tile_plane, et, pol_ring, pol_stream);
+            const bool bad = (a.dbg & 4) ? false
+                                         : tc_split_f16<CU, 128>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0,
+                                                                 a.tile_plane, et, pol_ring, pol_stream);
             if (bad) a.flags[tile] = 1u;
             fence_proxy_async();
             __syncwarp();
@@ -1330,6 +1348,7 @@ struct FirTcState {
     CUtensorMap tmStrip;         // the same ring as 5-D boxes {32 positions, re / im, block rows, part, buffer} for the strip kernel
     int strip_rows = 0;
     bool fused_smem_set[8] = {false, false, false, false, false, false, false, false};
+    bool strip_smem_set[4] = {false, false, false, false};
     bool persist_set = false;    // this handle holds a reference on its device's persisting-L2 carve-out
     bool ctaps = false;          // complex taps: the bands hold the Gr parts, then the Gi parts
     uint16_t *d_A16 = nullptr;   // [3 (x2)][128][K] bf16: b1, b2, b3 of the band
@@ -1647,9 +1666,13 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     const cudaAccessPolicyWindow *wp = window ? &win : nullptr;
     int rc;
     if (use_strip) {
-        bool &set = st->fused_smem_set[6];
+        // converter variant (SGPU_FIR_TC_STRIPV): 0 = two positions per trip, 1 = four, 2 = four with 184 / 120 registers
+        const int sv = std::max(0, std::min(2, env_i("SGPU_FIR_TC_STRIPV", 1)));
+        auto kern = sv == 0 ? fir_tc_strip_kernel<2, kRegFlush, kRegConvert>
+                  : (sv == 1 ? fir_tc_strip_kernel<4, kRegFlush, kRegConvert> : fir_tc_strip_kernel<4, 184, 120>);
+        bool &set = st->strip_smem_set[sv];
         if (!set) {
-            SGPU_CUDA(cudaFuncSetAttribute(fir_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             set = true;
         }
         cudaLaunchConfig_t cfg{};
@@ -1664,7 +1687,7 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
             cfg.attrs = attr;
             cfg.numAttrs = 1;
         }
-        SGPU_CUDA(cudaLaunchKernelEx(&cfg, fir_tc_strip_kernel, st->tmAh, st->tmStrip, a, sg));
+        SGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, st->tmAh, st->tmStrip, a, sg));
         SGPU_LAUNCH_CHECK();
         count_launch();
         rc = SGPU_OK;

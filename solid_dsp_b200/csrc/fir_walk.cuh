@@ -202,11 +202,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
         }
     };
     // MIX: every element of the tile this lane loaded that belongs to this call's input gets its phasor
+    unsigned nco_theta = 0, nco_delta = 0;
+    if constexpr (MIX) nco_channel(a, ch, nco_theta, nco_delta);
     auto mix_tile = [&](const long long m_base) {
         const long long i_lo = (m_base - Qpad) * M - a.c0;
         float2 *base = reinterpret_cast<float2 *>(stage);
-        const unsigned d_row = (unsigned)RM * a.nco_delta, d_k = 32u * a.nco_delta;
-        unsigned th_row = a.nco_theta + (unsigned)(i_lo + lane) * a.nco_delta + (1u << 21);  // rounding folded in
+        const unsigned d_row = (unsigned)RM * nco_delta, d_k = 32u * nco_delta;
+        unsigned th_row = nco_theta + (unsigned)(i_lo + lane) * nco_delta + (1u << 21);  // rounding folded in
         long long i = i_lo + lane;
         for (int rho = 0; rho < rows; ++rho) {
             unsigned th = th_row;
