@@ -379,9 +379,11 @@ __device__ __forceinline__ bool tc_split_bf16(const TcFusedArgs &a, int tile, vo
 // factor that undoes the scale, 2^(E - 141), goes to sc[q / 64] for the epilogue (the taps' own power of two is part
 // of a.scale).
 // The loops are warp-uniform (the shuffles need all 32 lanes); lanes beyond q1 contribute zeros and store nothing.
-template <int U = 1, int NTHR = 32 * kEpiWarps>
+// SC = float: the table holds the factor 2^(E - 141) itself; SC = uint8_t: its biased exponent E - 14 (1 .. 240), for
+// the kernel whose shared memory is full (the flush warps shift it into a float).
+template <int U = 1, int NTHR = 32 * kEpiWarps, typename SC = float>
 __device__ __forceinline__ bool tc_split_f16(const TcFusedArgs &a, int tile, void *__restrict__ dstv,
-                                             float *__restrict__ sc, int q0, int q1, int et, uint64_t pol_ring,
+                                             SC *__restrict__ sc, int q0, int q1, int et, uint64_t pol_ring,
                                              uint64_t pol_stream) {
     const int ch = tile / a.tiles_per_ch, tt = tile - ch * a.tiles_per_ch;
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
@@ -404,7 +406,10 @@ __device__ __forceinline__ bool tc_split_f16(const TcFusedArgs &a, int tile, voi
         bad |= E == 255u;
         E = min(max(E, 15u), 254u);
         const float f = __uint_as_float((268u - E) << 23);  // 2^(141 - E)
-        if (valid && (lane & ((1 << (a.gsh - 3)) - 1)) == 0) sc[qq >> a.gsh] = __uint_as_float((E - 14u) << 23);  // 2^(E - 141): always a normal float
+        if (valid && (lane & ((1 << (a.gsh - 3)) - 1)) == 0) {  // 2^(E - 141): always a normal float
+            if constexpr (std::is_same<SC, float>::value) sc[qq >> a.gsh] = __uint_as_float((E - 14u) << 23);
+            else sc[qq >> a.gsh] = (SC)(E - 14u);
+        }
         uint32_t w1r[4], w1i[4], w2r[4], w2i[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -938,9 +943,10 @@ fir_tc_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // (192); warps 12-15 convert (104), exactly as in the chain kernel.
 struct StripGeom {
     int nrows;        // block rows per strip = 128 + ceil(Koff / 128)
-    int strip_bytes;  // 2 * nrows * 64, rounded up to 1024
-    int nsa;          // A stages
+    int strip_bytes;  // 2 * nrows * 64, rounded up to 512 (the SWIZZLE_64B pattern repeats every 512 bytes)
+    int nsa;          // A stages (streamed band)
     int nch0, nch1;   // chains of class pair 0 (chunks 4 s, 4 s + 1) and 1 (4 s + 2, 4 s + 3)
+    int grows;        // resident band: rows of G per part = 128 + 32 (nchunks - 1)
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
@@ -951,7 +957,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
-template <int CU, int RF, int RC>  // converter positions in flight per trip, register budgets of the flush / converter warps
+// RES: the band A is RESIDENT too.  A is Toeplitz: chunk q + 1 is chunk q moved down by 32 rows, so all chunks are
+// windows of one tall matrix G[r][kk] = g[r - 32 (nchunks - 1) + Koff - kk] (128 + 32 (nchunks - 1) rows of 32 taps, two
+// fp16 parts: 92 KB at 512 taps), loaded once per CTA; chunk q's descriptor starts (nchunks - 1 - q) x 2048 bytes into it.
+// Nothing streams but the samples: L2 -> SM traffic per tile drops from 852 KB to 532 KB at 512 taps (the kernel sat at the
+// L2's ~7 TB/s, profiles/r2a_kernels.md).  The scale table shrinks to one exponent byte per group to make room.
+template <int CU, int RF, int RC, bool RES>  // converter positions in flight per trip, register budgets of the flush / converter warps
 __global__ void __launch_bounds__(kChainThreads, 1)
 fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS,
                     const TcFusedArgs a, const StripGeom g) {
@@ -959,11 +970,12 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using F = Fmt<true, false>;
     constexpr int kAStage = F::kA;  // 16 KB: f1 and f2 of 128 x 32 taps
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t base = (smem_u32(smem_raw) + 511u) & ~511u;
     auto strip = [&](int c, int part) { return base + (uint32_t)(2 * c + part) * (uint32_t)g.strip_bytes; };
     const uint32_t abase = base + 8u * (uint32_t)g.strip_bytes;
     auto stage_a = [&](int s) { return abase + (uint32_t)s * kAStage; };
-    const uint32_t bars = abase + (uint32_t)g.nsa * kAStage;
+    const uint32_t gpart = (uint32_t)g.grows * 64u;  // RES: bytes of one part of G
+    const uint32_t bars = RES ? abase + 2u * gpart : abase + (uint32_t)g.nsa * kAStage;
     auto afull_bar = [&](int s) { return bars + 8u * s; };              // 4 slots
     auto aempty_bar = [&](int s) { return bars + 8u * (4 + s); };       // 4 slots
     auto tfull_bar = [&](int i) { return bars + 8u * (8 + i); };        // 2 slots
@@ -972,8 +984,10 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto rfree_bar = [&](int i) { return bars + 8u * (16 + i); };       // 4 slots: ring buffer i has been read
     auto sfull_bar = [&](int p) { return bars + 8u * (20 + p); };       // 2 slots: the strips of class pair p have landed
     auto sfree_bar = [&](int p) { return bars + 8u * (22 + p); };       // 2 slots: every MMA that reads them is done
-    const uint32_t tmem_slot = bars + 8u * 24;
-    float *sc_tab = reinterpret_cast<float *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);  // nbuf + 2 slots, as in the chain kernel
+    const uint32_t gfull_bar = bars + 8u * 24;                          // RES: the band has landed
+    const uint32_t tmem_slot = bars + 8u * 25;
+    using SC = typename std::conditional<RES, uint8_t, float>::type;
+    SC *sc_tab = reinterpret_cast<SC *>(smem_raw + (bars - smem_u32(smem_raw)) + 256);  // nbuf + 2 slots, as in the chain kernel
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -989,6 +1003,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(sfull_bar(i), 1);
             mbar_init(sfree_bar(i), 1);
         }
+        mbar_init(gfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
@@ -1006,7 +1021,12 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp < 4) {
         reg_dec<kRegProducer>();
-        if (warp == 0 && lane == 0) {  // ===== A producer: the band's K chunks in the order the chains consume them =====
+        if (warp == 0 && lane == 0 && RES) {  // ===== the band, once: G in boxes of 32 rows =====
+            mbar_expect_tx(gfull_bar, 2u * gpart);
+            for (int part = 0; part < 2; ++part)
+                for (int r = 0; r < g.grows; r += 32)
+                    tma_load_3d(abase + (uint32_t)part * gpart + (uint32_t)r * 64u, &tmA, gfull_bar, 0, r, part);
+        } else if (warp == 0 && lane == 0) {  // ===== A producer: the band's K chunks in the order the chains consume them =====
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -1056,6 +1076,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
             int stage = 0, rb = 0;
             uint32_t phase = 0, use = 0, sphase = 0;
+            if constexpr (RES) mbar_wait(gfull_bar, 0);
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int p = 0; p < 2; ++p) {
                     mbar_wait(sfull_bar(p), sphase);
@@ -1071,12 +1092,13 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t d = tmem_base + acc * kBN;
                         const int q0 = 4 * sft + 2 * p, q1 = min(q0 + 2, a.nchunks);
                         for (int q = q0; q < q1; ++q) {
-                            mbar_wait(afull_bar(stage), phase);
+                            if constexpr (!RES) mbar_wait(afull_bar(stage), phase);
                             tc_fence_after();
                             if (!(a.dbg & 1)) {
-                                const uint32_t sa = stage_a(stage);
+                                const uint32_t sa = RES ? abase + (uint32_t)(a.nchunks - 1 - q) * 2048u : stage_a(stage);
+                                const uint32_t a_part = RES ? gpart : (uint32_t)F::kAPart;
                                 const uint32_t sb0 = strip(q & 3, 0) + (uint32_t)sft * 128u, sb1 = strip(q & 3, 1) + (uint32_t)sft * 128u;
-                                const uint64_t da0 = umma_desc_sw64(sa), da1 = umma_desc_sw64(sa + F::kAPart);
+                                const uint64_t da0 = umma_desc_sw64(sa), da1 = umma_desc_sw64(sa + a_part);
                                 const uint64_t db0 = umma_desc_sw64(sb0), db1 = umma_desc_sw64(sb1);
 #pragma unroll
                                 for (int kk = 0; kk < F::kKSteps; ++kk) {
@@ -1086,10 +1108,12 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     umma_f16(d, da1 + off, db0 + off, F::kIdesc, 1u);                              // f1 h2
                                 }
                             }
-                            umma_commit(aempty_bar(stage));
-                            if (++stage == g.nsa) {
-                                stage = 0;
-                                phase ^= 1u;
+                            if constexpr (!RES) {
+                                umma_commit(aempty_bar(stage));
+                                if (++stage == g.nsa) {
+                                    stage = 0;
+                                    phase ^= 1u;
+                                }
                             }
                         }
                         umma_commit(tfull_bar(acc));
@@ -1111,7 +1135,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int fs = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             // scale group of (block b, class pair p, shift s): positions 128 (b + s) + 64 p + [0, 64) -> 2 (b + s) + p
-            const float *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + 2 * (64 * half);
+            const SC *__restrict__ scf = sc_tab + (size_t)fs * a.sc_len + 2 * (64 * half);
             float acc_[128];  // (re, im) of block 64 half + j at [2 j], [2 j + 1]
 #pragma unroll
             for (int j = 0; j < 128; ++j) acc_[j] = 0.f;
@@ -1122,7 +1146,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(tfull_bar(acc), (use >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kBN + half * 128;
-                    const float *__restrict__ scj = scf + 2 * sft + p;
+                    const SC *__restrict__ scj = scf + 2 * sft + p;
                     if (a.dbg & 16) {  // experiments: the chain is not read
                         tc_fence_before();
                         __syncwarp();
@@ -1142,7 +1166,9 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float mlt = scj[2 * (cg * 16 + j)];
+                            float mlt;
+                            if constexpr (RES) mlt = __uint_as_float((uint32_t)scj[2 * (cg * 16 + j)] << 23);
+                            else mlt = scj[2 * (cg * 16 + j)];
                             acc_[cg * 32 + 2 * j] = fmaf(v[2 * j], mlt, acc_[cg * 32 + 2 * j]);
                             acc_[cg * 32 + 2 * j + 1] = fmaf(v[2 * j + 1], mlt, acc_[cg * 32 + 2 * j + 1]);
                         }
@@ -1181,7 +1207,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             if (wrapped) mbar_wait(rfree_bar(wb), fphase);
             const bool bad = (a.dbg & 4) ? false
-                                         : tc_split_f16<CU, 128>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0,
+                                         : tc_split_f16<CU, 128, SC>(a, tile, ring + (size_t)wb * buf_bytes, sc_tab + (size_t)ws * a.sc_len, 0,
                                                                  a.tile_plane, et, pol_ring, pol_stream);
             if (bad) a.flags[tile] = 1u;
             fence_proxy_async();
@@ -1356,6 +1382,9 @@ struct FirTcState {
     uint16_t *d_Ah = nullptr;    // [2 (x2)][128][K] fp16: f1, f2 of the band times 2^tap_shift
     CUtensorMap tmAh;
     int tap_shift = 0;
+    uint16_t *d_G = nullptr;     // [2][grows][32] fp16: the band as one tall Toeplitz matrix (strip kernel, resident band)
+    CUtensorMap tmG;
+    int grows = 0;
     float *d_tp = nullptr;       // [L][S][tw] f32 taps for fir_tc_post_kernel
     uint32_t *d_flags = nullptr; // [flags_cap] non-finite tile flags, all zero between calls
     size_t flags_cap = 0;
@@ -1431,6 +1460,35 @@ int fir_tc_create_pfb(FirTcState **out, const float *tp, int L, int S, bool comp
     };
     int rc = upload_band(3, false, &st->d_A16, &st->tmA16);
     if (rc == SGPU_OK) rc = upload_band(2, true, &st->d_Ah, &st->tmAh);
+    if (rc == SGPU_OK && L == 1 && !complex_taps) {
+        // G[part][r][kk] = g[r - 32 (nchunks - 1) + Koff - kk] * 2^tap_shift: chunk q of A is rows [32 (nchunks - 1 - q), + 128)
+        st->grows = kBM + kKC * (st->nchunks - 1);
+        std::vector<uint16_t> G((size_t)2 * st->grows * kKC, 0);
+        for (int r = 0; r < st->grows; ++r)
+            for (int kk = 0; kk < kKC; ++kk) {
+                const int jj = r - kKC * (st->nchunks - 1) + st->Koff - kk;
+                if (jj < 0 || jj >= T) continue;
+                float gv = ldexpf(tp[jj], st->tap_shift);
+                for (int part = 0; part < 2; ++part) {
+                    const uint16_t bits = host_f16_rne(gv);
+                    G[((size_t)part * st->grows + r) * kKC + kk] = bits;
+                    gv -= host_f16_to_f32(bits);
+                }
+            }
+        if (cudaMalloc(&st->d_G, G.size() * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMemcpy(st->d_G, G.data(), G.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(SGPU_ERR_CUDA, "upload of the Toeplitz tap matrix failed");
+        else {
+            const cuuint64_t gdim[3] = {(cuuint64_t)kKC, (cuuint64_t)st->grows, 2};
+            const cuuint64_t gstr[2] = {(cuuint64_t)kKC * 2, (cuuint64_t)kKC * 2 * st->grows};
+            const cuuint32_t box[3] = {kKC, 32, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = enc(&st->tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, st->d_G, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) rc = fail(SGPU_ERR_CUDA, "cuTensorMapEncodeTiled(G) failed: %d", (int)r);
+        }
+    }
     if (rc != SGPU_OK) {
         fir_tc_destroy(st);
         return rc;
@@ -1461,6 +1519,7 @@ void fir_tc_destroy(FirTcState *st) {
     if (st->d_ring) cudaFree(st->d_ring);
     if (st->d_A16) cudaFree(st->d_A16);
     if (st->d_Ah) cudaFree(st->d_Ah);
+    if (st->d_G) cudaFree(st->d_G);
     if (st->d_tp) cudaFree(st->d_tp);
     if (st->d_flags) cudaFree(st->d_flags);
     delete st;
@@ -1521,13 +1580,19 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     // Strip kernel (real-tap FIR, samples resident in shared memory): chains of two chunks in class-pair order
     StripGeom sg{};
     sg.nrows = 128 + (int)ceil_div((size_t)st->Koff, 128);
-    sg.strip_bytes = (int)round_up((size_t)2 * sg.nrows * 64, 1024);
+    sg.strip_bytes = (int)round_up((size_t)2 * sg.nrows * 64, 512);
+    sg.grows = st->grows;
     sg.nch0 = (st->nchunks + 3) / 4;
     sg.nch1 = (st->nchunks - 2 + 3) / 4;
     const int tile_plane = (int)round_up((size_t)(st->Koff + kNB * R), R);
-    const size_t strip_tab = (size_t)(2 + 2) * round_up(ceil_div((size_t)tile_plane, 64) + 2, 4) * sizeof(float);
+    const size_t strip_groups = round_up(ceil_div((size_t)tile_plane, 64) + 2, 4);
+    const int strip_nbuf = std::max(2, std::min(3, env_i("SGPU_FIR_TC_RING", 2)));  // ring buffers per CTA of the strip kernel
+    const size_t strip_tab = (size_t)(strip_nbuf + 2) * strip_groups * sizeof(float);
     for (sg.nsa = 4; sg.nsa >= 2; --sg.nsa)
-        if ((size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 1024 + 256 + strip_tab <= (size_t)227 * 1024) break;
+        if ((size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 512 + 256 + strip_tab <= (size_t)227 * 1024) break;
+    // the whole band resident next to the strips (512 taps: 132 KB + 92 KB), exponent bytes instead of float scales
+    const size_t res_smem = (size_t)8 * sg.strip_bytes + (size_t)2 * sg.grows * 64 + 512 + 256 + (size_t)(strip_nbuf + 2) * strip_groups;
+    const bool strip_res = st->d_G != nullptr && res_smem <= (size_t)227 * 1024 && env_i("SGPU_FIR_TC_RESIDENT", 1) != 0;
     const bool use_strip = want_f16 && !st->ctaps && R == 128 && sg.nsa >= 2 && sg.nrows <= 256 && env_i("SGPU_FIR_TC_STRIP", 1) != 0;
     if (use_strip) gchunks = 2;
     const int nchains = use_strip ? sg.nch0 + sg.nch1 : (st->nchunks + gchunks - 1) / gchunks;
@@ -1535,7 +1600,7 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     const int parts = fmt ? 2 : 3, elem = 2;
     // ring buffers per CTA: the one-chain kernel's groups of warps split NG tiles ahead; the chain kernel's converter
     // warps run one tile ahead of the MMAs
-    const int nbuf = nchains == 1 ? kOneRing : (use_strip ? 2 : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", 2))));
+    const int nbuf = nchains == 1 ? kOneRing : (use_strip ? strip_nbuf : std::max(2, std::min(4, env_i("SGPU_FIR_TC_RING", 2))));
     if (!st->d_ring || st->ring_ctas < sm_count || st->tile_plane != tile_plane || st->ring_fmt != fmt || st->ring_nbuf != nbuf) {
         if (st->d_ring) {
             SGPU_CUDA(cudaStreamSynchronize(s));
@@ -1667,9 +1732,11 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     int rc;
     if (use_strip) {
         // converter variant (SGPU_FIR_TC_STRIPV): 0 = two positions per trip, 1 = four, 2 = four with 184 / 120 registers
-        const int sv = std::max(0, std::min(2, env_i("SGPU_FIR_TC_STRIPV", 1)));
-        auto kern = sv == 0 ? fir_tc_strip_kernel<2, kRegFlush, kRegConvert>
-                  : (sv == 1 ? fir_tc_strip_kernel<4, kRegFlush, kRegConvert> : fir_tc_strip_kernel<4, 184, 120>);
+        int sv = std::max(0, std::min(2, env_i("SGPU_FIR_TC_STRIPV", 1)));
+        if (strip_res) sv = 3;
+        auto kern = sv == 0 ? fir_tc_strip_kernel<2, kRegFlush, kRegConvert, false>
+                  : (sv == 1 ? fir_tc_strip_kernel<4, kRegFlush, kRegConvert, false>
+                  : (sv == 2 ? fir_tc_strip_kernel<4, 184, 120, false> : fir_tc_strip_kernel<4, kRegFlush, kRegConvert, true>));
         bool &set = st->strip_smem_set[sv];
         if (!set) {
             SGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1678,7 +1745,8 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3((unsigned)kChainThreads);
-        cfg.dynamicSmemBytes = (size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 1024 + 256 + (size_t)(nbuf + 2) * a.sc_len * sizeof(float);
+        cfg.dynamicSmemBytes = strip_res ? res_smem
+                                         : (size_t)8 * sg.strip_bytes + (size_t)sg.nsa * Fmt<true, false>::kA + 512 + 256 + (size_t)(nbuf + 2) * a.sc_len * sizeof(float);
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         if (wp) {
@@ -1687,7 +1755,7 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
             cfg.attrs = attr;
             cfg.numAttrs = 1;
         }
-        SGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, st->tmAh, st->tmStrip, a, sg));
+        SGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, strip_res ? st->tmG : st->tmAh, st->tmStrip, a, sg));
         SGPU_LAUNCH_CHECK();
         count_launch();
         rc = SGPU_OK;
