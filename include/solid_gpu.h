@@ -92,6 +92,11 @@ int sgpu_abi_version(void);
 const char *sgpu_last_error(void);
 const char *sgpu_status_name(int status);
 /* Properties of the current CUDA device (cudaGetDevice). */
+/* Pinned host memory placed on the NUMA node of `device` (-1: the current device) for the SGPU_HOST calls: the
+ * reference's callers hand over `&[In]` slices in ordinary host memory (filter/mod.rs:14); a GPU caller that wants the
+ * PCIe ceiling allocates its sample buffers here.  Free with sgpu_host_free. */
+int sgpu_host_alloc(size_t bytes, int device, void **out);
+int sgpu_host_free(void *p);
 int sgpu_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t sgpu_launch_count(void);

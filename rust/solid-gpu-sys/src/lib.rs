@@ -154,6 +154,9 @@ extern "C" {
     pub fn sgpu_dot_execute(d: *mut sgpu_dot, x: *const c_float, n_x: size_t, x_stride: size_t, n_vec: size_t,
                             result: *mut c_float, mem: c_int, stream: *mut c_void) -> c_int;
 
+    pub fn sgpu_host_alloc(bytes: size_t, device: c_int, out: *mut *mut c_void) -> c_int;
+    pub fn sgpu_host_free(p: *mut c_void) -> c_int;
+
     pub fn sgpu_nco_create(n_channels: size_t, out: *mut *mut sgpu_nco) -> c_int;
     pub fn sgpu_nco_destroy(n: *mut sgpu_nco) -> c_int;
     pub fn sgpu_nco_clone(n: *const sgpu_nco, out: *mut *mut sgpu_nco) -> c_int;

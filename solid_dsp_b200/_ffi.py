@@ -58,6 +58,8 @@ PROTOTYPES = {
     "sgpu_status_name": (C.c_char_p, [C.c_int]),
     "sgpu_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4 + [c_sizep]),
     "sgpu_launch_count": (C.c_uint64, []),
+    "sgpu_host_alloc": (C.c_int, [c_size, C.c_int, vpp]),
+    "sgpu_host_free": (C.c_int, [vp]),
     "sgpu_fir_create": (C.c_int, [c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, C.c_int, c_size, vpp]),
     "sgpu_fir_create_per_channel": (C.c_int, [c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, C.c_int, c_size, vpp]),
     "sgpu_fir_taps_per_channel": (C.c_int, [vp]),

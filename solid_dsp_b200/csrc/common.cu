@@ -1,4 +1,8 @@
 // Library-level entry points: errors, device probe, launch counter, sharding arithmetic.
+#include <sched.h>
+
+#include <cctype>
+
 #include "sgpu_common.cuh"
 
 namespace sgpu {
@@ -121,6 +125,75 @@ size_t host_chunk_len(size_t C, size_t n_in) {
 }
 
 }  // namespace sgpu
+
+// ---------------------------------------------------------------------------------------------
+// Pinned host memory on the NUMA node of a GPU.  The SGPU_HOST path is bounded by the host <-> device copies; on a
+// multi-socket box a pinned buffer that lives on the other socket costs a hop over the inter-socket link per byte
+// (tools/pcie_probe.py measures both placements).  The pages are first-touched while the calling thread is bound to
+// the CPUs the kernel reports as local to the GPU's PCIe root (/sys/bus/pci/devices/<bdf>/local_cpulist).
+namespace {
+bool gpu_local_cpus(int device, cpu_set_t *set) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) return false;
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bdf);
+    FILE *fp = fopen(path, "r");
+    if (!fp) return false;
+    char buf[4096] = {0};
+    const size_t got = fread(buf, 1, sizeof(buf) - 1, fp);
+    fclose(fp);
+    if (got == 0) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+            for (int i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET(i, set); ++n; }
+        } else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) {
+            CPU_SET(a, set);
+            ++n;
+        }
+    }
+    return n > 0;
+}
+}  // namespace
+
+SGPU_EXPORT int sgpu_host_alloc(size_t bytes, int device, void **out) {
+    if (!out) return sgpu::fail(SGPU_ERR_INVALID_ARGUMENT, "host_alloc: out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return SGPU_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return sgpu::fail(SGPU_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0) cudaGetDevice(&device);
+    cpu_set_t old_set, gpu_set;
+    const bool have_old = sched_getaffinity(0, sizeof(old_set), &old_set) == 0;
+    const bool bound = have_old && gpu_local_cpus(device, &gpu_set) && sched_setaffinity(0, sizeof(gpu_set), &gpu_set) == 0;
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        // first touch under the GPU-local binding (cudaHostAlloc usually faults the pages in itself; this makes sure)
+        volatile char *c = static_cast<volatile char *>(p);
+        for (size_t i = 0; i < bytes; i += 4096) c[i] = 0;
+    }
+    if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return sgpu::fail(SGPU_ERR_ALLOC, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    *out = p;
+    return SGPU_OK;
+}
+
+SGPU_EXPORT int sgpu_host_free(void *p) {
+    if (!p) return SGPU_OK;
+    if (cudaFreeHost(p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return sgpu::fail(SGPU_ERR_CUDA, "cudaFreeHost failed");
+    }
+    return SGPU_OK;
+}
 
 SGPU_EXPORT int sgpu_abi_version(void) { return SGPU_ABI_VERSION; }
 

@@ -6,6 +6,9 @@
 //   InterpolatingFIRFilter::execute_block filter/fir/interp.rs:102-111 -> pfb.rs:85-90
 //   Window::push / to_vec               window/mod.rs:63-71,44-51  (history: hist_update_kernel)
 //   DotProduct::execute                 dot_product/mod.rs:159-170 (fir_core.cuh)
+#include <map>
+#include <mutex>
+
 #include "fir_core.cuh"
 #include "fir_tc.cuh"
 #include "nco.cuh"
@@ -662,9 +665,19 @@ SGPU_EXPORT int sgpu_fir_coefficients(const sgpu_fir *f, double *out) { return s
 
 namespace {
 
+// cudaFuncSetAttribute is a driver round trip (~1 us): remember the largest size set per (device, kernel)
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
+    static std::mutex m;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_pair(dev, reinterpret_cast<const void *>(kernel));
+    std::lock_guard<std::mutex> lock(m);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return SGPU_OK;
     SGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
     return SGPU_OK;
 }
 

@@ -201,29 +201,60 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
             }
         }
     };
-    // MIX: every element of the tile this lane loaded that belongs to this call's input gets its phasor
+    // MIX: every sample of the tile that belongs to this call's input is multiplied by conj(phasor) IN PLACE, one
+    // float4 (positions j, j + 1 of one phase plane = input samples i, i + M) per step: lane -> (plane, position pair),
+    // rows in batches of five so that the shared-memory latencies overlap.
     unsigned nco_theta = 0, nco_delta = 0;
     if constexpr (MIX) nco_channel(a, ch, nco_theta, nco_delta);
     auto mix_tile = [&](const long long m_base) {
         const long long i_lo = (m_base - Qpad) * M - a.c0;
-        float2 *base = reinterpret_cast<float2 *>(stage);
-        const unsigned d_row = (unsigned)RM * nco_delta, d_k = 32u * nco_delta;
-        unsigned th_row = nco_theta + (unsigned)(i_lo + lane) * nco_delta + (1u << 21);  // rounding folded in
-        long long i = i_lo + lane;
-        for (int rho = 0; rho < rows; ++rho) {
-            unsigned th = th_row;
+        const bool interior = i_lo >= 0 && i_lo + (long long)rows * RM <= a.n_in;
+        const unsigned d_row = (unsigned)RM * nco_delta, d_m = (unsigned)M * nco_delta;
+        constexpr int COMBOS = M * (R / 2);
 #pragma unroll
-            for (int k = 0; k < LPRW; ++k) {
-                const long long ii = i + k * 32;
-                if (ii >= 0 && ii < a.n_in) {
-                    float2 *p = base + eoff[k] + 2 * rho;
-                    const float2 x = *p, cs = lut_s[th >> 22];
-                    *p = make_float2(fmaf(cs.x, x.x, cs.y * x.y), fmaf(cs.x, x.y, -cs.y * x.x));
+        for (int c0 = 0; c0 < COMBOS; c0 += 32) {
+            const int c = c0 + lane;
+            if (COMBOS % 32 != 0 && c >= COMBOS) break;
+            const int p = c % M, jp = c / M;
+            float4 *cell = stage + p * plane_f4 + jp * RS;
+            const int e0 = 2 * jp * M + (M - 1 - p);  // offset of the pair's first sample inside a row of all planes
+            unsigned th = nco_theta + (unsigned)(i_lo + e0) * nco_delta + (1u << 21);  // rounding folded in
+            long long i0 = i_lo + e0;
+            auto mix1 = [&](float &xr, float &xi, const float2 cs) {  // conj(c + j s) x  (nco/mod.rs:147-151)
+                const float r = fmaf(cs.x, xr, cs.y * xi), i = fmaf(cs.x, xi, -cs.y * xr);
+                xr = r;
+                xi = i;
+            };
+            constexpr int NB = 5;  // rows per batch: 5 cells and 10 table entries in flight per lane
+            int rho = 0;
+            if (interior) {
+                for (; rho + NB <= rows; rho += NB) {
+                    float4 v[NB];
+                    float2 t0[NB], t1[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        v[b] = cell[rho + b];
+                        t0[b] = lut_s[(th + (unsigned)b * d_row) >> 22];
+                        t1[b] = lut_s[(th + (unsigned)b * d_row + d_m) >> 22];
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        mix1(v[b].x, v[b].y, t0[b]);
+                        mix1(v[b].z, v[b].w, t1[b]);
+                        cell[rho + b] = v[b];
+                    }
+                    th += NB * d_row;
                 }
-                th += d_k;
+                i0 += (long long)rho * RM;
             }
-            th_row += d_row;
-            i += RM;
+            for (; rho < rows; ++rho) {
+                float4 v = cell[rho];
+                if (interior || (i0 >= 0 && i0 < a.n_in)) mix1(v.x, v.y, lut_s[th >> 22]);
+                if (interior || (i0 + M >= 0 && i0 + M < a.n_in)) mix1(v.z, v.w, lut_s[(th + d_m) >> 22]);
+                cell[rho] = v;
+                th += d_row;
+                i0 += RM;
+            }
         }
     };
     const int g = lane / PS, part = lane % PS;
@@ -237,7 +268,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_decim_warp_kernel(const Fir
 #pragma unroll 1
     for (int t = 0; t < TPW && m_base < a.n_out; ++t, m_base += STEP) {
         cp_async_wait_all();
-        if constexpr (MIX) mix_tile(m_base);  // each lane touches only what it loaded itself: no barrier in front
+        if constexpr (MIX) {
+            __syncwarp();  // the tile has landed for every lane
+            mix_tile(m_base);
+        }
         __syncwarp();
         float2 acc[R];
 #pragma unroll

@@ -70,8 +70,27 @@ struct HostPipe {
 size_t host_chunk_len(size_t C, size_t n_in);
 
 template <class OutLen, class Run>
+int host_pipeline_body(HostPipe &hp, size_t C, const float *in, size_t n_in, size_t in_stride, float *out,
+                       size_t out_stride, size_t max_out_per_in, OutLen out_len, Run run, cudaStream_t s);
+
+// On any error the three streams are drained before the call returns: no copy into the caller's `out` (or out of
+// `in`) is still in flight when the caller sees the status.
+template <class OutLen, class Run>
 int host_pipeline(HostPipe &hp, size_t C, const float *in, size_t n_in, size_t in_stride, float *out,
                   size_t out_stride, size_t max_out_per_in, OutLen out_len, Run run, cudaStream_t s) {
+    const int st = host_pipeline_body(hp, C, in, n_in, in_stride, out, out_stride, max_out_per_in, out_len, run, s);
+    if (st != SGPU_OK) {
+        if (hp.s_in) cudaStreamSynchronize(hp.s_in);
+        cudaStreamSynchronize(s);
+        if (hp.s_out) cudaStreamSynchronize(hp.s_out);
+        (void)cudaGetLastError();
+    }
+    return st;
+}
+
+template <class OutLen, class Run>
+int host_pipeline_body(HostPipe &hp, size_t C, const float *in, size_t n_in, size_t in_stride, float *out,
+                       size_t out_stride, size_t max_out_per_in, OutLen out_len, Run run, cudaStream_t s) {
     const size_t chunk = host_chunk_len(C, n_in);
     const size_t max_out = chunk * max_out_per_in + 1;
     int st = hp.ensure(C * chunk * 8, C * max_out * 8);
