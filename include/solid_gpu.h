@@ -82,6 +82,8 @@ typedef struct sgpu_interp sgpu_interp; /* InterpolatingFIRFilter (+ its PolyPha
 typedef struct sgpu_iir sgpu_iir;       /* IIRFilter / Decimating- / InterpolatingIIRFilter   */
 typedef struct sgpu_dot sgpu_dot;       /* DotProduct                              */
 typedef struct sgpu_autocorr sgpu_autocorr; /* AutoCorrelator                      */
+typedef struct sgpu_ctx sgpu_ctx;         /* a set of GPUs of this box                */
+typedef struct sgpu_sharded sgpu_sharded; /* one filter object spread over a context   */
 typedef struct sgpu_nco sgpu_nco;       /* NCO (one phase accumulator per channel) */
 typedef struct sgpu_ddc sgpu_ddc;       /* NCO mix-down -> DecimatingFIRFilter      */
 
@@ -332,6 +334,41 @@ int sgpu_ddc_write(sgpu_ddc *d, const float *in, size_t n_in, size_t in_stride, 
                    void *stream);        /* mixed, pushed, no output (decim.rs:136-139) */
 int sgpu_ddc_reset(sgpu_ddc *d);         /* NCO::reset + the decimator's window and counter */
 int sgpu_ddc_last_fused(const sgpu_ddc *d); /* 1: the last call mixed inside the decimator kernel */
+
+/* ---- multi-GPU context -----------------------------------------
+ * One caller thread, host buffers, several GPUs behind one filter object: what a caller like
+ * the reference's main.rs:39-41 (one Vec in, one Vec out) needs to use the whole box.
+ *   - C > 1 channels (independent reference objects): contiguous channel ranges per GPU.
+ *   - one FIR / decimating-FIR stream (C == 1): contiguous time segments per call; segment
+ *     d > 0 starts where the decimator's counter is 0 (fir/decim.rs:221-228) and is primed with
+ *     the T-1 samples in front of it, sliced from the caller's buffer.  Calls too short to
+ *     give every GPU 65536 samples use fewer GPUs.  One IIR stream stays on the first GPU.
+ *   - every GPU writes its outputs into the caller's one host buffer (that is the gather: no
+ *     collective on this path); results and streaming state are those of the single handle.
+ * sgpu_ctx_create(0, ..) takes every visible GPU; sgpu_ctx_create_devices takes an explicit
+ * list, in which a device may appear more than once (several shards on one GPU). */
+int sgpu_ctx_create(int n_gpus, sgpu_ctx **out);
+int sgpu_ctx_create_devices(const int *devices, int n, sgpu_ctx **out);
+int sgpu_ctx_destroy(sgpu_ctx *ctx);
+int sgpu_ctx_devices(const sgpu_ctx *ctx);
+int sgpu_ctx_fir_create(sgpu_ctx *ctx, const double *taps, size_t n_taps, sgpu_tapkind kind,
+                        size_t n_channels, double scale_re, double scale_im, int is_decimator,
+                        size_t decimation, sgpu_sharded **out);       /* fir/mod.rs:79, decim.rs:27 */
+int sgpu_ctx_interp_create(sgpu_ctx *ctx, const double *taps, size_t n_taps, sgpu_tapkind kind,
+                           size_t n_channels, size_t interpolation, sgpu_sharded **out); /* interp.rs:27 */
+int sgpu_ctx_iir_create(sgpu_ctx *ctx, sgpu_iirtype type, const double *ff, size_t n_ff,
+                        const double *fb, size_t n_fb, size_t n_channels, sgpu_iirwrap wrap,
+                        size_t factor, sgpu_sharded **out);           /* iir/mod.rs:92 */
+int sgpu_sharded_destroy(sgpu_sharded *f);
+int sgpu_sharded_shards(const sgpu_sharded *f);
+int sgpu_sharded_shard_info(const sgpu_sharded *f, int index, int *device, size_t *first_channel,
+                            size_t *n_channels);
+int sgpu_sharded_last_segments(const sgpu_sharded *f); /* GPUs the last call really used */
+size_t sgpu_sharded_out_len(const sgpu_sharded *f, size_t n_in);
+int sgpu_sharded_reset(sgpu_sharded *f);
+/* Filter::execute_block (filter/mod.rs:14) over host buffers; returns when `out` is complete */
+int sgpu_sharded_execute_block(sgpu_sharded *f, const float *in, size_t n_in, size_t in_stride,
+                               float *out, size_t out_stride, size_t *n_out);
 
 /* ---- sharding helpers (pure host arithmetic; no collective) --------------------------
  * Channels: contiguous ranges, remainder spread over the first ranks.

@@ -42,6 +42,8 @@ pub const SGPU_IIR_INTERPOLATING: c_int = 2;
 #[repr(C)] pub struct sgpu_dot { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_autocorr { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_nco { _private: [u8; 0] }
+#[repr(C)] pub struct sgpu_ctx { _private: [u8; 0] }
+#[repr(C)] pub struct sgpu_sharded { _private: [u8; 0] }
 #[repr(C)] pub struct sgpu_ddc { _private: [u8; 0] }
 pub const SGPU_ALL_CHANNELS: size_t = usize::MAX;
 
@@ -188,6 +190,28 @@ extern "C" {
                           mem: c_int, stream: *mut c_void) -> c_int;
     pub fn sgpu_ddc_reset(d: *mut sgpu_ddc) -> c_int;
     pub fn sgpu_ddc_last_fused(d: *const sgpu_ddc) -> c_int;
+
+    pub fn sgpu_ctx_create(n_gpus: c_int, out: *mut *mut sgpu_ctx) -> c_int;
+    pub fn sgpu_ctx_create_devices(devices: *const c_int, n: c_int, out: *mut *mut sgpu_ctx) -> c_int;
+    pub fn sgpu_ctx_destroy(ctx: *mut sgpu_ctx) -> c_int;
+    pub fn sgpu_ctx_devices(ctx: *const sgpu_ctx) -> c_int;
+    pub fn sgpu_ctx_fir_create(ctx: *mut sgpu_ctx, taps: *const c_double, n_taps: size_t, kind: c_int, n_channels: size_t,
+                               scale_re: c_double, scale_im: c_double, is_decimator: c_int, decimation: size_t,
+                               out: *mut *mut sgpu_sharded) -> c_int;
+    pub fn sgpu_ctx_interp_create(ctx: *mut sgpu_ctx, taps: *const c_double, n_taps: size_t, kind: c_int,
+                                  n_channels: size_t, interpolation: size_t, out: *mut *mut sgpu_sharded) -> c_int;
+    pub fn sgpu_ctx_iir_create(ctx: *mut sgpu_ctx, kind: c_int, ff: *const c_double, n_ff: size_t, fb: *const c_double,
+                               n_fb: size_t, n_channels: size_t, wrap: c_int, factor: size_t,
+                               out: *mut *mut sgpu_sharded) -> c_int;
+    pub fn sgpu_sharded_destroy(f: *mut sgpu_sharded) -> c_int;
+    pub fn sgpu_sharded_shards(f: *const sgpu_sharded) -> c_int;
+    pub fn sgpu_sharded_shard_info(f: *const sgpu_sharded, index: c_int, device: *mut c_int, first_channel: *mut size_t,
+                                   n_channels: *mut size_t) -> c_int;
+    pub fn sgpu_sharded_last_segments(f: *const sgpu_sharded) -> c_int;
+    pub fn sgpu_sharded_out_len(f: *const sgpu_sharded, n_in: size_t) -> size_t;
+    pub fn sgpu_sharded_reset(f: *mut sgpu_sharded) -> c_int;
+    pub fn sgpu_sharded_execute_block(f: *mut sgpu_sharded, input: *const c_float, n_in: size_t, in_stride: size_t,
+                                      out: *mut c_float, out_stride: size_t, n_out: *mut size_t) -> c_int;
 
     pub fn sgpu_shard_channels(n_channels: size_t, world: c_int, rank: c_int, first: *mut size_t,
                                count: *mut size_t) -> c_int;

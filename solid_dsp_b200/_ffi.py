@@ -156,6 +156,20 @@ PROTOTYPES = {
     "sgpu_ddc_write": (C.c_int, [vp, vp, c_size, c_size, C.c_int, vp]),
     "sgpu_ddc_reset": (C.c_int, [vp]),
     "sgpu_ddc_last_fused": (C.c_int, [vp]),
+    "sgpu_ctx_create": (C.c_int, [C.c_int, vpp]),
+    "sgpu_ctx_create_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int, vpp]),
+    "sgpu_ctx_destroy": (C.c_int, [vp]),
+    "sgpu_ctx_devices": (C.c_int, [vp]),
+    "sgpu_ctx_fir_create": (C.c_int, [vp, c_dp, c_size, C.c_int, c_size, C.c_double, C.c_double, C.c_int, c_size, vpp]),
+    "sgpu_ctx_interp_create": (C.c_int, [vp, c_dp, c_size, C.c_int, c_size, c_size, vpp]),
+    "sgpu_ctx_iir_create": (C.c_int, [vp, C.c_int, c_dp, c_size, c_dp, c_size, c_size, C.c_int, c_size, vpp]),
+    "sgpu_sharded_destroy": (C.c_int, [vp]),
+    "sgpu_sharded_shards": (C.c_int, [vp]),
+    "sgpu_sharded_shard_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), c_sizep, c_sizep]),
+    "sgpu_sharded_last_segments": (C.c_int, [vp]),
+    "sgpu_sharded_out_len": (c_size, [vp, c_size]),
+    "sgpu_sharded_reset": (C.c_int, [vp]),
+    "sgpu_sharded_execute_block": (C.c_int, [vp, vp, c_size, c_size, vp, c_size, c_sizep]),
     "sgpu_shard_channels": (C.c_int, [c_size, C.c_int, C.c_int, c_sizep, c_sizep]),
     "sgpu_shard_stream": (C.c_int, [c_size, c_size, C.c_int, C.c_int, c_sizep, c_sizep]),
 }
