@@ -642,7 +642,8 @@ def run_gpu_arm(args):
     # ---- the other BASELINE configs (default run, one GPU): driver-visible numbers for every config
     if name == "fir" and world == 1 and args.log2_samples == 30 and not args.no_workloads:
         block = {}
-        for other in ("fir64", "decim", "interp", "iir_batch", "iir_scan", "ddc"):
+        side = os.environ.get("SGPU_BENCH_SIDE", "fir64,decim,interp,iir_batch,iir_scan,ddc").split(",")
+        for other in [w for w in side if w in WORKLOADS and w != "fir"]:
             try:
                 block[other] = run_side_workload(other, args, dev, dist)
             except Exception as e:  # noqa: BLE001  (a failing side workload must not take the headline line with it)
