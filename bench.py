@@ -142,6 +142,11 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        """Evaluate only the samples delivered from now on."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -173,7 +178,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             p = [t.strip() for t in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -452,27 +457,36 @@ class Workload:
         """W warm-up steps, K timed steps between barriers; device time, max over ranks."""
         torch, dist = self.torch, self.dist
         from solid_dsp_b200 import launch_count
-        for _ in range(warmup):
-            self.step()
-        self.barrier()
+        # the clock sampler starts BEFORE the warm-up (nvidia-smi needs a few hundred ms to deliver its first line: waiting
+        # for it between the warm-up and the timed steps would let the GPU fall idle right before the timed region); only
+        # the lines that arrive after the timed region has started are evaluated
         sampler = None
         if self.rank == 0 and sample_clocks:
             sampler = ClockSampler(self.dev.index)
             sampler.start()
             sampler.wait_first()
+        # the warm-up keeps its result alive across the next step exactly like the timed loop does: a step's output (32 GiB
+        # for the interpolator) is allocated while the previous one is still referenced, so the caching allocator needs TWO
+        # blocks -- a warm-up that dropped each result at once left the second cudaMalloc (~100 ms) inside timed step 2
+        y = None
+        for _ in range(warmup):
+            y = self.step()
+        self.barrier()
+        if sampler is not None:
+            sampler.mark()
         self.kernel_events = []
         l0 = launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         e0.record()
-        y = None
         for _ in range(steps):
             y = self.step()
         e1.record()
         self.barrier()
         ms_total = e0.elapsed_time(e1)
         # workloads without per-call events (fir64: the step is one C call) time the kernel as the step
-        ms_kernel = sum(a.elapsed_time(b) for a, b in self.kernel_events) / steps if self.kernel_events else ms_total / steps
+        per_step = [a.elapsed_time(b) for a, b in self.kernel_events]
+        ms_kernel = sum(per_step) / steps if per_step else ms_total / steps
         launches = launch_count() - l0
         if self.world > 1:
             t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=self.dev)
@@ -496,7 +510,7 @@ class Workload:
         self.last_y = y
         ms_step = ms_total / steps
         return {"ms_step": ms_step, "ms_kernel": ms_kernel, "value": self.units_total / (ms_step * 1e-3) / 1e9,
-                "launches": launches, "clocks": clocks}
+                "launches": launches, "clocks": clocks, "kernel_ms_steps": [round(v, 4) for v in per_step[:64]]}
 
     def parity(self):
         """Oracle check of the timed buffers on EVERY rank (the first outputs of rank r > 0 depend on the halo it
@@ -615,6 +629,7 @@ def run_gpu_arm(args):
     line = None
     if rank == 0:
         roofline, on_tensor = wl.roofline(res["ms_kernel"])
+        roofline["kernel_ms_steps"] = res["kernel_ms_steps"]
         cpu = None
         if world == 1 and not args.no_cpu:
             rate1, what1, _ = cpu_reference_path(name, 1, args.cpu_seconds)
@@ -671,7 +686,8 @@ def run_side_workload(name, args, dev, dist):
         rate1, what1, _ = cpu_reference_path(name, 1, min(args.cpu_seconds, 3.0))
         cpu = {"value": rate1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": what1}
     out = {"config": workload_config(name, 1, args.log2_samples), "value": res["value"], "unit": UNIT, "steps": steps,
-           "warmup": 3, "ms_per_step": res["ms_step"], "kernel_ms": res["ms_kernel"], "gpu_launches": res["launches"],
+           "warmup": 3, "ms_per_step": res["ms_step"], "kernel_ms": res["ms_kernel"], "kernel_ms_steps": res["kernel_ms_steps"],
+           "gpu_launches": res["launches"],
            "clocks": res["clocks"],
            "roofline": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel")},
            "roofline_frac_fma": roofline["fma"]["frac"], "roofline_frac_hbm": roofline["hbm"]["frac"],
