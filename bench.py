@@ -654,18 +654,39 @@ def run_gpu_arm(args):
     del wl
     gc.collect()
     torch.cuda.empty_cache()
-    # ---- the other BASELINE configs (default run, one GPU): driver-visible numbers for every config
-    if name == "fir" and world == 1 and args.log2_samples == 30 and not args.no_workloads:
+    # ---- the other BASELINE configs: driver-visible numbers for every config.  One GPU: all of them, with a 1-core CPU
+    # baseline each.  N > 1: the channel-sharded ones (contiguous channel ranges, no data-path collective),
+    # oracle parity on EVERY rank -- so that the driver's scaling run carries them too.
+    if name == "fir" and args.log2_samples == 30 and not args.no_workloads:
+        default_side = "fir64,decim,interp,iir_batch,iir_scan,ddc" if world == 1 else "decim,interp,iir_batch"
+        side = [w for w in os.environ.get("SGPU_BENCH_SIDE", default_side).split(",") if w in WORKLOADS and w != "fir"]
         block = {}
-        side = os.environ.get("SGPU_BENCH_SIDE", "fir64,decim,interp,iir_batch,iir_scan,ddc").split(",")
-        for other in [w for w in side if w in WORKLOADS and w != "fir"]:
+        guard = None
+        if world > 1:
+            # a rank that fails alone would leave the others in a collective: after `side_timeout` seconds every rank gives
+            # up on the block, rank 0 still prints the headline line (the block says what happened), exit code 0
+            def give_up(why=None):
+                if rank == 0:
+                    line["workloads"] = dict(block, error=why or f"side workloads did not finish within {args.side_timeout:.0f} s")
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+            guard = threading.Timer(args.side_timeout, give_up)
+            guard.daemon = True
+            guard.start()
+        for other in side:
             try:
-                block[other] = run_side_workload(other, args, dev, dist)
+                res_o = run_side_workload(other, args, dev, dist, world, rank)
             except Exception as e:  # noqa: BLE001  (a failing side workload must not take the headline line with it)
-                block[other] = {"error": f"{type(e).__name__}: {e}"}
+                res_o = {"error": f"{type(e).__name__}: {e}"}
+                if world > 1:  # the other ranks are inside this workload's collectives: their timers end them, exit code 0
+                    give_up(f"rank {rank}, {other}: {res_o['error']}")
+            block[other] = res_o
             gc.collect()
             torch.cuda.empty_cache()
-        line["workloads"] = block
+        if guard is not None:
+            guard.cancel()
+        if rank == 0:
+            line["workloads"] = block
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -673,19 +694,22 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def run_side_workload(name, args, dev, dist):
+def run_side_workload(name, args, dev, dist, world=1, rank=0):
     """One of the other BASELINE configs at its full size, about 5 s: device-resident value, kernel time, both roofline
-    denominators, oracle parity, clocks, 1-core cpu_baseline."""
-    wl = Workload(name, args, 1, 0, dev, dist)
+    denominators, oracle parity (every rank), clocks, 1-core cpu_baseline (one GPU only)."""
+    wl = Workload(name, args, world, rank, dev, dist)
     steps = 200 if name == "fir64" else 10
     res = wl.run_timed(3, steps)
     parity = None if args.no_check else wl.parity()
+    if rank != 0:
+        return None
     roofline, _ = wl.roofline(res["ms_kernel"])
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         rate1, what1, _ = cpu_reference_path(name, 1, min(args.cpu_seconds, 3.0))
         cpu = {"value": rate1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "sample": what1}
-    out = {"config": workload_config(name, 1, args.log2_samples), "value": res["value"], "unit": UNIT, "steps": steps,
+    out = {"config": workload_config(name, world, args.log2_samples), "value": res["value"], "unit": UNIT, "n_gpus": world,
+           "scaling": "weak" if name == "fir64" else "strong", "steps": steps,
            "warmup": 3, "ms_per_step": res["ms_step"], "kernel_ms": res["ms_kernel"], "kernel_ms_steps": res["kernel_ms_steps"],
            "gpu_launches": res["launches"],
            "clocks": res["clocks"],
@@ -883,6 +907,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the block of the other BASELINE configs")
+    ap.add_argument("--side-timeout", type=float, default=240.0,
+                    help="N > 1: seconds the block of side workloads may take before the headline line is printed without it")
     ap.add_argument("--watchdog", type=float, default=1500.0, help="seconds after which a stuck run dumps its stacks and exits 3")
     args = ap.parse_args()
     import faulthandler

@@ -494,5 +494,32 @@ class AutoCorrelator {
     sgpu_autocorr *h_ = nullptr;
 };
 }  // namespace auto_correlator
+
+// ------------------------------------------------------------------------------------------------
+namespace firdes {
+
+enum class FirdesErrorCode { Bandwidth, StopBandLevel, Mu };  // firdes/mod.rs:17-25 (those firdes_kaiser returns)
+
+struct FirdesError : std::runtime_error {
+    FirdesErrorCode code;
+    explicit FirdesError(FirdesErrorCode c) : std::runtime_error("Firdes Error"), code(c) {}
+};
+
+// firdes_kaiser -- firdes/mod.rs:278-305, computed on the GPU (sgpu_firdes_kaiser)
+inline std::vector<double> firdes_kaiser(size_t filter_length, double cutoff_frequency, double stop_band_attenuation,
+                                         double fractional_sample_offset) {
+    std::vector<double> h(filter_length);
+    const int st = sgpu_firdes_kaiser(filter_length, &cutoff_frequency, &stop_band_attenuation, &fractional_sample_offset, 1,
+                                      h.data(), SGPU_HOST, nullptr);
+    switch (st) {
+        case SGPU_OK: return h;
+        case SGPU_ERR_FIRDES_BANDWIDTH: throw FirdesError(FirdesErrorCode::Bandwidth);
+        case SGPU_ERR_FIRDES_STOP_BAND_LEVEL: throw FirdesError(FirdesErrorCode::StopBandLevel);
+        case SGPU_ERR_FIRDES_MU: throw FirdesError(FirdesErrorCode::Mu);
+        default: throw GpuError(st);
+    }
+}
+
+}  // namespace firdes
 }  // namespace filter
 }  // namespace solid

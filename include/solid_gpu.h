@@ -60,6 +60,10 @@ typedef enum sgpu_status {
     SGPU_ERR_IIR_INTERPOLATION_LESS_THAN_ONE = -16,
     /* iir/sos.rs:18-21  SecondOrderErrorCode::CoefficientsNotInRange */
     SGPU_ERR_SOS_COEFFICIENTS_NOT_IN_RANGE = -17,
+    /* firdes/mod.rs:17-25  FirdesErrorCode (the variants firdes_kaiser can return, :284-290) */
+    SGPU_ERR_FIRDES_BANDWIDTH = -20,
+    SGPU_ERR_FIRDES_STOP_BAND_LEVEL = -21,
+    SGPU_ERR_FIRDES_MU = -22,
     /* library-side */
     SGPU_ERR_INVALID_ARGUMENT = -30,
     SGPU_ERR_CAPACITY = -31, /* `out` too small for the outputs this call produces */
@@ -293,6 +297,17 @@ int sgpu_dot_coefficients(const sgpu_dot *d, double *out); /* dot_product/mod.rs
  * length n_x each (vector v at x + v*x_stride); result[v] cf32. */
 int sgpu_dot_execute(sgpu_dot *d, const float *x, size_t n_x, size_t x_stride, size_t n_vec,
                      float *result, sgpu_mem mem, void *stream);
+
+/* ---- tap design on the device ---------------------------------------
+ * firdes_kaiser (firdes/mod.rs:278-305; kaiser_beta :243-253, windows/kaiser.rs:33-46, math/mod.rs:17-27,41-100,
+ * 171-183) for n_designs filters of filter_length taps each in one launch, f64, one thread per tap: design d uses
+ * cutoff_frequency[d], stop_band_attenuation[d], fractional_sample_offset[d] (host arrays; the last may be NULL = 0)
+ * and writes out[d * filter_length ..] (`mem` says where `out` lives; SGPU_HOST returns after the copy).  The result
+ * is what sgpu_fir_create / _create_per_channel take as `taps`.  Errors in the reference's order (:284-290):
+ * SGPU_ERR_FIRDES_MU, _BANDWIDTH, _STOP_BAND_LEVEL. */
+int sgpu_firdes_kaiser(size_t filter_length, const double *cutoff_frequency, const double *stop_band_attenuation,
+                       const double *fractional_sample_offset, size_t n_designs, double *out, sgpu_mem mem,
+                       void *stream);
 
 /* ---- NCO (nco/mod.rs) and the digital down-converter ----------------------------------
  * the per-sample step next to the decimator.  An sgpu_nco is C reference NCO

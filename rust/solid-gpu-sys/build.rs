@@ -11,7 +11,7 @@ fn main() {
     let cuda_home = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
     let nvcc = PathBuf::from(&cuda_home).join("bin/nvcc");
     // keep in step with SRCS in solid_dsp_b200/csrc/Makefile
-    let sources = ["common.cu", "fir.cu", "fir_tc.cu", "iir.cu", "dot.cu", "autocorr.cu", "nco.cu", "ctx.cu"];
+    let sources = ["common.cu", "fir.cu", "fir_tc.cu", "iir.cu", "dot.cu", "autocorr.cu", "nco.cu", "ctx.cu", "firdes.cu"];
     let mut objects = Vec::new();
     for src in sources.iter() {
         let obj = out.join(format!("{}.o", src));

@@ -17,6 +17,9 @@ pub const SGPU_ERR_IIR_SOS_SIZE_NOT_MULTIPLE_OF_3: c_int = -14;
 pub const SGPU_ERR_IIR_DECIMATION_LESS_THAN_ONE: c_int = -15;
 pub const SGPU_ERR_IIR_INTERPOLATION_LESS_THAN_ONE: c_int = -16;
 pub const SGPU_ERR_SOS_COEFFICIENTS_NOT_IN_RANGE: c_int = -17;
+pub const SGPU_ERR_FIRDES_BANDWIDTH: c_int = -20;
+pub const SGPU_ERR_FIRDES_STOP_BAND_LEVEL: c_int = -21;
+pub const SGPU_ERR_FIRDES_MU: c_int = -22;
 pub const SGPU_ERR_INVALID_ARGUMENT: c_int = -30;
 pub const SGPU_ERR_CAPACITY: c_int = -31;
 pub const SGPU_ERR_CUDA: c_int = -32;
@@ -159,6 +162,9 @@ extern "C" {
     pub fn sgpu_host_alloc(bytes: size_t, device: c_int, out: *mut *mut c_void) -> c_int;
     pub fn sgpu_host_free(p: *mut c_void) -> c_int;
 
+    pub fn sgpu_firdes_kaiser(filter_length: size_t, cutoff_frequency: *const f64, stop_band_attenuation: *const f64,
+                              fractional_sample_offset: *const f64, n_designs: size_t, out: *mut f64, mem: c_int,
+                              stream: *mut c_void) -> c_int;
     pub fn sgpu_nco_create(n_channels: size_t, out: *mut *mut sgpu_nco) -> c_int;
     pub fn sgpu_nco_destroy(n: *mut sgpu_nco) -> c_int;
     pub fn sgpu_nco_clone(n: *const sgpu_nco, out: *mut *mut sgpu_nco) -> c_int;

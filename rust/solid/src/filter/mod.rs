@@ -13,3 +13,4 @@ pub mod fir;
 pub mod iir;
 pub mod auto_correlator;
 pub mod ddc;
+pub mod firdes;

@@ -37,6 +37,9 @@ ERR_IIR_SOS_SIZE_NOT_MULTIPLE_OF_3 = -14
 ERR_IIR_DECIMATION_LESS_THAN_ONE = -15
 ERR_IIR_INTERPOLATION_LESS_THAN_ONE = -16
 ERR_SOS_COEFFICIENTS_NOT_IN_RANGE = -17
+ERR_FIRDES_BANDWIDTH = -20
+ERR_FIRDES_STOP_BAND_LEVEL = -21
+ERR_FIRDES_MU = -22
 ERR_INVALID_ARGUMENT = -30
 ERR_CAPACITY = -31
 ERR_CUDA = -32
@@ -132,6 +135,7 @@ PROTOTYPES = {
     "sgpu_dot_len": (c_size, [vp]),
     "sgpu_dot_coefficients": (C.c_int, [vp, c_dp]),
     "sgpu_dot_execute": (C.c_int, [vp, vp, c_size, c_size, c_size, vp, C.c_int, vp]),
+    "sgpu_firdes_kaiser": (C.c_int, [c_size, c_dp, c_dp, c_dp, c_size, vp, C.c_int, vp]),
     "sgpu_nco_create": (C.c_int, [c_size, vpp]),
     "sgpu_nco_destroy": (C.c_int, [vp]),
     "sgpu_nco_clone": (C.c_int, [vp, vpp]),

@@ -214,6 +214,9 @@ SGPU_EXPORT const char *sgpu_status_name(int s) {
         case SGPU_ERR_IIR_DECIMATION_LESS_THAN_ONE: return "IIRErrorCode::DecimationLessThanOne";
         case SGPU_ERR_IIR_INTERPOLATION_LESS_THAN_ONE: return "IIRErrorCode::InterpolationLessThanOne";
         case SGPU_ERR_SOS_COEFFICIENTS_NOT_IN_RANGE: return "SecondOrderErrorCode::CoefficientsNotInRange";
+        case SGPU_ERR_FIRDES_BANDWIDTH: return "FirdesErrorCode::Bandwidth";
+        case SGPU_ERR_FIRDES_STOP_BAND_LEVEL: return "FirdesErrorCode::StopBandLevel";
+        case SGPU_ERR_FIRDES_MU: return "FirdesErrorCode::Mu";
         case SGPU_ERR_INVALID_ARGUMENT: return "SGPU_ERR_INVALID_ARGUMENT";
         case SGPU_ERR_CAPACITY: return "SGPU_ERR_CAPACITY";
         case SGPU_ERR_CUDA: return "SGPU_ERR_CUDA";

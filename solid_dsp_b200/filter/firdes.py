@@ -71,7 +71,8 @@ def kaiser(index: int, window_length: int, beta: float) -> float:  # windows/kai
     if beta < 0.0:
         raise WindowError("BetaLessThanZero")
     t = float(index) - float(window_length - 1) / 2.0
-    r = 2.0 * t / float(window_length - 1)
+    den = float(window_length - 1)
+    r = 2.0 * t / den if den != 0.0 else float("nan")  # a 1-tap window: 0.0 / 0.0 = NaN in the reference's f64 arithmetic
     return besseli(beta * math.sqrt(1.0 - r * r), 0.0) / besseli(beta, 0.0)
 
 
@@ -148,3 +149,38 @@ def filter_crosscorrelation(h, g, lag: int) -> float:  # firdes/mod.rs:487-526
     for i in range(n):
         r += h[ih + i] * g[ig + i]
     return r
+
+
+def firdes_kaiser_device(filter_length: int, cutoff_frequency, stop_band_attenuation, fractional_sample_offset=0.0,
+                         device_out=None, stream=None):
+    """firdes_kaiser (firdes/mod.rs:278-305) computed ON THE GPU (sgpu_firdes_kaiser, csrc/firdes.cu): one design, or
+    one design per element when the parameters are sequences (a bank of per-channel filters in one launch).  Returns a
+    list of taps (a list of lists for several designs), or fills `device_out` (a torch float64 CUDA tensor of shape
+    [n_designs, filter_length]) and returns it.  Raises FirdesError with the reference's variants."""
+    import ctypes as C
+    from .. import _ffi
+    many = hasattr(cutoff_frequency, "__len__")
+    fc = [float(v) for v in (cutoff_frequency if many else [cutoff_frequency])]
+    n = len(fc)
+
+    def arr(v):
+        vals = [float(t) for t in v] if hasattr(v, "__len__") else [float(v)] * n
+        if len(vals) != n:
+            raise ValueError("firdes_kaiser_device: parameter sequences of different lengths")
+        return (C.c_double * n)(*vals)
+    a_fc, a_as, a_mu = arr(fc), arr(stop_band_attenuation), arr(fractional_sample_offset)
+    if device_out is not None:
+        assert device_out.is_cuda and device_out.numel() == n * filter_length and device_out.is_contiguous()
+        out_ptr, mem = C.c_void_p(device_out.data_ptr()), _ffi.DEVICE
+    else:
+        host = (C.c_double * max(n * filter_length, 1))()
+        out_ptr, mem = C.cast(host, C.c_void_p), _ffi.HOST
+    st = _ffi.lib.sgpu_firdes_kaiser(filter_length, a_fc, a_as, a_mu, n, out_ptr, mem, stream)
+    if st in (_ffi.ERR_FIRDES_MU, _ffi.ERR_FIRDES_BANDWIDTH, _ffi.ERR_FIRDES_STOP_BAND_LEVEL):
+        raise FirdesError({_ffi.ERR_FIRDES_MU: "Mu", _ffi.ERR_FIRDES_BANDWIDTH: "Bandwidth",
+                           _ffi.ERR_FIRDES_STOP_BAND_LEVEL: "StopBandLevel"}[st])
+    _ffi.check(st)
+    if device_out is not None:
+        return device_out
+    rows = [list(host[d * filter_length:(d + 1) * filter_length]) for d in range(n)]
+    return rows if many else rows[0]
