@@ -531,6 +531,24 @@ struct sgpu_fir {
     int last_mix_fused = 0;
 };
 
+// Is this call long enough for the tensor kernel?  A tensor tile (16384 outputs, one CTA) takes 16-30 us from the first
+// sample load to the last store whatever the call size, and the band load, TMEM allocation and the second launch add to
+// it, so calls that do not fill the chip are served faster by the FFMA2 kernel, whose short-call geometry is one 512-output
+// tile per warp.  Measured per-call completion times, back-to-back calls with device pointers
+// (tools/call_size_crossover.py; tensor / FFMA2 in us):
+//   128 taps:  2^19 24.8 / 10.5   2^20 24.9 / 16.7   2^21 26.9 / 25.8   2^22 41.2 /  47.2   2^23  66 /   89
+//   512 taps:  2^17 28.7 / 18.5   2^18 30.6 / 18.5   2^19 31.0 / 26.8   2^20 31.1 /  47.4   2^21  33 /   78   2^23 78 / 301
+//  2048 taps:  2^17 57.2 / 51.3   2^18 57.4 / 51.3   2^19 57.6 / 88.3   2^20 59.7 / 168.5   2^21  62 /  291
+// -> tensor from 2^19 samples AND 2^29 sample-taps per call on (complex taps count twice).  SGPU_FIR_TC_MIN_SAMPLES, when
+// set, replaces the rule by a plain per-channel sample count (the GPU tests pin 2^15 to exercise the tensor kernel on
+// short streams).
+static bool tc_call_is_long_enough(const sgpu_fir *f, long long n_in) {
+    if (const char *e = getenv("SGPU_FIR_TC_MIN_SAMPLES")) return n_in >= atoll(e);
+    const long long total = n_in * (long long)f->C;
+    return n_in >= (1LL << 15) && total >= (1LL << 19) && total * (long long)f->T * (f->complex_taps ? 2 : 1) >= (1LL << 29);
+}
+
+
 static int fir_R(const sgpu_fir *f) { return f->complex_taps ? 8 : kR; }
 
 static int fir_upload_taps(sgpu_fir *f) {
@@ -782,11 +800,10 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
     if (n_out <= 0) return SGPU_OK;  // a decimator call shorter than one period: the caller enqueues the history update
     if (f->M == 1 && !f->per_channel && (f->complex_taps || f->scale_im == 0.0) &&
         (long long)f->T >= env_int("SGPU_FIR_TC_MIN_TAPS", f->complex_taps ? 56 : 112) && f->T <= 16384 /* band matrix: 512 B per tap */ &&
-        n_in >= (long long)env_int("SGPU_FIR_TC_MIN_SAMPLES", 1 << 15) && env_int("SGPU_FIR_TC", 1)) {
+        tc_call_is_long_enough(f, n_in) && env_int("SGPU_FIR_TC", 1)) {
         // Long filters (real or complex taps): banded-Toeplitz product on the tcgen05 tensor cores (fir_tc.cu, DESIGN
-        // 4.9).  Thresholds from measurements: tools/tc_taps_crossover.py and tools/tc_probe.py with
-        // SGPU_FIR_TC_MIN_SAMPLES=1 (calls of 2^17 ... 2^21 samples: 47-65 us per call against 74-123 us for the
-        // FFMA2 kernel, whose blocks each walk 16384 outputs).
+        // 4.9).  Thresholds from measurements: tools/tc_taps_crossover.py (taps) and tools/call_size_crossover.py (call
+        // size, see tc_call_is_long_enough).
         if (!f->tc_tried) {
             f->tc_tried = true;
             // a failed set-up is not fatal: the FP32 kernels below serve the call, the reason stays in sgpu_last_error

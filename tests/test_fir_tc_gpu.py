@@ -322,3 +322,35 @@ def test_complex_taps(torch, T):
     finally:
         del os.environ["SGPU_FIR_TC"]
     assert (y - y2).abs().max().item() <= TOL * y2.abs().max().item()
+
+
+def test_default_dispatch_rule(torch, FIR, monkeypatch):
+    """Without SGPU_FIR_TC_MIN_SAMPLES the library picks the kernel by the size of the call (csrc/fir.cu:
+    tc_call_is_long_enough, measured with tools/call_size_crossover.py): short calls of a long filter stay on the FFMA2
+    kernel, long calls go to the tensor cores, and a stream may cross the rule in either direction without a seam."""
+    monkeypatch.delenv("SGPU_FIR_TC_MIN_SAMPLES", raising=False)
+    T = 512
+    h = f32_taps(O.firdes_kaiser(T, 0.1, 80.0, 0.0))
+    n_short, n_long = 1 << 17, (1 << 20) + 3
+    x = _rand(torch, n_short + n_long + n_short, 11)
+    f = FIR(h, 1.0)
+    y1 = f.execute_block(x[:n_short])
+    assert f.last_path == "ffma"      # 2^17 samples x 512 taps: 18.5 us on FFMA2, 28.7 us on the tensor kernel
+    y2 = f.execute_block(x[n_short:n_short + n_long])
+    assert f.last_path == "tensor"    # 2^20 x 512 = 2^29 sample-taps
+    y3 = f.execute_block(x[n_short + n_long:])
+    assert f.last_path == "ffma"
+    y = torch.cat([y1, y2, y3]).cpu().numpy()
+    xs = x.cpu().numpy()
+    for s0 in (0, n_short - 200, n_short + n_long - 300, y.size - 4096):
+        lo = max(0, s0 - (T - 1))
+        ref = O.fir_fast(h, xs[lo:s0 + 4096])[s0 - lo:]
+        assert nerr(y[s0:s0 + 4096], ref) <= TOL
+    # a short filter needs a longer call: 128 taps x 2^20 samples is still FFMA2, x 2^22 is tensor
+    h128 = f32_taps(O.firdes_kaiser(128, 0.1, 80.0, 0.0))
+    f = FIR(h128, 1.0)
+    f.execute_block(x[:1 << 20])
+    assert f.last_path == "ffma"
+    xx = _rand(torch, 1 << 22, 12)
+    f.execute_block(xx)
+    assert f.last_path == "tensor"
