@@ -151,3 +151,43 @@ def test_config5_iir_full_batch_and_stream(torch_cuda):
         lo = max(0, start - 4096)
         ref, _ = O.sos_cascade_fast(ff, fb, _window(s, lo, start + 8192))
         assert nerr(_window(ys, start, start + 8192), ref[start - lo:]) <= TOL
+
+
+def test_ddc_full_batch(torch_cuda):
+    """the NCO mix-down fused into config 3's decimator, at config 3's full size."""
+    torch = torch_cuda
+    from solid_dsp_b200.filter.ddc import DigitalDownConverter
+    from solid_dsp_b200.filter.fir import DecimatingFIRFilter
+    h = f32_taps(O.firdes_kaiser(256, 0.5 / 8 * 0.9, 80.0, 0.0))
+    C, n, M = 4096, 1 << 20, 8
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.empty((C, n), dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).uniform_(-1, 1, generator=g)
+    # zero frequency, zero phase: the phasor is exactly (1, 0), so the DDC IS the decimator -- bit for bit
+    d0 = DigitalDownConverter(h, 1.0, M, frequency=0.0, n_channels=C)
+    y0 = d0.execute_block(x)
+    assert d0.last_fused and y0.shape == (C, n // M)
+    yd = DecimatingFIRFilter(h, 1.0, M, n_channels=C).execute_block(x)
+    assert torch.equal(y0, yd)
+    del y0, yd
+    # a real mix: oracle windows at the start and at the end of the first, a middle and the last channel (the 32-bit
+    # phase accumulator has wrapped tens of thousands of times by then), channels with their own frequency and phase
+    d = DigitalDownConverter(h, 1.0, M, frequency=0.6183, n_channels=C)
+    d.nco.set_frequency(-2.9, channel=2047)
+    d.nco.set_phase(1.0, channel=4095)
+    raw = {c: d.nco.raw(c) for c in (0, 2047, 4095)}
+    y = d.execute_block(x)
+    assert d.last_fused and y.shape == (C, n // M)
+    for c in (0, 2047, 4095):
+        theta, delta = raw[c]
+        for start in (0, n - (1 << 14)):
+            pre = start - max(0, start - 256)
+            lo = start - pre
+            xs = _window(x[c], lo, start + (1 << 14))
+            ref = O.ddc_fast(h, xs, 1.0, M, count0=lo % M, raw=((theta + lo * delta) & 0xFFFFFFFF, delta))[-(1 << 14) // M:]
+            got = _window(y[c], start // M, start // M + (1 << 14) // M)
+            assert nerr(got, ref) <= TOL
+    # the accumulators have advanced by exactly n steps (nco/mod.rs:93-96 per sample)
+    for c in (0, 2047, 4095):
+        theta, delta = raw[c]
+        assert d.nco.raw(c) == ((theta + n * delta) & 0xFFFFFFFF, delta)
