@@ -50,6 +50,8 @@ WORKLOADS = {
                   flop_per_unit=256.0, bytes_per_unit=16.0, unit="input sample"),
     "decim": dict(desc="BASELINE configs[2]: decimator M=8, 256 taps, 4096 channels x 2^20 samples",
                   flop_per_unit=128.0, bytes_per_unit=9.0, unit="input sample"),
+    "decim_pc": dict(desc="SURVEY 8d: BASELINE configs[2] with per-channel taps -- 4096 different 256-tap Kaiser designs (computed on the device), M=8, 4096 channels x 2^20 samples",
+                     flop_per_unit=128.0, bytes_per_unit=9.0, unit="input sample"),
     "interp": dict(desc="BASELINE configs[3]: interpolator L=4, 128 taps, 1024 channels x 2^20 inputs",
                    flop_per_unit=128.0, bytes_per_unit=10.0, unit="output sample"),
     "iir_batch": dict(desc="BASELINE configs[4a]: 8-section biquad cascade, 65536 channels x 2^14 samples",
@@ -67,7 +69,7 @@ DDC_FREQ = 0.1234  # radians per sample of the mix-down NCO
 FIR64_ROWS = 32    # fir64: the calls rotate over 32 buffers of 2^20 samples (512 MB in + out: every call reads cold data)
 SHAPES = {  # channels, log2(samples per channel)
     "decim": (4096, 20), "interp": (1024, 20), "iir_batch": (65536, 14), "iir_scan": (1, 28), "autocorr": (1024, 20),
-    "ddc": (4096, 20),
+    "ddc": (4096, 20), "decim_pc": (4096, 20),
 }
 
 # (pole radius, pole angle / pi) of the benchmark's biquad sections: conjugate pole pairs, double zero at z = -1, unit DC
@@ -106,6 +108,14 @@ def workload_taps(name, impl="ours"):
         return f32_taps(kaiser(64, 0.25, 60.0, 0.0))
     if name in ("decim", "ddc"):
         return f32_taps(kaiser(256, 0.5 / 8 * 0.9, 80.0, 0.0))
+    if name == "decim_pc":
+        # one design per channel: cut-offs spread over [0.5, 0.9] of the decimated band.  Ours: all 4096 designs in one
+        # launch of sgpu_firdes_kaiser; the reference arm only needs one of them (the cost does not depend on the values)
+        chans = SHAPES[name][0]
+        fcs = [0.5 / 8 * (0.5 + 0.4 * c / chans) for c in range(chans)]
+        if impl == "reference":
+            return f32_taps(kaiser(256, fcs[0], 80.0, 0.0))
+        return f32_taps(firdes.firdes_kaiser_device(256, fcs, 80.0, 0.0))
     if name == "interp":
         return f32_taps(kaiser(128, 0.5 / 4 * 0.9, 80.0, 0.0))
     if name == "autocorr":
@@ -215,7 +225,7 @@ def cpu_reference_path(name: str, n_threads: int, budget_s: float, native: bool 
             O.run_units("fir", x, n_in, n_units, n_in, out, n_in, n_threads, coefs=taps, preroll=T - 1,
                         x_offset=T - 1, native=native)
             return time.perf_counter() - t0, n_units * n_in
-        if name in ("decim", "ddc"):
+        if name in ("decim", "ddc", "decim_pc"):
             x = rng.uniform(-1, 1, n_units * n_in) + 1j * rng.uniform(-1, 1, n_units * n_in)
             out = np.zeros(n_units * (n_in // 8 + 1), dtype=np.complex128)
             t0 = time.perf_counter()
@@ -407,7 +417,7 @@ class Workload:
                 c_loc = 1  # one stream: time segments per rank, warm-up halo from the previous rank
                 self.units_total = n_per
             else:
-                _, c_loc = sharding.shard_channels(chans, world, rank)
+                c_first, c_loc = sharding.shard_channels(chans, world, rank)
                 self.units_total = chans * n_per * (4 if name == "interp" else 1)
             n_loc = n_per
             if name == "iir_scan" and world > 1:
@@ -415,6 +425,9 @@ class Workload:
             self.x = rand_c((c_loc, n_loc))
             if name == "decim":
                 self.filt = DecimatingFIRFilter(taps, 1.0, 8, n_channels=c_loc)
+            elif name == "decim_pc":  # [C][T] taps: every channel owns its coefficients (fir/mod.rs:79-88)
+                self.taps = taps = taps[c_first:c_first + c_loc]
+                self.filt = DecimatingFIRFilter(taps, 1.0, 8)
             elif name == "ddc":
                 from solid_dsp_b200.filter.ddc import DigitalDownConverter
                 self.filt = DigitalDownConverter(taps, 1.0, 8, DDC_FREQ, n_channels=c_loc)
@@ -579,7 +592,7 @@ class Workload:
                 traffic = traffic_detail.get("dram_bytes")
         kernel = {"fir": "fir_tc_fused_kernel (tcgen05.mma kind::f16, TMA, TMEM) + fir_tc_post_kernel" if on_tensor else "fir_warp_kernel<R=16>",
                   "fir64": "fir_warp_kernel<R=16> (one launch per call, history written by the same kernel)",
-                  "decim": "fir_decim_warp_kernel<M=8,PS=4>", "ddc": "fir_decim_warp_kernel<M=8,PS=4,NCO mix>",
+                  "decim": "fir_decim_warp_kernel<M=8,PS=4>", "decim_pc": "fir_decim_warp_kernel<M=8,PS=4> (per-channel tap images)", "ddc": "fir_decim_warp_kernel<M=8,PS=4,NCO mix>",
                   "interp": "fir_interp_walk_kernel<L=4,K=5>", "iir_batch": "iir_sos_kernel<8>",
                   "iir_scan": "iir_sos_kernel<8> (chunked scan)", "autocorr": "autocorr_kernel"}[name]
         r = {
@@ -658,7 +671,7 @@ def run_gpu_arm(args):
     # baseline each.  N > 1: the channel-sharded ones (contiguous channel ranges, no data-path collective),
     # oracle parity on EVERY rank -- so that the driver's scaling run carries them too.
     if name == "fir" and args.log2_samples == 30 and not args.no_workloads:
-        default_side = "fir64,decim,interp,iir_batch,iir_scan,ddc" if world == 1 else "decim,interp,iir_batch"
+        default_side = "fir64,decim,decim_pc,interp,iir_batch,iir_scan,ddc" if world == 1 else "decim,interp,iir_batch"
         side = [w for w in os.environ.get("SGPU_BENCH_SIDE", default_side).split(",") if w in WORKLOADS and w != "fir"]
         block = {}
         guard = None
@@ -716,7 +729,7 @@ def run_side_workload(name, args, dev, dist, world=1, rank=0):
            "roofline": {k: roofline[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel")},
            "roofline_frac_fma": roofline["fma"]["frac"], "roofline_frac_hbm": roofline["hbm"]["frac"],
            "parity": parity, "cpu_baseline": cpu}
-    if name in ("decim", "interp"):
+    if name in ("decim", "decim_pc", "interp"):
         out["unit_note"] = "decim: input samples/s; interp: output samples/s"
     return out
 
@@ -758,18 +771,19 @@ def spot_check(name, taps, filt, x, y, halo_prev, rank=0, nco_raw=None):
             e = nerr(got[start:start + 8192], ref)
             windows.append([row, start, e])
             worst = max(worst, e)
-    elif name in ("decim", "ddc"):
+    elif name in ("decim", "ddc", "decim_pc"):
         # the timed handle streams (history = tail of the previous step): compare outputs that
         # depend only on this call's inputs, i.e. skip the first ceil(T/M) of every window
-        skip = len(taps) // 8 + 1
+        skip = np.shape(taps)[-1] // 8 + 1
         n = x.shape[1]
         for c in rng.integers(0, x.shape[0], 3):
+            taps_c = taps[int(c)] if name == "decim_pc" else taps
             for start in (0, (n // 2) & ~7, n - (1 << 15)):
                 xs = x[int(c), start:start + (1 << 15)].cpu().numpy()
                 if name == "ddc":  # the NCO phase at sample `start` of the checked step
                     th0, dl = nco_raw[int(c)]
                     xs = O.nco_mix_down_block(xs, raw=((th0 + start * dl) & 0xFFFFFFFF, dl))
-                ref = O.fir_fast(taps, xs, 1.0, 8)[skip:]
+                ref = O.fir_fast(taps_c, xs, 1.0, 8)[skip:]
                 got = y[int(c), start // 8 + skip:start // 8 + skip + len(ref)].cpu().numpy()
                 e = nerr(got, ref)
                 windows.append([int(c), start, e])
