@@ -120,6 +120,8 @@ def lib(native: bool = False):
     sig("so_firdes_notch", C.c_int, c_size, C.c_double, C.c_double, c_dp)
     sig("so_filter_autocorrelation", C.c_double, c_dp, c_size, C.c_ssize_t)
     sig("so_filter_crosscorrelation", C.c_double, c_dp, c_size, c_dp, c_size, C.c_ssize_t)
+    sig("so_filter_isi", None, c_dp, c_size, c_size, c_size, c_dp)
+    sig("so_filter_energy", C.c_int, c_dp, c_size, C.c_double, c_size, c_dp)
     sig("so_pll_active_lag", C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp)
     sig("so_nco_constrain", C.c_uint32, C.c_double)
     sig("so_nco_new", vp)
@@ -682,6 +684,24 @@ def filter_crosscorrelation(h, g, lag):
     h = np.ascontiguousarray(h, dtype=np.float64)
     g = np.ascontiguousarray(g, dtype=np.float64)
     return lib().so_filter_crosscorrelation(_p(h), len(h), _p(g), len(g), lag)
+
+
+def filter_isi(h, samples_per_symbol, filter_delay):
+    """firdes/mod.rs:553-573 -> (rms, max)"""
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    out = np.zeros(2)
+    lib().so_filter_isi(_p(h), len(h), samples_per_symbol, filter_delay, _p(out))
+    return float(out[0]), float(out[1])
+
+
+def filter_energy(h, cutoff_frequency, fft_size):
+    """firdes/mod.rs:603-640 (DotProduct FORWARD on e^{j 2 pi f k})"""
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    out = np.zeros(1)
+    st = lib().so_filter_energy(_p(h), len(h), float(cutoff_frequency), fft_size, _p(out))
+    if st:
+        raise ValueError({-1: "Bandwidth", -2: "FilterSize", -3: "FFTSize"}[st])
+    return float(out[0])
 
 
 def pll_active_lag(w, zeta, k):

@@ -812,6 +812,48 @@ SO_API double so_filter_crosscorrelation(const double *h, size_t nh, const doubl
     for (size_t i = 0; i < (size_t)n; i++) r += h[ih + i] * g[ig + i];
     return r;
 }
+/* filter_isi -- firdes/mod.rs:553-573: (rms, max) of |r(i * sps) / r(0)|, i = 1 .. 2 * delay - 1 */
+SO_API void so_filter_isi(const double *h, size_t n, size_t sps, size_t delay, double *out2) {
+    out2[0] = out2[1] = 0.0;
+    if (2 * sps * delay + 1 != n) return;                       /* :554-561 */
+    double rxx0 = so_filter_autocorrelation(h, n, 0);
+    double isi_rms = 0.0, isi_max = 0.0;
+    for (size_t i = 1; i < 2 * delay; i++) {
+        double e = fabs(so_filter_autocorrelation(h, n, (ptrdiff_t)(i * sps)) / rxx0);
+        isi_rms += e * e;
+        if (i == 1 || e > isi_max) isi_max = e;
+    }
+    out2[0] = sqrt(isi_rms / (2.0 * (double)delay));
+    out2[1] = isi_max;
+}
+/* filter_energy -- firdes/mod.rs:603-640: the crate's own caller of DotProduct::execute (FORWARD, f64 coefficients on
+ * complex samples e^{j 2 pi f k}); relative energy above the cut-off.  Returns -1 / -2 / -3 for the Bandwidth /
+ * FilterSize / FFTSize errors (:608-614). */
+SO_API int so_filter_energy(const double *h, size_t n, double fc, size_t fft_size, double *out) {
+    if (!(fc >= 0.0 && fc <= 0.5)) return -1;
+    if (n == 0) return -2;
+    if (fft_size == 0) return -3;
+    cplx *ejwt = (cplx *)calloc(n, sizeof(cplx));
+    so_dotprod dp;
+    dp_init(&dp, h, n, 0, SO_FORWARD);
+    double e_total = 0.0, e_stop = 0.0;
+    for (size_t i = 0; i < fft_size; i++) {
+        double f = 0.5 * (double)i / (double)fft_size;
+        for (size_t k = 0; k < n; k++) {                        /* Complex::from_polar(1.0, theta) */
+            double th = 2.0 * M_PI * f * (double)k;
+            ejwt[k].re = 1.0 * cos(th);
+            ejwt[k].im = 1.0 * sin(th);
+        }
+        cplx v = dp_execute(&dp, ejwt, n);
+        double e2 = v.re * v.re - v.im * (-v.im);               /* (v * v.conj()).re */
+        e_total += e2;
+        if (f > fc) e_stop += e2;
+    }
+    dp_free(&dp);
+    free(ejwt);
+    *out = e_stop / e_total;
+    return 0;
+}
 /* iirdes/pll/mod.rs:24-52; num/den each 3 values.  Returns -1 on a rejected argument. */
 SO_API int so_pll_active_lag(double w, double zeta, double k, double *num, double *den) {
     if (w <= 0.0 || zeta <= 0.0 || k <= 0.0) return -1;

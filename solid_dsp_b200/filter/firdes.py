@@ -151,6 +151,61 @@ def filter_crosscorrelation(h, g, lag: int) -> float:  # firdes/mod.rs:487-526
     return r
 
 
+def filter_isi(h, samples_per_symbol: int, filter_delay: int):  # firdes/mod.rs:553-573
+    """(rms, max) inter-symbol interference of a filter of 2 * sps * delay + 1 taps; (0, 0) on a length mismatch."""
+    if 2 * samples_per_symbol * filter_delay + 1 != len(h):
+        return 0.0, 0.0
+    rxx0 = filter_autocorrelation(h, 0)
+    isi_rms, isi_max = 0.0, 0.0
+    for i in range(1, 2 * filter_delay):
+        e = abs(filter_autocorrelation(h, i * samples_per_symbol) / rxx0)
+        isi_rms += e * e
+        if i == 1 or e > isi_max:
+            isi_max = e
+    return math.sqrt(isi_rms / (2.0 * float(filter_delay))), isi_max
+
+
+def _energy_checks(h, cutoff_frequency, fft_size):  # firdes/mod.rs:608-614
+    if not (0.0 <= cutoff_frequency <= 0.5):
+        raise FirdesError("Bandwidth")
+    if len(h) == 0:
+        raise FirdesError("FilterSize")
+    if fft_size == 0:
+        raise FirdesError("FFTSize")
+
+
+def filter_energy(h, cutoff_frequency: float, fft_size: int) -> float:
+    """Relative out-of-band energy, firdes/mod.rs:603-640, host f64: the crate's own caller of `DotProduct::execute`
+    (FORWARD coefficients against e^{j 2 pi f k}, `sum += value * sample` sequentially, dot_product/mod.rs:159-170)."""
+    _energy_checks(h, cutoff_frequency, fft_size)
+    e_total, e_stop = 0.0, 0.0
+    for i in range(fft_size):
+        f = 0.5 * float(i) / float(fft_size)
+        re, im = 0.0, 0.0
+        for k, c in enumerate(h):
+            th = 2.0 * math.pi * f * float(k)
+            re += c * (1.0 * math.cos(th))
+            im += c * (1.0 * math.sin(th))
+        e2 = re * re - im * (-im)
+        e_total += e2
+        if f > cutoff_frequency:
+            e_stop += e2
+    return e_stop / e_total
+
+
+def filter_energy_device(h, cutoff_frequency: float, fft_size: int) -> float:
+    """filter_energy with its `DotProduct::execute` calls on the GPU: the fft_size sample vectors e^{j 2 pi f k} are ONE
+    batched sgpu_dot_execute (f32 on the device, so the result carries f32 rounding: ~1e-6 relative)."""
+    import numpy as np
+    from ..dot_product import Direction, DotProduct
+    _energy_checks(h, cutoff_frequency, fft_size)
+    f = 0.5 * np.arange(fft_size, dtype=np.float64) / float(fft_size)
+    ejwt = np.exp(2j * np.pi * f[:, None] * np.arange(len(h), dtype=np.float64)[None, :]).astype(np.complex64)
+    v = np.asarray(DotProduct(list(h), Direction.FORWARD).execute(ejwt), dtype=np.complex128)
+    e2 = (v * np.conj(v)).real
+    return float(np.sum(e2[f > cutoff_frequency]) / np.sum(e2))
+
+
 def firdes_kaiser_device(filter_length: int, cutoff_frequency, stop_band_attenuation, fractional_sample_offset=0.0,
                          device_out=None, stream=None):
     """firdes_kaiser (firdes/mod.rs:278-305) computed ON THE GPU (sgpu_firdes_kaiser, csrc/firdes.cu): one design, or

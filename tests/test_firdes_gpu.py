@@ -87,3 +87,23 @@ def test_errors_follow_the_reference_order(firdes):
             firdes.firdes_kaiser(*args)
         assert str(e2.value) == code
     assert firdes.firdes_kaiser_device(0, 0.2, 60.0, 0.0) == []
+
+
+def test_filter_energy_with_the_dot_products_on_the_gpu(firdes):
+    """firdes::filter_energy is the reference crate's own caller of DotProduct::execute (firdes/mod.rs:620-629): 128
+    sample vectors e^{j 2 pi f k} against FORWARD coefficients.  Here they are one batched sgpu_dot_execute; the f64 host
+    form reproduces the reference's golden (0.3152318 as f32) exactly, the device form within f32 rounding."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "reference_doctests.json").read_text())["firdes_energy"]
+    h = firdes.firdes_notch(*g["notch"])
+    host = firdes.filter_energy(h, g["cutoff"], g["fft_size"])
+    assert np.float32(host) == np.float32(g["expect"])
+    dev = firdes.filter_energy_device(h, g["cutoff"], g["fft_size"])
+    assert abs(dev - host) <= 1e-5 * host
+    # a long filter and a fine grid: 4096 dot products of 2049 terms in one call; the cut-off sits inside the pass band so
+    # that the ratio is not dominated by the f32 rounding of an 80 dB stop band
+    h2 = firdes.firdes_kaiser(2049, 0.1, 80.0, 0.0)
+    want = O.filter_energy(h2, 0.05, 4096)
+    assert 0.3 < want < 0.7
+    assert abs(firdes.filter_energy_device(h2, 0.05, 4096) - want) <= 1e-5 * want

@@ -78,6 +78,20 @@ def test_design_goldens(golden):
     g = ref["firdes_crosscorrelation"]
     v = firdes.filter_crosscorrelation(firdes.firdes_kaiser(*g["kaiser"]), firdes.firdes_notch(*g["notch"]), g["lag"])
     assert np.float32(v) == np.float32(g["expect"])
+    g = ref["firdes_isi"]
+    rms, mx = firdes.filter_isi(firdes.firdes_notch(*g["notch"]), g["samples_per_symbol"], g["filter_delay"])
+    assert (np.float32(rms), np.float32(mx)) == (np.float32(g["expect"][0]), np.float32(g["expect"][1]))
+    assert (rms, mx) == O.filter_isi(O.firdes_notch(*g["notch"]), g["samples_per_symbol"], g["filter_delay"])
+    g = ref["firdes_energy"]
+    e = firdes.filter_energy(firdes.firdes_notch(*g["notch"]), g["cutoff"], g["fft_size"])
+    assert np.float32(e) == np.float32(g["expect"]) and e == O.filter_energy(O.firdes_notch(*g["notch"]), g["cutoff"], g["fft_size"])
+    for args, code in (((0.6, 128), "Bandwidth"), ((0.35, 0), "FFTSize")):
+        with pytest.raises(firdes.FirdesError) as err:
+            firdes.filter_energy(firdes.firdes_notch(*g["notch"]), *args)
+        assert str(err.value) == code
+    with pytest.raises(firdes.FirdesError) as err:
+        firdes.filter_energy([], 0.35, 128)
+    assert str(err.value) == "FilterSize"
     with pytest.raises(firdes.FirdesError):
         firdes.firdes_kaiser(8, 0.7, 60.0)
     with pytest.raises(iirdes.IirdesError):

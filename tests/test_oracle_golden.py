@@ -122,6 +122,18 @@ def test_firdes(ref):
     h = O.firdes_kaiser(*g["kaiser"])
     n = O.firdes_notch(*g["notch"])
     assert np.float32(O.filter_crosscorrelation(h, n, g["lag"])) == np.float32(g["expect"])
+    # the two analysis routines behind the taps: filter_isi, and filter_energy -- the crate's own caller of
+    # DotProduct::execute (firdes/mod.rs:620-629)
+    g = ref["firdes_isi"]
+    rms, mx = O.filter_isi(O.firdes_notch(*g["notch"]), g["samples_per_symbol"], g["filter_delay"])
+    assert np.float32(rms) == np.float32(g["expect"][0]) and np.float32(mx) == np.float32(g["expect"][1])
+    assert O.filter_isi(O.firdes_notch(*g["notch"]), 2, g["filter_delay"]) == (0.0, 0.0)   # length mismatch, :554-561
+    g = ref["firdes_energy"]
+    assert np.float32(O.filter_energy(O.firdes_notch(*g["notch"]), g["cutoff"], g["fft_size"])) == np.float32(g["expect"])
+    for bad, code in (((0.6, 128), "Bandwidth"), ((0.35, 0), "FFTSize")):
+        with pytest.raises(ValueError) as e:
+            O.filter_energy(O.firdes_notch(*g["notch"]), *bad)
+        assert str(e.value) == code
     assert len(O.firdes_kaiser(*ref["firdes_kaiser_len"]["kaiser"])) == 8
     assert len(O.firdes_notch(*ref["firdes_notch_len"]["notch"])) == 17
 
