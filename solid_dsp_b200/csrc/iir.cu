@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     // are staged (8-byte cp.async, double buffered in the second tile buffer) while the outputs are
     // produced in the first one: input, then L-1 zeros (iir/interp.rs:184-190).
     long long ip_done = 0;  // inputs per row consumed by this path
+    int ip_phase = 0;       // outputs since the last input when the guarded path takes over (0: the next output carries one)
     if constexpr (WRAP == 2) {
         const int L = a.factor;
         const bool pow2 = (L & (L - 1)) == 0 && L >= 2 && L <= kTile;
@@ -348,6 +349,69 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
             }
             ip_done = tiles2 * IN_T;
             full_tiles = tiles2;
+        }
+        // Any other L <= the tile (iir/interp.rs:184-190 takes every factor): the same structure with the input
+        // positions tracked instead of shifted.  Output o of a row is input o / L when L | o, else a zero; a tile of 32
+        // outputs consumes the inputs ceil(32 t / L) .. ceil(32 (t + 1) / L) - 1 (IN_MAX = ceil(32 / L) at most), staged
+        // one tile ahead with 8-byte cp.async; every row of the warp is in the same phase.
+        const long long tiles3 = (!pow2 && L >= 3 && L <= kTile) ? len0 / kTile : 0;
+        if (tiles3 > 0) {
+            const int IN_MAX = (kTile + L - 1) / L;
+            constexpr int IPITCH = kTile / 2 + 1;
+            constexpr int ISTAGE = 32 * IPITCH;
+            float2 *ibuf = reinterpret_cast<float2 *>(buf + kTileF4);
+            const int dr = 32 / IN_MAX, dc = 32 - dr * IN_MAX;  // (row, column) step of element e -> e + 32
+            const int r0 = lane / IN_MAX, c0 = lane - r0 * IN_MAX;
+            long long in_next = 0;  // first input of the next tile to stage
+            auto stage_in = [&](float2 *dst, const long long t) {
+                // inputs of tile t: [in_next, in_hi)
+                const long long in_hi = ((t + 1) * kTile + L - 1) / L;
+                const int nt = (int)(in_hi - in_next);
+                const float2 *ld = a.in + in_base + in_next;
+                int r = r0, c = c0;
+                for (int i = 0; i < IN_MAX; ++i) {
+                    if (c < nt && r < 32) {
+                        const int rl = r < nvalid ? r : nvalid - 1;
+                        cp_async8(dst + r * IPITCH + c, ld + (long long)rl * rstr_in + c);
+                    }
+                    r += dr;
+                    c += dc;
+                    if (c >= IN_MAX) { c -= IN_MAX; ++r; }
+                }
+                cp_async_commit();
+                in_next = in_hi;
+            };
+            stage_in(ibuf, 0);
+            int nextpos = 0;  // position inside the current tile of the next output that carries an input
+            for (long long t = 0; t < tiles3; ++t) {
+                const float2 *irow = ibuf + (t & 1) * ISTAGE + lane * IPITCH;
+                if (t + 1 < tiles3) {
+                    stage_in(ibuf + ((t + 1) & 1) * ISTAGE, t + 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                float4 *orow = buf + lane * kRowF4;
+                int idx = 0;
+#pragma unroll
+                for (int j = 0; j < LPR; ++j) {
+                    float2 y0 = make_float2(0.f, 0.f), y1 = y0;
+                    if (2 * j == nextpos) { y0 = irow[idx++]; nextpos += L; }
+                    y0 = filter_step<NSEC, FOLD, NORD>(y0, st, a.k);
+                    if (2 * j + 1 == nextpos) { y1 = irow[idx++]; nextpos += L; }
+                    y1 = filter_step<NSEC, FOLD, NORD>(y1, st, a.k);
+                    orow[j] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+                nextpos -= kTile;
+                __syncwarp();
+                if (a.write_out) store_tile(buf);
+                st_ptr += kTile;
+                __syncwarp();
+            }
+            ip_done = (tiles3 * kTile + L - 1) / L;
+            ip_phase = (int)((tiles3 * kTile) % L);
+            full_tiles = tiles3;
         }
     }
 
@@ -440,7 +504,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) iir_sos_kernel(const IirArgs a)
     if (full_tiles < ntiles) {
         float4 *cur = buf;
         const float2 *my_in = a.in + in_base + (long long)lane * rstr_in;
-        int ip_cnt = 0;       // interpolator phase (WRAP 2)
+        int ip_cnt = ip_phase;  // interpolator phase (WRAP 2)
         long long ip_in = ip_done;  // next input index (WRAP 2)
         for (long long t = full_tiles; t < ntiles; ++t) {
             const long long s0 = t * kTile;

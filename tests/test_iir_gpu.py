@@ -191,7 +191,7 @@ def test_iir_decimating(iir, M):
         assert nerr(parts[c], ref) <= TOL
 
 
-@pytest.mark.parametrize("L", [1, 2, 5])
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 6, 7, 12, 31, 32, 33, 40])
 def test_iir_interpolating(iir, L):
     rng = np.random.default_rng(L)
     ff, fb = _sections(3)
@@ -202,6 +202,14 @@ def test_iir_interpolating(iir, L):
     for c in (0, 32):
         ref = O.InterpolatingIIRFilter(ff, fb, O.SECOND_ORDER, L).execute_block(x[c])
         assert nerr(got[c], ref) <= TOL
+    # exact positions: an impulse at input 3 comes out of the first section chain at output 3 L and nowhere before
+    # (iir/interp.rs:184-190: the input, then L - 1 zeros); every factor, tile path (L <= 32) and guarded path
+    imp = np.zeros((33, 50), dtype=np.complex64)
+    imp[:, 3] = 1.0
+    y = iir.InterpolatingIIRFilter(ff, fb, iir.IIRFilterType.SecondOrder, L, n_channels=33).execute_block(imp)
+    assert not np.any(y[:, :3 * L]) and np.all(y[:, 3 * L] != 0)
+    ref = O.InterpolatingIIRFilter(ff, fb, O.SECOND_ORDER, L).execute_block(imp[0])
+    assert nerr(y[17], ref) <= TOL
 
 
 def test_iir_normal_mode(iir):
