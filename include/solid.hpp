@@ -138,13 +138,31 @@ inline void check_ctor(int st) {
         default: throw GpuError(st);
     }
 }
+inline std::vector<double> flatten(const std::vector<std::vector<double>> &per_channel) {
+    std::vector<double> flat;
+    for (const auto &row : per_channel) {
+        if (row.size() != per_channel[0].size()) throw std::invalid_argument("per-channel tap sets of different lengths");
+        flat.insert(flat.end(), row.begin(), row.end());
+    }
+    return flat;
+}
 }  // namespace detail_fir
+
+struct PerChannel {};                    // tag: the constructor takes one tap set per channel
+inline constexpr PerChannel per_channel{};
 
 class FIRFilter : public Filter<cf32, cf32> {  // fir/mod.rs:58-316
    public:
     FIRFilter(const std::vector<double> &coefficents, double scale, size_t n_channels = 1) {  // ::new :79
         detail_fir::check_ctor(sgpu_fir_create(coefficents.data(), coefficents.size(), SGPU_TAPS_REAL,
                                                n_channels, scale, 0.0, 0, 0, &h_));
+    }
+    /// one tap set per channel (`per_channel[c]` = the coefficients of reference object c; every reference filter owns
+    /// its coefficients, fir/mod.rs:79-88): sgpu_fir_create_per_channel
+    FIRFilter(PerChannel, const std::vector<std::vector<double>> &taps, double scale) {
+        const std::vector<double> flat = detail_fir::flatten(taps);
+        detail_fir::check_ctor(sgpu_fir_create_per_channel(flat.data(), taps.empty() ? 0 : taps[0].size(), SGPU_TAPS_REAL,
+                                                           taps.size(), scale, 0.0, 0, 0, &h_));
     }
     FIRFilter(const FIRFilter &o) { detail::check(sgpu_fir_clone(o.h_, &h_)); }  // #[derive(Clone)]
     FIRFilter &operator=(const FIRFilter &) = delete;
@@ -207,6 +225,11 @@ class DecimatingFIRFilter : public FIRFilter {  // fir/decim.rs:5-295
                         size_t n_channels = 1) {  // ::new :27
         detail_fir::check_ctor(sgpu_fir_create(coefficents.data(), coefficents.size(), SGPU_TAPS_REAL,
                                                n_channels, scale, 0.0, 1, decimation, &h_));
+    }
+    DecimatingFIRFilter(PerChannel, const std::vector<std::vector<double>> &taps, double scale, size_t decimation) {
+        const std::vector<double> flat = detail_fir::flatten(taps);
+        detail_fir::check_ctor(sgpu_fir_create_per_channel(flat.data(), taps.empty() ? 0 : taps[0].size(), SGPU_TAPS_REAL,
+                                                           taps.size(), scale, 0.0, 1, decimation, &h_));
     }
     DecimatingFIRFilter(const DecimatingFIRFilter &o) : FIRFilter() { detail::check(sgpu_fir_clone(o.h_, &h_)); }
     size_t get_decimation() const { return sgpu_fir_decimation(h_); }  // :96
@@ -521,5 +544,135 @@ inline std::vector<double> firdes_kaiser(size_t filter_length, double cutoff_fre
 }
 
 }  // namespace firdes
+// ------------------------------------------------------------------------------------------------
+namespace ddc {
+
+// NCO mix-down feeding a DecimatingFIRFilter (nco/mod.rs:147-151 -> fir/decim.rs:221-256), the mix fused into the
+// decimator's tile on the hot shapes: sgpu_ddc_*.  Frequency / phase through nco().
+class DigitalDownConverter {
+   public:
+    DigitalDownConverter(const std::vector<double> &coefficents, double scale, size_t decimation, double frequency,
+                         size_t n_channels = 1) {
+        fir::detail_fir::check_ctor(sgpu_ddc_create(coefficents.data(), coefficents.size(), SGPU_TAPS_REAL, n_channels, scale,
+                                                    0.0, decimation, &h_));
+        detail::check(sgpu_nco_set_frequency(sgpu_ddc_nco(h_), SGPU_ALL_CHANNELS, frequency));
+    }
+    DigitalDownConverter(const DigitalDownConverter &o) { detail::check(sgpu_ddc_clone(o.h_, &h_)); }
+    DigitalDownConverter &operator=(const DigitalDownConverter &) = delete;
+    ~DigitalDownConverter() { sgpu_ddc_destroy(h_); }
+    sgpu_nco *nco() { return sgpu_ddc_nco(h_); }
+    size_t channels() const { return sgpu_fir_channels(sgpu_ddc_filter(h_)); }
+    bool last_fused() const { return sgpu_ddc_last_fused(h_) == 1; }
+    void reset() { detail::check(sgpu_ddc_reset(h_)); }
+    std::vector<cf32> execute_block(const std::vector<cf32> &samples) {  // channel-major [channels][n]
+        const size_t C = channels(), n = samples.size() / C;
+        const size_t cap = sgpu_ddc_out_len(h_, n);
+        std::vector<cf32> out(C * cap);
+        size_t n_out = 0;
+        detail::check(sgpu_ddc_execute_block(h_, detail::fp(samples.data()), n, n, detail::fp(out.data()), cap ? cap : 1, &n_out,
+                                             SGPU_HOST, nullptr));
+        return out;
+    }
+
+   private:
+    sgpu_ddc *h_ = nullptr;
+};
+
+}  // namespace ddc
 }  // namespace filter
+
+// ------------------------------------------------------------------------------------------------
+namespace nco {
+
+// NCO -- nco/mod.rs:26-188: `n_channels` oscillators (32-bit phase and step, 1024-entry sine table)
+class NCO {
+   public:
+    explicit NCO(size_t n_channels = 1) { detail::check(sgpu_nco_create(n_channels, &h_)); }  // ::new :36-50
+    NCO(const NCO &o) { detail::check(sgpu_nco_clone(o.h_, &h_)); }
+    NCO &operator=(const NCO &) = delete;
+    ~NCO() { sgpu_nco_destroy(h_); }
+    void reset() { detail::check(sgpu_nco_reset(h_)); }                                                          // :53
+    void set_frequency(double delta_theta, size_t ch = SGPU_ALL_CHANNELS) { detail::check(sgpu_nco_set_frequency(h_, ch, delta_theta)); }  // :59
+    void adjust_frequency(double dt, size_t ch = SGPU_ALL_CHANNELS) { detail::check(sgpu_nco_adjust_frequency(h_, ch, dt)); }          // :64
+    void set_phase(double phi, size_t ch = SGPU_ALL_CHANNELS) { detail::check(sgpu_nco_set_phase(h_, ch, phi)); }                      // :79
+    void adjust_phase(double dphi, size_t ch = SGPU_ALL_CHANNELS) { detail::check(sgpu_nco_adjust_phase(h_, ch, dphi)); }              // :84
+    void step(uint64_t count = 1) { detail::check(sgpu_nco_step(h_, count)); }                                   // :93
+    size_t channels() const { return sgpu_nco_channels(h_); }
+    // the per-sample loop the reference's mix_up_block / mix_down_block intend (:141-172); channel-major [channels][n]
+    std::vector<cf32> mix_block(const std::vector<cf32> &samples, bool up) {
+        const size_t C = channels(), n = samples.size() / C;
+        std::vector<cf32> out(samples.size());
+        detail::check(sgpu_nco_mix_block(h_, up ? 1 : 0, detail::fp(samples.data()), n, n, detail::fp(out.data()), n ? n : 1,
+                                         SGPU_HOST, nullptr));
+        return out;
+    }
+    std::vector<cf32> mix_up_block(const std::vector<cf32> &x) { return mix_block(x, true); }
+    std::vector<cf32> mix_down_block(const std::vector<cf32> &x) { return mix_block(x, false); }
+
+   private:
+    sgpu_nco *h_ = nullptr;
+};
+
+}  // namespace nco
+
+// ------------------------------------------------------------------------------------------------
+namespace multi_gpu {
+
+// Every GPU of the box behind ONE filter object and one caller thread (host buffers): sgpu_ctx_* / sgpu_sharded_*.
+class Context {
+   public:
+    explicit Context(int n_gpus = 0) { detail::check(sgpu_ctx_create(n_gpus, &h_)); }          // 0 = every visible GPU
+    explicit Context(const std::vector<int> &devices) {                                        // a device may repeat
+        detail::check(sgpu_ctx_create_devices(devices.data(), (int)devices.size(), &h_));
+    }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    ~Context() { sgpu_ctx_destroy(h_); }
+    int devices() const { return sgpu_ctx_devices(h_); }
+    sgpu_ctx *handle() { return h_; }
+
+   private:
+    sgpu_ctx *h_ = nullptr;
+};
+
+class ShardedFilter {
+   public:
+    // FIRFilter / DecimatingFIRFilter (decimation = 0: plain FIR) over the context's GPUs
+    static ShardedFilter fir(Context &ctx, const std::vector<double> &taps, double scale, size_t decimation, size_t n_channels) {
+        ShardedFilter f;
+        filter::fir::detail_fir::check_ctor(sgpu_ctx_fir_create(ctx.handle(), taps.data(), taps.size(), SGPU_TAPS_REAL, n_channels,
+                                                                scale, 0.0, decimation ? 1 : 0, decimation, &f.h_));
+        f.C_ = n_channels;
+        return f;
+    }
+    static ShardedFilter interp(Context &ctx, const std::vector<double> &taps, size_t interpolation, size_t n_channels) {
+        ShardedFilter f;
+        filter::fir::detail_fir::check_ctor(sgpu_ctx_interp_create(ctx.handle(), taps.data(), taps.size(), SGPU_TAPS_REAL, n_channels,
+                                                                   interpolation, &f.h_));
+        f.C_ = n_channels;
+        return f;
+    }
+    ShardedFilter(ShardedFilter &&o) noexcept : h_(o.h_), C_(o.C_) { o.h_ = nullptr; }
+    ShardedFilter(const ShardedFilter &) = delete;
+    ShardedFilter &operator=(const ShardedFilter &) = delete;
+    ~ShardedFilter() { if (h_) sgpu_sharded_destroy(h_); }
+    int shards() const { return sgpu_sharded_shards(h_); }
+    int last_segments() const { return sgpu_sharded_last_segments(h_); }
+    void reset() { detail::check(sgpu_sharded_reset(h_)); }
+    std::vector<cf32> execute_block(const std::vector<cf32> &samples) {  // Filter::execute_block, channel-major
+        const size_t n = samples.size() / C_;
+        const size_t cap = sgpu_sharded_out_len(h_, n);
+        std::vector<cf32> out(C_ * cap);
+        size_t n_out = 0;
+        detail::check(sgpu_sharded_execute_block(h_, detail::fp(samples.data()), n, n, detail::fp(out.data()), cap ? cap : 1, &n_out));
+        return out;
+    }
+
+   private:
+    ShardedFilter() = default;
+    sgpu_sharded *h_ = nullptr;
+    size_t C_ = 1;
+};
+
+}  // namespace multi_gpu
 }  // namespace solid

@@ -20,6 +20,12 @@ void so_autocorr_fast(size_t window_size, size_t delay, const double *hist, size
                       double *out);
 int so_firdes_kaiser(size_t len, double fc, double as, double mu, double *h);
 int so_pll_active_lag(double w, double zeta, double k, double *num, double *den);
+typedef struct so_nco so_nco;
+so_nco *so_nco_new(void);
+void so_nco_free(so_nco *n);
+void so_nco_set_frequency(so_nco *n, double dt);
+void so_nco_set_phase(so_nco *n, double phi);
+void so_nco_mix_block(so_nco *n, int up, const double *x, size_t len, double *out);
 }
 
 using namespace solid;
@@ -185,6 +191,96 @@ int main() {
         std::vector<double> ref(2 * n);
         so_autocorr_fast(48, 16, nullptr, 0, xd.data(), n, ref.data());
         EXPECT(nerr(y, ref, n) <= TOL, "AutoCorrelator(48, 16) vs oracle");
+    }
+    // round-2 additions of the ABI through the compiled mirror: per-channel taps, NCO, the fused DDC, the multi-GPU context
+    {
+        const size_t C = 5, T = 200, n = 6000;
+        std::vector<std::vector<double>> bank(C, std::vector<double>(T));
+        for (size_t c = 0; c < C; ++c) {
+            so_firdes_kaiser(T, 0.05 + 0.08 * (double)c, 60.0, 0.0, bank[c].data());
+            bank[c] = f32round(bank[c]);
+        }
+        auto x = rand_cf32(gen, C * n);
+        FIRFilter f(solid::filter::fir::per_channel, bank, 0.5);
+        auto y = f.execute_block(x);
+        DecimatingFIRFilter d(solid::filter::fir::per_channel, bank, 0.5, 4);
+        auto yd = d.execute_block(x);
+        double worst = 0, worst_d = 0;
+        for (size_t c = 0; c < C; ++c) {
+            std::vector<cf32> xc(x.begin() + c * n, x.begin() + (c + 1) * n), yc(y.begin() + c * n, y.begin() + (c + 1) * n);
+            std::vector<cf32> ydc(yd.begin() + c * (n / 4), yd.begin() + (c + 1) * (n / 4));
+            auto xd = widen(xc);
+            std::vector<double> ref(2 * n + 2);
+            so_fir_fast(bank[c].data(), T, 0, 0.5, 0.0, 0, 0, nullptr, xd.data(), n, ref.data());
+            worst = std::max(worst, nerr(yc, ref, n));
+            const size_t m = so_fir_fast(bank[c].data(), T, 0, 0.5, 0.0, 4, 0, nullptr, xd.data(), n, ref.data());
+            EXPECT(m == n / 4, "per-channel decimator output count");
+            worst_d = std::max(worst_d, nerr(ydc, ref, m));
+        }
+        EXPECT(worst <= TOL && worst_d <= TOL, "per-channel taps (FIR, decimator) vs one oracle object per channel");
+    }
+    {
+        using solid::filter::ddc::DigitalDownConverter;
+        using solid::nco::NCO;
+        const size_t C = 3, T = 256, M = 8, n = 40000;
+        std::vector<double> h(T);
+        so_firdes_kaiser(T, 0.5 / 8 * 0.9, 80.0, 0.0, h.data());
+        h = f32round(h);
+        auto x = rand_cf32(gen, C * n);
+        NCO osc(C);
+        osc.set_frequency(0.1234);
+        osc.set_phase(1.0, 2);
+        auto mixed = osc.mix_down_block(x);
+        DigitalDownConverter ddc(h, 1.0, M, 0.1234, C);
+        sgpu_nco_set_phase(ddc.nco(), 2, 1.0);
+        auto y = ddc.execute_block(x);
+        EXPECT(ddc.last_fused(), "DDC took the fused kernel");
+        double worst_mix = 0, worst = 0;
+        for (size_t c = 0; c < C; ++c) {
+            so_nco *o = so_nco_new();
+            so_nco_set_frequency(o, 0.1234);
+            if (c == 2) so_nco_set_phase(o, 1.0);
+            std::vector<cf32> xc(x.begin() + c * n, x.begin() + (c + 1) * n), mc(mixed.begin() + c * n, mixed.begin() + (c + 1) * n);
+            std::vector<cf32> yc(y.begin() + c * (n / M), y.begin() + (c + 1) * (n / M));
+            auto xd = widen(xc);
+            std::vector<double> md(2 * n), ref(2 * n + 2);
+            so_nco_mix_block(o, 0, xd.data(), n, md.data());
+            so_nco_free(o);
+            worst_mix = std::max(worst_mix, nerr(mc, md, n));
+            const size_t m = so_fir_fast(h.data(), T, 0, 1.0, 0.0, M, 0, nullptr, md.data(), n, ref.data());
+            worst = std::max(worst, nerr(yc, ref, m));
+        }
+        EXPECT(worst_mix <= TOL, "NCO mix_down block vs oracle (nco/mod.rs:147-151)");
+        EXPECT(worst <= TOL, "fused DDC vs oracle mix_down -> decimator");
+    }
+    {
+        using solid::multi_gpu::Context;
+        using solid::multi_gpu::ShardedFilter;
+        Context ctx(std::vector<int>{0, 0, 0});  // three shards on this GPU: the code path of three GPUs
+        EXPECT(ctx.devices() == 3, "context of three shards");
+        const size_t T = 300, n = 400000;
+        std::vector<double> h(T);
+        so_firdes_kaiser(T, 0.1, 70.0, 0.0, h.data());
+        h = f32round(h);
+        auto x = rand_cf32(gen, n);
+        auto f = ShardedFilter::fir(ctx, h, 1.0, 0, 1);  // ONE stream cut into time segments, halo sliced from the host buffer
+        auto y = f.execute_block(x);
+        auto xd = widen(x);
+        std::vector<double> ref(2 * n + 2);
+        so_fir_fast(h.data(), T, 0, 1.0, 0.0, 0, 0, nullptr, xd.data(), n, ref.data());
+        EXPECT(f.last_segments() == 3 && nerr(y, ref, n) <= TOL, "one FIR stream over three shards vs oracle");
+        auto g = ShardedFilter::fir(ctx, h, 1.0, 5, 7);  // 7 decimator channels in contiguous ranges
+        const size_t nc = 9000;
+        auto xc = rand_cf32(gen, 7 * nc);
+        auto yc = g.execute_block(xc);
+        double worst = 0;
+        for (size_t c = 0; c < 7; ++c) {
+            std::vector<cf32> xi(xc.begin() + c * nc, xc.begin() + (c + 1) * nc), yi(yc.begin() + c * (nc / 5), yc.begin() + (c + 1) * (nc / 5));
+            auto xw = widen(xi);
+            const size_t m = so_fir_fast(h.data(), T, 0, 1.0, 0.0, 5, 0, nullptr, xw.data(), nc, ref.data());
+            worst = std::max(worst, nerr(yi, ref, m));
+        }
+        EXPECT(g.shards() == 3 && worst <= TOL, "decimator channels over three shards vs oracle");
     }
     std::printf("%s (%d failure%s), kernels launched: %llu\n", failures ? "FAILED" : "PASSED", failures,
                 failures == 1 ? "" : "s", (unsigned long long)sgpu_launch_count());
