@@ -836,13 +836,30 @@ int fir_launch_block(sgpu_fir *f, const float2 *d_in, long long n_in, long long 
             if (st) return st;                                                                \
             const long long per_block = 32LL * kR * TPWV * NWV;                               \
             dim3 grid((unsigned)((n_out + per_block - 1) / per_block), (unsigned)f->C);       \
-            kern<<<grid, NWV * 32, smem, s>>>(a);                                             \
+            if (pdl) {                                                                        \
+                cudaLaunchConfig_t cfg{};                                                     \
+                cfg.gridDim = grid;                                                           \
+                cfg.blockDim = dim3(NWV * 32);                                                \
+                cfg.dynamicSmemBytes = smem;                                                  \
+                cfg.stream = s;                                                               \
+                cudaLaunchAttribute at[1];                                                    \
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                \
+                at[0].val.programmaticStreamSerializationAllowed = 1;                         \
+                cfg.attrs = at;                                                               \
+                cfg.numAttrs = 1;                                                             \
+                SGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, a));                                 \
+            } else {                                                                          \
+                kern<<<grid, NWV * 32, smem, s>>>(a);                                         \
+            }                                                                                 \
             done = true;                                                                      \
         }                                                                                     \
     } while (0)
         // Eight tiles per warp amortise the tap staging on long streams, but a short call (BASELINE config 1: 64 taps
         // x 2^20 samples = 64 blocks of 16384 outputs) would leave most of the chip idle: one tile per warp there.
         const bool small = (n_out + 16383) / 16384 * (long long)f->C < 4LL * f->sm_count && env_int("SGPU_FIR_SMALL", 1);
+        // short calls are bounded by the launch-to-launch floor of a stream (6.4 us per dependent kernel):
+        // programmatic dependent launch lets call k + 1 be scheduled and stage its taps while call k runs
+        const bool pdl = small && env_int("SGPU_FIR_PDL", 1);
         if (f->Qpad == kR) {  // <= 16 taps: single tap chunk
             if (small) LAUNCH_FWARP(4, 4, 1, true, 1);
             else LAUNCH_FWARP(4, 4, 1, true, 8);

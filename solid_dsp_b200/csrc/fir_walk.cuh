@@ -342,13 +342,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) fir_warp_kernel(const FirArgs a
     const int stage_f4 = max((R / 2) * RS + 1, 32 * (R / 2 + 1));  // room for the output transpose
     float *taps_s = reinterpret_cast<float *>(smem + (size_t)NW * NS * stage_f4);
     const int ch = blockIdx.y;
-    hist_tail_update(a, ch, tid, NW * 32);
+    // Programmatic dependent launch (short calls, csrc/fir.cu): the next call on the stream may be scheduled while this
+    // one still runs; everything up to griddepcontrol.wait touches only the handle's constant tap image, so a call's
+    // launch latency and tap staging hide behind its predecessor.  Both instructions are no-ops on an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     {
         const int n4 = (Qpad + kTapSkew) / 4;
         const float4 *src = reinterpret_cast<const float4 *>(a.taps + (long long)ch * a.tap_stride);
         float4 *dst = reinterpret_cast<float4 *>(taps_s);
         for (int i = tid; i < n4; i += NW * 32) dst[i] = src[i];
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor has completed: its history and outputs are visible
+    hist_tail_update(a, ch, tid, NW * 32);
     __syncthreads();
     const float2 *__restrict__ x = a.in + (long long)ch * a.in_stride;
     float4 *stage0 = smem + (size_t)warp * NS * stage_f4;
