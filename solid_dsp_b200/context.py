@@ -49,8 +49,10 @@ class ShardedFilter:
     def reset(self):
         check(lib.sgpu_sharded_reset(self._h))
 
-    def execute_block(self, samples):
-        """Filter::execute_block (filter/mod.rs:14): numpy complex64 [n] or [C, n] in host memory."""
+    def execute_block(self, samples, out=None):
+        """Filter::execute_block (filter/mod.rs:14): numpy complex64 [n] or [C, n] in host memory.  `out`: an optional
+        complex64 array [C, >= n_out] to receive the outputs (e.g. a PinnedArray's: the copies then run at the PCIe rate;
+        a fresh pageable array, like the reference's `Vec`, costs the driver's staged copies)."""
         a = np.asarray(samples)
         squeeze = a.ndim <= 1
         a = np.ascontiguousarray(np.atleast_2d(a), dtype=np.complex64)
@@ -58,9 +60,14 @@ class ShardedFilter:
             raise ValueError(f"expected {self._C} channels, got {a.shape[0]}")
         n = a.shape[1]
         n_out = self.out_len(n)
-        out = np.zeros((self._C, max(n_out, 1)), dtype=np.complex64)
+        if out is None:
+            out = np.zeros((self._C, max(n_out, 1)), dtype=np.complex64)
+        else:
+            out = np.atleast_2d(out)
+            if out.dtype != np.complex64 or out.shape[0] != self._C or out.shape[1] < max(n_out, 1) or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous complex64 array [channels, >= n_out]")
         got = _ffi.c_size()
-        check(lib.sgpu_sharded_execute_block(self._h, a.ctypes.data, n, max(n, 1), out.ctypes.data, max(n_out, 1), C.byref(got)))
+        check(lib.sgpu_sharded_execute_block(self._h, a.ctypes.data, n, max(n, 1), out.ctypes.data, out.shape[1], C.byref(got)))
         assert got.value == n_out
         r = out[:, :n_out]
         return r[0] if squeeze else r
