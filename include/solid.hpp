@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "solid_gpu.h"
+#include "solid_host.hpp"  // Window<T>, CircularBuffer<T>: host-only types of the same path
 
 namespace solid {
 
