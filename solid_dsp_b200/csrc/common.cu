@@ -1,7 +1,9 @@
 // Library-level entry points: errors, device probe, launch counter, sharding arithmetic.
 #include <sched.h>
 
+#include <algorithm>
 #include <cctype>
+#include <thread>
 
 #include "sgpu_common.cuh"
 
@@ -96,7 +98,35 @@ int HostPipe::ensure(size_t need_in, size_t need_out) {
     return SGPU_OK;
 }
 
+int HostPipe::ensure_staging(size_t need_in, size_t need_out) {
+    if (need_in > h_in_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (h_in[i]) cudaFreeHost(h_in[i]);
+            h_in[i] = nullptr;
+        }
+        h_in_bytes = 0;
+        for (int i = 0; i < 2; ++i) SGPU_CUDA(cudaHostAlloc(&h_in[i], need_in, cudaHostAllocDefault));
+        h_in_bytes = need_in;
+    }
+    if (need_out > h_out_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (h_out[i]) cudaFreeHost(h_out[i]);
+            h_out[i] = nullptr;
+        }
+        h_out_bytes = 0;
+        for (int i = 0; i < 2; ++i) SGPU_CUDA(cudaHostAlloc(&h_out[i], need_out, cudaHostAllocDefault));
+        h_out_bytes = need_out;
+    }
+    return SGPU_OK;
+}
+
 void HostPipe::release() {
+    for (int i = 0; i < 2; ++i) {
+        if (h_in[i]) cudaFreeHost(h_in[i]);
+        if (h_out[i]) cudaFreeHost(h_out[i]);
+        h_in[i] = h_out[i] = nullptr;
+    }
+    h_in_bytes = h_out_bytes = 0;
     for (int i = 0; i < 2; ++i) {
         if (d_in[i]) cudaFree(d_in[i]);
         if (d_out[i]) cudaFree(d_out[i]);
@@ -110,6 +140,52 @@ void HostPipe::release() {
     if (s_out) cudaStreamDestroy(s_out);
     s_in = s_out = nullptr;
     in_bytes = out_bytes = 0;
+}
+
+bool host_staging_enabled() {
+    const char *e = getenv("SGPU_HOST_STAGING");
+    return e ? atoi(e) != 0 : false;  // off until measured on the GPU box (tests/test_host_staging_gpu.py switches it on)
+}
+
+bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void par_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows) {
+    const size_t total = width * rows;
+    if (total == 0) return;
+    // bytes [lo, hi) of the rows x width index space
+    auto copy_range = [=](size_t lo, size_t hi) {
+        size_t r = lo / width, off = lo - r * width;
+        while (lo < hi) {
+            const size_t n = std::min(width - off, hi - lo);
+            memcpy(static_cast<char *>(dst) + r * dst_pitch + off, static_cast<const char *>(src) + r * src_pitch + off, n);
+            lo += n;
+            ++r;
+            off = 0;
+        }
+    };
+    unsigned hc = std::thread::hardware_concurrency();
+    size_t nt = total < ((size_t)4 << 20) ? 1 : std::min<size_t>(8, std::max<unsigned>(1, hc / 2));
+    if (const char *e = getenv("SGPU_HOST_COPY_THREADS")) nt = std::max(1, atoi(e));
+    if (nt <= 1) {
+        copy_range(0, total);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    const size_t per = (total + nt - 1) / nt;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t lo = std::min(total, t * per), hi = std::min(total, (t + 1) * per);
+        if (lo < hi) th.emplace_back(copy_range, lo, hi);
+    }
+    copy_range(0, std::min(total, per));
+    for (auto &x : th) x.join();
 }
 
 size_t host_chunk_len(size_t C, size_t n_in) {
