@@ -21,7 +21,8 @@ x = np.empty(n, dtype=np.complex64)
 for a in range(0, n, 1 << 22):
     x[a:a + (1 << 22)] = (rng.uniform(-1, 1, 1 << 22) + 1j * rng.uniform(-1, 1, 1 << 22)).astype(np.complex64)
 for label, staging, env in (("driver-staged copies", "0", None), ("library staging, host threads", "1", None),
-                            ("library staging, 1 thread", "1", "1")):
+                            ("library staging, 1 thread", "1", "1"), ("library staging, 16 threads", "1", "16"),
+                            ("library staging, 4 threads", "1", "4")):
     os.environ["SGPU_HOST_STAGING"] = staging
     if env:
         os.environ["SGPU_HOST_COPY_THREADS"] = env
