@@ -31,3 +31,30 @@ def test_cpp_mirror_parity():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASSED" in r.stdout
+
+
+def _build_c_example():
+    root = CPP.parent.parent
+    out = CPP / "_build" / "fir_stream"
+    (CPP / "_build").mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", f"-I{root / 'include'}", str(root / "examples" / "c" / "fir_stream.c"),
+                    f"-L{root / 'solid_dsp_b200' / 'lib'}", "-lsolid_gpu", "-lm",
+                    f"-Wl,-rpath,{root / 'solid_dsp_b200' / 'lib'}", "-o", str(out)], check=True, capture_output=True)
+    return out
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu():
+    """examples/c/fir_stream.c: a plain C caller of include/solid_gpu.h (the header is C, not only C++).  Without a GPU
+    the first call returns SGPU_ERR_NO_DEVICE -- there is no CPU fallback."""
+    import torch
+    exe = _build_c_example()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_c_example_runs")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "SGPU_ERR_NO_DEVICE" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs():
+    r = subprocess.run([str(_build_c_example())], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
