@@ -501,6 +501,7 @@ fir_tc_one_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     using F = Fmt<F16, CT>;
     constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // fir_tc_post_kernel may be scheduled behind this grid now (it waits for its completion)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + NS * F::kStage;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -707,6 +708,7 @@ fir_tc_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using F = Fmt<F16, CT>;
     constexpr int NS = F::kNStages;
     extern __shared__ uint8_t smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // fir_tc_post_kernel may be scheduled behind this grid now (it waits for its completion)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + NS * F::kStage;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -970,6 +972,7 @@ fir_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using F = Fmt<true, false>;
     constexpr int kAStage = F::kA;  // 16 KB: f1 and f2 of 128 x 32 taps
     extern __shared__ uint8_t smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // fir_tc_post_kernel may be scheduled behind this grid now (it waits for its completion)
     const uint32_t base = (smem_u32(smem_raw) + 511u) & ~511u;
     auto strip = [&](int c, int part) { return base + (uint32_t)(2 * c + part) * (uint32_t)g.strip_bytes; };
     const uint32_t abase = base + 8u * (uint32_t)g.strip_bytes;
@@ -1251,6 +1254,9 @@ struct TcPostArgs {
 };
 
 __global__ void __launch_bounds__(256) fir_tc_post_kernel(const TcPostArgs a) {
+    // launched with programmatic stream serialization: the launch latency hides behind the tensor kernel, the work starts
+    // when that grid has completed and its flags and outputs are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if ((int)blockIdx.x >= a.fix_blocks) {
         const long long i = (long long)(blockIdx.x - a.fix_blocks) * 256 + threadIdx.x;
         if (i >= a.hist_total) return;
@@ -1795,7 +1801,18 @@ int fir_tc_run(FirTcState *st, const float2 *in, long long n_in, long long in_st
     p.scale = scale;
     p.scale_im = scale_im;
     const long long hist_blocks = (p.hist_total + 255) / 256;
-    fir_tc_post_kernel<<<(unsigned)(p.fix_blocks + hist_blocks), 256, 0, s>>>(p);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(p.fix_blocks + hist_blocks));
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = env_i("SGPU_FIR_TC_PDL", 1) ? 1 : 0;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SGPU_CUDA(cudaLaunchKernelEx(&cfg, fir_tc_post_kernel, p));
+    }
     SGPU_LAUNCH_CHECK();
     count_launch();
     return SGPU_OK;
