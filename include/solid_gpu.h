@@ -25,7 +25,11 @@
  *     handle's device, work is enqueued on `stream` (a cudaStream_t, NULL = default stream)
  *     and the call returns without synchronising.  SGPU_HOST: pageable or pinned host
  *     memory; the call stages through device buffers owned by the handle and returns after
- *     the result is in `out`.
+ *     the result is in `out`.  Pinned buffers (sgpu_host_alloc, cudaHostAlloc, cudaHostRegister)
+ *     are copied directly at the PCIe rate; pageable buffers of 4 MiB or more go through pinned
+ *     staging buffers of the handle, filled and drained by host threads while the neighbouring
+ *     chunk is on the bus (SGPU_HOST_STAGING=0: the driver's own staged copies).  `in` and
+ *     `out` must not overlap.
  *   - A handle is one logical stream of calls (like `&mut self`): not thread-safe per
  *     handle; distinct handles may be used from distinct threads.
  *   - No CPU fallback exists: without a usable sm_100 device every create returns
